@@ -1,0 +1,221 @@
+/*
+ * rampvo_b200.h — C-ABI of librampvo_b200.so
+ *
+ * B200 (sm_100a) implementation of the RAMP-VO per-frame recurrent-update hot path
+ * (uzh-rpg/rampvo): altcorr patch gather + patch<->frame correlation lookup, the
+ * projective transform, the fastba Gauss-Newton / Schur bundle adjustment over the
+ * patch graph, the patch-graph bookkeeping (neighbors, group plans) and the update
+ * operator's non-GEMM stages.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the function name ends in `_host`;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), except
+ *     the `_host` variants which copy in, run, copy out and synchronise `stream`;
+ *   - index arrays (ii, jj, kk, ix, jx) are int64, like the reference's `long` accessors;
+ *   - return value 0 = success; non-zero = error, message via rvo_last_error();
+ *     nothing ever calls exit()/abort() (the reference exit(1)s at block_e.cu:20-26,
+ *     ba.cpp:151-152 — SURVEY.md §5);
+ *   - poses are rows [tx,ty,tz,qx,qy,qz,qw] (ramp/lietorch/groups.py:273), world->camera.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference checkout, uzh-rpg/rampvo @ 9353aaa).
+ */
+#ifndef RAMPVO_B200_H
+#define RAMPVO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVO_ABI_VERSION 1
+
+/* element types of feature tensors */
+enum { RVO_F16 = 0, RVO_F32 = 1 };
+
+/* error codes */
+enum {
+  RVO_OK = 0,
+  RVO_ERR_ARG = 1,      /* bad argument (shape / dtype / alignment / null pointer) */
+  RVO_ERR_CUDA = 2,     /* a CUDA runtime call failed */
+  RVO_ERR_WORKSPACE = 3 /* workspace too small */
+};
+
+int rvo_abi_version(void);
+const char* rvo_last_error(void);
+/* compute capability of the current device as major*10+minor (100 on B200); <0 on error */
+int rvo_device_cc(void);
+
+/* A strided view of a 4-D feature tensor, logical dims [N, C, H, W], strides in ELEMENTS.
+ * Channels-last storage (sC == 1) selects the tensor-core fast path of rvo_corr_*. */
+typedef struct {
+  const void* data;
+  int32_t dtype;           /* RVO_F16 / RVO_F32 */
+  int32_t N, C, H, W;
+  int64_t sN, sC, sH, sW;
+} rvo_fmap_t;
+
+/* ------------------------------------------------------------------ altcorr ---- */
+
+/* cuda_corr.patchify_forward (ramp/altcorr/correlation.cpp:47, kernel
+ * correlation_kernel.cu:17-47): patches[b,m,c,a,b'] = net[b,c,floor(y)+a-R,floor(x)+b'-R],
+ * D = 2R+2, zero outside the map.  `net` is the [B,C,H,W] view (N == B); coords [B,M,2] f32
+ * (x,y); out is a dense [B,M,C,D,D] tensor of net's dtype. Bit-exact gather. */
+int rvo_patchify_forward(const rvo_fmap_t* net, const float* coords, int M, int radius,
+                         void* out, void* stream);
+
+/* altcorr.patchify(..., mode='bilinear') (ramp/altcorr/correlation.py:51-68): gather + 4-corner
+ * blend fused, evaluated in fp32 with the reference's operation order
+ * ((1-dy)*(1-dx))*P[a,b] + ((1-dy)*dx)*P[a,b+1] + (dy*(1-dx))*P[a+1,b] + (dy*dx)*P[a+1,b+1].
+ * out dims [B,M,C,d,d], d = 2R+1, with caller-given element strides (so the gmap ring can be
+ * written patch-pixel-major / channels-last); out_dtype RVO_F16 (rounded once) or RVO_F32. */
+int rvo_patchify_bilinear(const rvo_fmap_t* net, const float* coords, int M, int radius,
+                          void* out, int out_dtype, int64_t oB, int64_t oM, int64_t oC,
+                          int64_t oH, int64_t oW, void* stream);
+
+/* cuda_corr.forward (ramp/altcorr/correlation.cpp:27, kernel correlation_kernel.cu:83-136 plus the
+ * host-side bilinear blend and permute at :221-232).
+ *   fmap1: patch features, logical [Np, C, P, P] (N=Np, H=W=P)
+ *   fmap2: frame features, logical [Nf, C, H2, W2]
+ *   coords [E,2,P,P] f32 (x plane then y plane), ii[e] -> patch, jj[e] -> frame
+ *   out    [E, 2R+1 (x offset), 2R+1 (y offset), P, P] of fmap1's dtype
+ * fp32 accumulation and fp32 blend (the reference accumulates in the feature dtype). */
+int rvo_corr_forward(const rvo_fmap_t* fmap1, const rvo_fmap_t* fmap2, const float* coords,
+                     const int64_t* ii, const int64_t* jj, int E, int radius, void* out,
+                     void* stream);
+
+/* Ramp_vo.corr (ramp/Ramp_vo.py:175-182): both pyramid levels in ONE launch.
+ *   level l reads pyr[l] at coords * scale[l]  (scale = 1, 0.25 on the hot path)
+ *   patch index = kk[e] % pmod, frame index = jj[e] % fmod (ring buffers; pass 0 for no modulo)
+ *   out [E, 7,7,P,P, nlevels] flattened to [E, 49*P*P*nlevels] (= 882) of fmap1's dtype. */
+int rvo_corr_pyramid(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const float* scale,
+                     int nlevels, const float* coords, const int64_t* kk, const int64_t* jj,
+                     int64_t pmod, int64_t fmod, int E, int radius, void* out, void* stream);
+
+/* Host-buffer variant of rvo_corr_pyramid: every pointer (also inside the rvo_fmap_t views) is
+ * HOST memory; copies in, launches, copies the [E,882] result back, synchronises. */
+int rvo_corr_pyramid_host(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const float* scale,
+                          int nlevels, const float* coords, const int64_t* kk, const int64_t* jj,
+                          int64_t pmod, int64_t fmod, int E, int radius, void* out, void* stream);
+
+/* ------------------------------------------------------- projective_ops -------- */
+
+/* flags for rvo_transform */
+enum { RVO_TF_TONLY = 1, RVO_TF_NOCLAMP = 2 };
+
+/* pops.transform (ramp/projective_ops.py:50-101) fused into one kernel: iproj (:16-26),
+ * Gij = T_j * T_i^-1 (lietorch se3.h:36-47), act4 (se3.h:53-56), proj with Z clamped at 0.1
+ * (:29-47).
+ *   poses [*,7], patches [*,3,P,P], intrinsics [*,4]; ii/jj/kk [E]
+ *   coords_pp  [E,P,P,2]  (pops.transform layout) or NULL
+ *   coords_cf  [E,2,P,P]  (Ramp_vo.reproject layout, Ramp_vo.py:192) or NULL
+ *   depth_out  [E,P,P]    (the d of proj(depth=True)) or NULL
+ *   valid_out  [E,P,P]    ((Z > 0.2) as float, `valid=True`) or NULL
+ * RVO_TF_TONLY zeroes the rotation of Gij (flow_mag, :113); RVO_TF_NOCLAMP gives the un-clamped
+ * projection of cuda_ba.reproject (ramp/fastba/ba_cuda.cu:379-429) with intrinsics[0] for
+ * every frame. */
+int rvo_transform(const float* poses, const float* patches, const float* intrinsics,
+                  const int64_t* ii, const int64_t* jj, const int64_t* kk, int E, int P,
+                  int flags, float* coords_pp, float* coords_cf, float* depth_out,
+                  float* valid_out, void* stream);
+
+/* pops.transform(jacobian=True) (ramp/projective_ops.py:68-96): additionally the centre-pixel
+ * Jacobians Ji [E,2,6], Jj [E,2,6], Jz [E,2,1] and valid [E] = (Z > 0.2). */
+int rvo_transform_jac(const float* poses, const float* patches, const float* intrinsics,
+                      const int64_t* ii, const int64_t* jj, const int64_t* kk, int E, int P,
+                      float* coords_pp, float* valid, float* Ji, float* Jj, float* Jz,
+                      void* stream);
+
+/* cuda_ba.reproject (ramp/fastba/ba.cpp:49-57, kernel ba_cuda.cu:379-429): coords [E,2,P,P]. */
+int rvo_reproject(const float* poses, const float* patches, const float* intrinsics,
+                  const int64_t* ii, const int64_t* jj, const int64_t* kk, int E, int P,
+                  float* coords, void* stream);
+
+/* pops.point_cloud (ramp/projective_ops.py:103-105) restricted to what Ramp_vo.update uses
+ * (Ramp_vo.py:308-310): centre pixel, X/W normalised: points [m,3]. ix[k] = frame of patch k. */
+int rvo_point_cloud(const float* poses, const float* patches, const float* intrinsics,
+                    const int64_t* ix, int m, int P, float* points, void* stream);
+
+/* pops.flow_mag (ramp/projective_ops.py:108-118): per edge, per patch pixel
+ * beta*|x(i->j) - x(i->i)| + (1-beta)*|x_tonly(i->j) - x(i->i)|; out [E,P,P]. */
+int rvo_flow_mag(const float* poses, const float* patches, const float* intrinsics,
+                 const int64_t* ii, const int64_t* jj, const int64_t* kk, int E, int P,
+                 float beta, float* out, void* stream);
+
+/* ------------------------------------------------------------- patch-graph plan -- */
+
+/* The bookkeeping the reference redoes with torch::_unique + host loops in every call
+ * (ramp/fastba/ba.cpp:62-95 for neighbors, ramp/fastba/ba_cuda.cu:447-449 for the compact patch
+ * numbering kx/ku, ramp/blocks.py:43 for the SoftAgg groups) is computed ONCE per graph, on the
+ * device, with no host synchronisation: edges are sorted by (kk, jj, edge id) so that every
+ * patch owns one contiguous segment.
+ *   kmax / jmax: exclusive upper bounds on the values in kk / jj (sizes of the patch and pose
+ *   tables); 0 = unknown (kk < 2^42, jj < 2^21 assumed).  Values must be non-negative.
+ *   plan: caller-owned device buffer of rvo_plan_bytes(E) bytes. */
+int64_t rvo_plan_bytes(int E);
+int rvo_graph_plan(const int64_t* kk, const int64_t* jj, int E, int64_t kmax, int64_t jmax,
+                   void* plan, int64_t plan_bytes, void* stream);
+/* device pointers into a plan: count[0] = number of distinct patches U; perm[E] = edge ids in
+ * sorted order; seg_of[E] = compact patch id of each sorted position (the reference's `ku`,
+ * permuted); seg_start[U+1]; kx[U] = sorted distinct patch ids.  Any out pointer may be NULL. */
+int rvo_plan_groups(const void* plan, int E, const int32_t** count, const int32_t** perm,
+                    const int32_t** seg_of, const int32_t** seg_start, const int64_t** kx);
+
+/* ------------------------------------------------------------------ fastba ------ */
+
+/* cuda_ba.neighbors (ramp/fastba/ba.cpp:59-97) entirely on the device (the reference round-trips
+ * through the CPU): group edges by kk, order each group by jj ascending (stable in edge index);
+ * ix[e] = previous edge in that order or -1, jx[e] = next or -1.  Bit-exact.
+ * rvo_neighbors builds a plan in `ws` (rvo_neighbors_ws_bytes(E) bytes) and links it;
+ * rvo_plan_neighbors reuses an existing plan. */
+int64_t rvo_neighbors_ws_bytes(int E);
+int rvo_neighbors(const int64_t* kk, const int64_t* jj, int E, int64_t kmax, int64_t jmax,
+                  int64_t* ix, int64_t* jx, void* ws, int64_t ws_bytes, void* stream);
+int rvo_plan_neighbors(const void* plan, int E, int64_t* ix, int64_t* jx, void* stream);
+
+/* cuda_ba.forward (ramp/fastba/ba.cpp:32-46 -> cuda_ba, ba_cuda.cu:433-582): `iterations`
+ * Gauss-Newton steps with the patch (inverse-depth) block eliminated by a Schur complement;
+ * updates poses[t0..t1) and the depths of every patch referenced by kk IN PLACE.
+ *   poses [n_poses,7], patches [n_patches,3,P,P], intrinsics [*,4] (row 0 used, ba_cuda.cu:254-258)
+ *   target [E,2], weight [E,2], lmbda [1] (device scalar), ii/jj/kk [E]
+ *   PPF / eff_impl are accepted for signature parity: E is always kept block-sparse (one dense
+ *   6N-row per patch, never the 6N x M matrix), so both settings give the same result.
+ *   Frames outside [t0,t1) are fixed (the reference only guards the lower end, ba_cuda.cu:338-345).
+ * ws: workspace of rvo_ba_ws_bytes(E, n_patches, t1-t0) bytes; it begins with the graph plan. */
+int64_t rvo_ba_ws_bytes(int E, int64_t n_patches, int n_free);
+int rvo_ba_forward(float* poses, float* patches, const float* intrinsics, const float* target,
+                   const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
+                   const int64_t* kk, int E, int64_t n_poses, int64_t n_patches, int P, int PPF,
+                   int t0, int t1, int iterations, int eff_impl, void* ws, int64_t ws_bytes,
+                   void* stream);
+
+/* One Gauss-Newton iteration in three steps, split where a patch graph sharded by source frame
+ * needs its all-reduce:
+ *   rvo_ba_plan      once per graph: sort / group the edges into `ws`;
+ *   rvo_ba_assemble  local edges -> reduced camera system [S | y], row-major [6n, 6n+1], n = t1-t0,
+ *                    BEFORE damping, full symmetric S.  Sy == NULL keeps it inside ws.  Per-patch
+ *                    Q, u and E rows stay in ws for the back substitution;
+ *   (the caller sums Sy over ranks — NCCL all-reduce)
+ *   rvo_ba_solve     damping S += I*(1e-4*S+1), Cholesky, pose retraction T <- Exp(dX) T, local
+ *                    depth back substitution dZ = Q (u - E^T dX) and depth retraction. */
+int rvo_ba_plan(const int64_t* kk, const int64_t* jj, int E, int64_t n_poses, int64_t n_patches,
+                int n_free, void* ws, int64_t ws_bytes, void* stream);
+int rvo_ba_assemble(const float* poses, const float* patches, const float* intrinsics,
+                    const float* target, const float* weight, const float* lmbda,
+                    const int64_t* ii, const int64_t* jj, int E, int64_t n_patches, int P, int t0,
+                    int t1, float* Sy, void* ws, int64_t ws_bytes, void* stream);
+int rvo_ba_solve(float* poses, float* patches, const float* Sy, int E, int64_t n_patches, int P,
+                 int t0, int t1, void* ws, int64_t ws_bytes, void* stream);
+
+/* Host-buffer variant of rvo_ba_forward (all pointers HOST; poses/patches copied back). */
+int rvo_ba_forward_host(float* poses, float* patches, const float* intrinsics, const float* target,
+                        const float* weight, const float* lmbda, const int64_t* ii,
+                        const int64_t* jj, const int64_t* kk, int E, int64_t n_poses,
+                        int64_t n_patches, int P, int PPF, int t0, int t1, int iterations,
+                        int eff_impl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAMPVO_B200_H */

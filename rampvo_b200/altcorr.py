@@ -1,0 +1,133 @@
+"""Drop-in for ramp.altcorr (ramp/altcorr/correlation.py:51-74, cuda_corr ramp/altcorr/correlation.cpp:57-62).
+
+Same names, argument order and tensor layouts as the reference; the work is done by
+librampvo_b200.so (rvo_patchify_*, rvo_corr_*).  Forward only: the backward kernels belong to the
+training row and raise until that row is built.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _no_grad_inputs(*ts):
+    for t in ts:
+        if torch.is_tensor(t) and t.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError(
+                "rampvo_b200.altcorr: backward (cuda_corr.backward / patchify_backward) is not built "
+                "yet; call under torch.no_grad()")
+
+
+def patchify_forward(net, coords, radius):
+    """cuda_corr.patchify_forward: raw (2R+2)^2 gather, [B,M,C,D,D] in net's dtype, bit-exact."""
+    _lib.require_cuda(net, coords)
+    B, C, H, W = net.shape
+    M = coords.shape[1]
+    D = 2 * radius + 2
+    coords = coords.to(torch.float32).contiguous()
+    out = torch.empty(B, M, C, D, D, dtype=net.dtype, device=net.device)
+    with torch.cuda.device(net.device):
+        v = _lib.fmap_view(net)
+        _lib.check(_lib.lib().rvo_patchify_forward(ctypes.byref(v), _lib.ptr(coords), M, radius,
+                                                   _lib.ptr(out), _lib.stream_ptr()),
+                   "rvo_patchify_forward")
+    return [out]
+
+
+def patchify(net, coords, radius, mode='bilinear', out=None):
+    """ramp.altcorr.patchify (correlation.py:51-68).
+
+    net [B,C,H,W] (any strides, fp16/fp32), coords [B,M,2] (x,y).  'bilinear' returns
+    [B,M,C,2R+1,2R+1] in fp32 (the reference's fp32 offsets promote the product to fp32,
+    correlation.py:57-66); any other mode returns the raw [B,M,C,2R+2,2R+2] gather.
+    `out` (optional, extension): a preallocated fp16/fp32 tensor view of shape [B,M,C,d,d] with
+    arbitrary strides — lets the caller write straight into a channels-last ring buffer.
+    """
+    _no_grad_inputs(net)
+    if mode != 'bilinear':
+        return patchify_forward(net, coords, radius)[0]
+    _lib.require_cuda(net, coords)
+    B, C, H, W = net.shape
+    M = coords.shape[1]
+    d = 2 * radius + 1
+    coords = coords.to(torch.float32).contiguous()
+    if out is None:
+        out = torch.empty(B, M, C, d, d, dtype=torch.float32, device=net.device)
+    else:
+        assert tuple(out.shape) == (B, M, C, d, d)
+        _lib.require_cuda(out)
+    s = out.stride()
+    with torch.cuda.device(net.device):
+        v = _lib.fmap_view(net)
+        _lib.check(_lib.lib().rvo_patchify_bilinear(ctypes.byref(v), _lib.ptr(coords), M, radius,
+                                                    _lib.ptr(out), _lib.dtype_code(out), s[0], s[1],
+                                                    s[2], s[3], s[4], _lib.stream_ptr()),
+                   "rvo_patchify_bilinear")
+    return out
+
+
+def _views(fmap1, fmap2):
+    if fmap1.dtype != fmap2.dtype:
+        raise RuntimeError("altcorr.corr: fmap1 and fmap2 must have the same dtype")
+    return _lib.fmap_view(fmap1), _lib.fmap_view(fmap2)
+
+
+def corr(fmap1, fmap2, coords, ii, jj, radius=1, dropout=1):
+    """ramp.altcorr.corr (correlation.py:71; cuda_corr.forward correlation_kernel.cu:193-233).
+
+    fmap1 [B,Np,C,P,P], fmap2 [B,Nf,C,H2,W2], coords [B,E,2,P,P] f32, ii/jj [E] int64 ->
+    [B,E,2R+1,2R+1,P,P] (x-offset dim first) in fmap1's dtype.  fp32 accumulation.  `dropout` only
+    affects the reference's backward pass (correlation.py:20-25) and is ignored here.
+    """
+    _no_grad_inputs(fmap1, fmap2)
+    _lib.require_cuda(fmap1, fmap2, coords, ii, jj)
+    B, E = coords.shape[0], coords.shape[1]
+    P = fmap1.shape[-1]
+    d = 2 * radius + 1
+    coords = coords.to(torch.float32).contiguous()
+    ii = ii.to(torch.int64).contiguous()
+    jj = jj.to(torch.int64).contiguous()
+    out = torch.empty(B, E, d, d, P, P, dtype=fmap1.dtype, device=fmap1.device)
+    L = _lib.lib()
+    with torch.cuda.device(fmap1.device):
+        for b in range(B):
+            v1, v2 = _views(fmap1[b], fmap2[b])
+            _lib.check(L.rvo_corr_forward(ctypes.byref(v1), ctypes.byref(v2), _lib.ptr(coords[b]),
+                                          _lib.ptr(ii), _lib.ptr(jj), E, radius, _lib.ptr(out[b]),
+                                          _lib.stream_ptr()), "rvo_corr_forward")
+    return out
+
+
+def corr_pyramid(gmap, pyramid, coords, kk, jj, pmod=0, fmod=0, radius=3, scales=None, out=None):
+    """Ramp_vo.corr (ramp/Ramp_vo.py:175-182) in one launch: every pyramid level, the bilinear blend,
+    the (x,y) permute and the level stack fused.
+
+    gmap [1,Np,C,P,P]; pyramid: list of [1,Nf,C,H_l,W_l]; coords [1,E,2,P,P]; patch index
+    kk % pmod, frame index jj % fmod (0 = no modulo).  Returns [1,E,(2R+1)^2*P*P*len(pyramid)].
+    Channels-last fp16 maps (stride(C) == 1) take the tensor-core path.
+    """
+    _lib.require_cuda(gmap, coords, kk, jj, *pyramid)
+    nl = len(pyramid)
+    if scales is None:
+        scales = [1.0, 0.25, 0.0625][:nl]
+    E = coords.shape[1]
+    P = gmap.shape[-1]
+    d = 2 * radius + 1
+    coords = coords.to(torch.float32).contiguous()
+    kk = kk.to(torch.int64).contiguous()
+    jj = jj.to(torch.int64).contiguous()
+    if out is None:
+        out = torch.empty(1, E, d * d * P * P * nl, dtype=gmap.dtype, device=gmap.device)
+    v1 = _lib.fmap_view(gmap[0])
+    arr = (_lib.FMap * nl)(*[_lib.fmap_view(p[0]) for p in pyramid])
+    for p in pyramid:
+        if p.dtype != gmap.dtype:
+            raise RuntimeError("altcorr.corr_pyramid: dtype mismatch between gmap and pyramid")
+    sc = (ctypes.c_float * nl)(*scales)
+    with torch.cuda.device(gmap.device):
+        _lib.check(_lib.lib().rvo_corr_pyramid(ctypes.byref(v1), arr, sc, nl, _lib.ptr(coords),
+                                               _lib.ptr(kk), _lib.ptr(jj), pmod, fmod, E, radius,
+                                               _lib.ptr(out), _lib.stream_ptr()),
+                   "rvo_corr_pyramid")
+    return out

@@ -1,0 +1,38 @@
+// error.cu — error reporting and device probing for librampvo_b200.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace rvo {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  cudaGetLastError();  // clear the sticky-less error so the next call starts clean
+  return RVO_ERR_CUDA;
+}
+
+}  // namespace rvo
+
+extern "C" int rvo_abi_version(void) { return RVO_ABI_VERSION; }
+
+extern "C" const char* rvo_last_error(void) { return rvo::g_err; }
+
+extern "C" int rvo_device_cc(void) {
+  int dev = 0, major = 0, minor = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return major * 10 + minor;
+}

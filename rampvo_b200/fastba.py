@@ -1,0 +1,86 @@
+"""Drop-in for ramp.fastba (ramp/fastba/ba.py:4-8, cuda_ba ramp/fastba/ba.cpp:183-188)."""
+import torch
+
+from . import _lib
+
+
+def _i64(t):
+    return t.to(torch.int64).contiguous()
+
+
+def neighbors(ii, jj, kmax=0, jmax=0):
+    """cuda_ba.neighbors(ii, jj) (ba.cpp:59-97; called as neighbors(kk, jj) at net.py:77): for each
+    edge the previous / next edge with the same first key, ordered by the second key (stable);
+    -1 at the ends.  Runs on the device — no host round trip.  kmax/jmax (optional, extension):
+    exclusive upper bounds of the two keys, which shorten the radix sort."""
+    _lib.require_cuda(ii, jj)
+    E = ii.numel()
+    ii, jj = _i64(ii), _i64(jj)
+    ix = torch.empty(E, dtype=torch.int64, device=ii.device)
+    jx = torch.empty(E, dtype=torch.int64, device=ii.device)
+    if E == 0:
+        return [ix, jx]
+    L = _lib.lib()
+    nb = L.rvo_neighbors_ws_bytes(E)
+    ws = _lib.Workspace.get(ii.device, nb, "neighbors")
+    with torch.cuda.device(ii.device):
+        _lib.check(L.rvo_neighbors(_lib.ptr(ii), _lib.ptr(jj), E, kmax, jmax, _lib.ptr(ix),
+                                   _lib.ptr(jx), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                   "rvo_neighbors")
+    return [ix, jx]
+
+
+def _flat(t, name, last):
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise RuntimeError("fastba: %s must be a contiguous float32 tensor" % name)
+    return t.view(-1, *last)
+
+
+def BA(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, M, iterations,
+       eff_impl=False):
+    """ramp.fastba.BA (ba.py:7 -> cuda_ba.forward, ba_cuda.cu:433-582).  Mutates `poses`
+    (rows t0..t1-1) and the inverse depths in `patches` IN PLACE and returns [] like the reference.
+    `poses` may be a lietorch SE3 (its .data is used, ba.py:8)."""
+    poses = getattr(poses, "data", poses)
+    _lib.require_cuda(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk)
+    P = patches.shape[-1]
+    pv = _flat(poses, "poses", (7,))
+    qv = _flat(patches, "patches", (3, P, P))
+    kv = _flat(intrinsics, "intrinsics", (4,))
+    tv = target.to(torch.float32).contiguous().view(-1, 2)
+    wv = weight.to(torch.float32).contiguous().view(-1, 2)
+    lm = lmbda.to(torch.float32).contiguous().view(-1)
+    E = ii.numel()
+    if tv.shape[0] != E or wv.shape[0] != E or jj.numel() != E or kk.numel() != E:
+        raise RuntimeError("fastba.BA: target/weight/ii/jj/kk disagree on the number of edges")
+    ii, jj, kk = _i64(ii), _i64(jj), _i64(kk)
+    L = _lib.lib()
+    n_poses, n_patches = pv.shape[0], qv.shape[0]
+    nb = L.rvo_ba_ws_bytes(E, n_patches, max(t1 - t0, 0))
+    ws = _lib.Workspace.get(pv.device, nb, "ba")
+    with torch.cuda.device(pv.device):
+        _lib.check(L.rvo_ba_forward(_lib.ptr(pv), _lib.ptr(qv), _lib.ptr(kv), _lib.ptr(tv),
+                                    _lib.ptr(wv), _lib.ptr(lm), _lib.ptr(ii), _lib.ptr(jj),
+                                    _lib.ptr(kk), E, n_poses, n_patches, P, int(M), int(t0), int(t1),
+                                    int(iterations), int(bool(eff_impl)), _lib.ptr(ws), ws.numel(),
+                                    _lib.stream_ptr()), "rvo_ba_forward")
+    return []
+
+
+def reproject(poses, patches, intrinsics, ii, jj, kk):
+    """cuda_ba.reproject (ba.cpp:49-57, ba_cuda.cu:379-429,585-617): coords [1,E,2,P,P]; no depth
+    clamp and intrinsics[0] for every frame, exactly like the reference kernel."""
+    poses = getattr(poses, "data", poses)
+    _lib.require_cuda(poses, patches, intrinsics, ii, jj, kk)
+    P = patches.shape[-1]
+    pv = _flat(poses, "poses", (7,))
+    qv = _flat(patches, "patches", (3, P, P))
+    kv = _flat(intrinsics, "intrinsics", (4,))
+    E = ii.numel()
+    ii, jj, kk = _i64(ii), _i64(jj), _i64(kk)
+    out = torch.empty(1, E, 2, P, P, dtype=torch.float32, device=pv.device)
+    with torch.cuda.device(pv.device):
+        _lib.check(_lib.lib().rvo_reproject(_lib.ptr(pv), _lib.ptr(qv), _lib.ptr(kv), _lib.ptr(ii),
+                                            _lib.ptr(jj), _lib.ptr(kk), E, P, _lib.ptr(out),
+                                            _lib.stream_ptr()), "rvo_reproject")
+    return out

@@ -1,0 +1,166 @@
+"""GPU parity: neighbors (bit-exact) and the Gauss-Newton / Schur BA vs the numpy oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ops as O
+from rampvo_b200 import _lib, fastba, synth
+from tests.util import perturb_poses, problem_tensors, rel_err, targets_from_reprojection
+
+pytestmark = pytest.mark.gpu
+
+
+def test_neighbors_bit_exact_random_and_ties():
+    rng = np.random.default_rng(0)
+    for E, nk, nj in [(1, 1, 1), (37, 5, 3), (5000, 300, 20), (45312, 2112, 40)]:
+        kk = rng.integers(0, nk, E)
+        jj = rng.integers(0, nj, E)
+        ix, jx = fastba.neighbors(torch.from_numpy(kk).cuda(), torch.from_numpy(jj).cuda())
+        ex, ey = O.neighbors(kk, jj)
+        assert (ix.cpu().numpy() == ex).all() and (jx.cpu().numpy() == ey).all()
+        # with the optional key bounds (shorter sort) the answer is the same
+        ix2, jx2 = fastba.neighbors(torch.from_numpy(kk).cuda(), torch.from_numpy(jj).cuda(), kmax=nk, jmax=nj)
+        assert (ix2 == ix).all() and (jx2 == jx).all()
+
+
+def test_neighbors_on_vo_graph_and_empty():
+    prob = synth.make_problem("default", 40, seed=0)
+    ix, jx = fastba.neighbors(torch.from_numpy(prob["kk"]).cuda(), torch.from_numpy(prob["jj"]).cuda())
+    ex, ey = O.neighbors(prob["kk"], prob["jj"])
+    assert ix.dtype == torch.int64 and (ix.cpu().numpy() == ex).all() and (jx.cpu().numpy() == ey).all()
+    e = torch.zeros(0, dtype=torch.long, device="cuda")
+    a, b = fastba.neighbors(e, e)
+    assert a.numel() == 0 and b.numel() == 0
+
+
+def _ba_case(config, n_frames, seed, noise=1.0):
+    prob = synth.make_problem(config, n_frames, seed=seed, noise_px=noise)
+    tgt = targets_from_reprojection(prob, O)
+    prob["poses"] = perturb_poses(prob)
+    return prob, tgt
+
+
+def _run_ba(prob, tgt, t0, t1, iters, eff=False):
+    t = problem_tensors(prob)
+    tg = torch.from_numpy(tgt).cuda()[None]
+    wg = torch.from_numpy(prob["weight"]).cuda()[None]
+    lm = torch.tensor([1e-4], device="cuda")
+    out = fastba.BA(t["poses"], t["patches"], t["intrinsics"], tg, wg, lm, t["ii"], t["jj"], t["kk"],
+                    t0, t1, prob["M"], iters, eff)
+    assert out == []
+    return t["poses"][0].cpu().numpy(), t["patches"][0].cpu().numpy()
+
+
+@pytest.mark.parametrize("config,n_frames", [("cfg1", 8), ("fast", 20), ("default", 40)])
+def test_ba_matches_oracle(config, n_frames):
+    """north_star tolerance: fp32 BA poses within 1e-4 rel of the (float64) restatement of cuda_ba."""
+    prob, tgt = _ba_case(config, n_frames, seed=21)
+    for iters in (1, 2):
+        p, q = _run_ba(prob, tgt, prob["t0"], prob["t1"], iters)
+        pe, qe = O.ba(prob["poses"], prob["patches"], prob["intrinsics"], tgt, prob["weight"], 1e-4,
+                      prob["ii"], prob["jj"], prob["kk"], prob["t0"], prob["t1"], iterations=iters)
+        assert rel_err(p, pe) < 1e-4, (config, iters)
+        assert rel_err(q[:, 2], qe[:, 2]) < 1e-4
+        # fixed poses and x/y patch coordinates are untouched
+        assert (p[:prob["t0"]] == prob["poses"][:prob["t0"]]).all()
+        assert (q[:, :2] == prob["patches"][:, :2]).all()
+    # eff_impl flag is accepted and gives the same answer
+    p2, q2 = _run_ba(prob, tgt, prob["t0"], prob["t1"], 2, eff=True)
+    assert rel_err(p2, p) < 1e-5
+
+
+def test_ba_structure_only_and_clamps():
+    prob, tgt = _ba_case("cfg1", 8, seed=22)
+    prob["patches"][5::7, 2] = 19.99       # pushes some depths over the d > 20 -> 1 reset
+    prob["patches"][3::11, 2] = 2e-4       # and some under the 1e-4 floor
+    p, q = _run_ba(prob, tgt, 4, 4, 2)
+    pe, qe = O.ba(prob["poses"], prob["patches"], prob["intrinsics"], tgt, prob["weight"], 1e-4,
+                  prob["ii"], prob["jj"], prob["kk"], 4, 4, iterations=2)
+    assert (p == prob["poses"]).all()
+    assert rel_err(q[:, 2], qe[:, 2]) < 1e-4
+    assert q[:, 2].min() >= 1e-4 - 1e-10 and q[:, 2].max() <= 20.0
+
+
+def test_ba_masks_and_fixed_window():
+    """out-of-bounds / behind-camera edges are masked (ba_cuda.cu:305-308); all edges fixed -> no-op on poses."""
+    prob, tgt = _ba_case("cfg1", 8, seed=23)
+    tgt[::5] += 500.0                      # residual gate 128 px
+    prob["patches"][::9, 2] = 1e-3         # far points
+    p, q = _run_ba(prob, tgt, prob["t0"], prob["t1"], 2)
+    pe, qe = O.ba(prob["poses"], prob["patches"], prob["intrinsics"], tgt, prob["weight"], 1e-4,
+                  prob["ii"], prob["jj"], prob["kk"], prob["t0"], prob["t1"], iterations=2)
+    assert np.isfinite(p).all() and rel_err(p, pe) < 1e-4
+    assert rel_err(q[:, 2], qe[:, 2]) < 1e-4
+
+
+def test_ba_assemble_reduced_system_matches_oracle():
+    """The split API: [S | y] before damping (what a sharded run all-reduces) vs the oracle's S, y."""
+    prob, tgt = _ba_case("default", 40, seed=24)
+    t = problem_tensors(prob)
+    L = _lib.lib()
+    E, N = prob["E"], prob["t1"] - prob["t0"]
+    n6 = 6 * N
+    K = prob["patches"].shape[0]
+    ws = torch.empty(L.rvo_ba_ws_bytes(E, K, N), dtype=torch.uint8, device="cuda")
+    Sy = torch.empty(n6, n6 + 1, device="cuda")
+    tg = torch.from_numpy(tgt).cuda()
+    wg = torch.from_numpy(prob["weight"]).cuda()
+    lm = torch.tensor([1e-4], device="cuda")
+    st = _lib.stream_ptr()
+    _lib.check(L.rvo_ba_plan(_lib.ptr(t["kk"]), _lib.ptr(t["jj"]), E, prob["n"], K, N, _lib.ptr(ws),
+                             ws.numel(), st), "plan")
+    _lib.check(L.rvo_ba_assemble(_lib.ptr(t["poses"]), _lib.ptr(t["patches"]), _lib.ptr(t["intrinsics"]),
+                                 _lib.ptr(tg), _lib.ptr(wg), _lib.ptr(lm), _lib.ptr(t["ii"]),
+                                 _lib.ptr(t["jj"]), E, K, 3, prob["t0"], prob["t1"], _lib.ptr(Sy),
+                                 _lib.ptr(ws), ws.numel(), st), "assemble")
+    s = O.ba_system(prob["poses"], prob["patches"], prob["intrinsics"], tgt, prob["weight"], 1e-4,
+                    prob["ii"], prob["jj"], prob["kk"], prob["t0"], prob["t1"])
+    got = Sy.cpu().numpy()
+    scale = np.abs(s["B"]).max()
+    assert np.abs(got[:, :n6] - s["S"]).max() < 2e-5 * scale     # fp32 sums of ~45k terms
+    assert np.abs(got[:, n6] - s["y"]).max() < 2e-5 * np.abs(s["v"]).max()
+    assert (got[:, :n6] == got[:, :n6].T).all()                   # exactly symmetric
+    # finishing with rvo_ba_solve == rvo_ba_forward(iterations=1)
+    _lib.check(L.rvo_ba_solve(_lib.ptr(t["poses"]), _lib.ptr(t["patches"]), _lib.ptr(Sy), E, K, 3,
+                              prob["t0"], prob["t1"], _lib.ptr(ws), ws.numel(), st), "solve")
+    p1, q1 = _run_ba(prob, tgt, prob["t0"], prob["t1"], 1)
+    assert rel_err(t["poses"][0].cpu().numpy(), p1) < 1e-5
+    assert rel_err(t["patches"][0, :, 2].cpu().numpy(), q1[:, 2]) < 1e-5
+
+
+def test_ba_host_variant_matches_device():
+    prob, tgt = _ba_case("cfg1", 8, seed=25)
+    p_dev, q_dev = _run_ba(prob, tgt, prob["t0"], prob["t1"], 2)
+    L = _lib.lib()
+    poses = prob["poses"].copy()
+    patches = prob["patches"].copy()
+    lm = np.array([1e-4], np.float32)
+    f = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = L.rvo_ba_forward_host(f(poses), f(patches), f(prob["intrinsics"]), f(tgt), f(prob["weight"]),
+                               f(lm), f(prob["ii"]), f(prob["jj"]), f(prob["kk"]), prob["E"],
+                               poses.shape[0], patches.shape[0], 3, prob["M"], prob["t0"], prob["t1"],
+                               2, 0, None)
+    _lib.check(rc, "rvo_ba_forward_host")
+    assert rel_err(poses, p_dev) < 1e-5 and rel_err(patches, q_dev) < 1e-5
+
+
+def test_ba_precise_window_runs_and_converges():
+    """precise.yaml-sized window (30 free poses, 180x180 system) on a reduced graph: the cost drops."""
+    M, l, r, o = synth.CONFIGS["precise"]
+    synth.CONFIGS["precise_small"] = (40, l, r, o)
+    prob, tgt = _ba_case("precise_small", 50, seed=26, noise=0.0)
+    w = np.ones_like(prob["weight"])
+    prob["weight"] = w
+
+    def cost(p, q):
+        rr, wm, *_ = O.ba_linearise(p, q, prob["intrinsics"], tgt, w, prob["ii"], prob["jj"], prob["kk"])
+        return float((wm * rr * rr).sum())
+    c0 = cost(prob["poses"], prob["patches"])
+    p, q = _run_ba(prob, tgt, prob["t0"], prob["t1"], 4)
+    assert prob["t1"] - prob["t0"] == 30
+    assert cost(p, q) < 0.05 * c0
+    pe, qe = O.ba(prob["poses"], prob["patches"], prob["intrinsics"], tgt, w, 1e-4, prob["ii"],
+                  prob["jj"], prob["kk"], prob["t0"], prob["t1"], iterations=4)
+    assert rel_err(p, pe) < 1e-4

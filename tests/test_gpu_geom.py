@@ -1,0 +1,93 @@
+"""GPU parity: fused projective transform kernels vs the numpy oracle (float64 ground truth)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ops as O
+from rampvo_b200 import fastba, projective_ops as pops, synth
+from rampvo_b200.lietorch import SE3
+from tests.util import problem_tensors
+
+pytestmark = pytest.mark.gpu
+
+TOL_PX = 2e-3   # fp32 projection at |x| ~ 160 px: a few ulp of 160 * conditioning of 1/Z
+
+
+@pytest.fixture(scope="module")
+def prob():
+    return synth.make_problem("cfg1", 8, seed=11)
+
+
+def test_transform_matches_oracle(prob):
+    t = problem_tensors(prob)
+    x1, valid = pops.transform(SE3(t["poses"]), t["patches"], t["intrinsics"], t["ii"], t["jj"],
+                               t["kk"], valid=True)
+    c, d, v = O.transform(prob["poses"], prob["patches"], prob["intrinsics"], prob["ii"], prob["jj"],
+                          prob["kk"])
+    assert x1.shape == (1, prob["E"], 3, 3, 2)
+    assert np.abs(x1[0].cpu().numpy() - c).max() < TOL_PX
+    assert (valid[0].cpu().numpy() == v).all()
+    x3 = pops.transform(SE3(t["poses"]), t["patches"], t["intrinsics"], t["ii"], t["jj"], t["kk"],
+                        depth=True)
+    assert x3.shape[-1] == 3
+    assert np.abs(x3[0, ..., 2].cpu().numpy() - d).max() < 1e-5 * d.max()
+    # Ramp_vo.reproject layout [1,E,2,P,P]
+    cf = pops.reproject_cf(SE3(t["poses"]), t["patches"], t["intrinsics"], t["ii"], t["jj"], t["kk"])
+    assert (cf == x1.permute(0, 1, 4, 2, 3)).all()
+
+
+def test_transform_tonly_and_clamp(prob):
+    t = problem_tensors(prob)
+    x1 = pops.transform(SE3(t["poses"]), t["patches"], t["intrinsics"], t["ii"], t["jj"], t["kk"],
+                        tonly=True)
+    c = O.transform(prob["poses"], prob["patches"], prob["intrinsics"], prob["ii"], prob["jj"],
+                    prob["kk"], tonly=True)[0]
+    assert np.abs(x1[0].cpu().numpy() - c).max() < TOL_PX
+    # points behind the camera: Z clamped at 0.1 (projective_ops.py:40)
+    p2 = prob["poses"].copy()
+    p2[:, 2] -= 5.0 * np.arange(len(p2))
+    t2 = torch.from_numpy(p2).cuda()[None]
+    x2 = pops.transform(SE3(t2), t["patches"], t["intrinsics"], t["ii"], t["jj"], t["kk"])
+    c2 = O.transform(p2, prob["patches"], prob["intrinsics"], prob["ii"], prob["jj"], prob["kk"])[0]
+    assert np.abs(x2[0].cpu().numpy() - c2).max() < 1e-5 * np.abs(c2).max() + TOL_PX
+
+
+def test_transform_jacobians(prob):
+    t = problem_tensors(prob)
+    x1, v, (Ji, Jj, Jz) = pops.transform(SE3(t["poses"]), t["patches"], t["intrinsics"], t["ii"],
+                                         t["jj"], t["kk"], jacobian=True)
+    c, ve, (Jie, Jje, Jze) = O.transform(prob["poses"], prob["patches"], prob["intrinsics"],
+                                         prob["ii"], prob["jj"], prob["kk"], jacobian=True)
+    assert Ji.shape == (1, prob["E"], 2, 6) and Jz.shape == (1, prob["E"], 2, 1)
+    for got, exp in ((Ji, Jie), (Jj, Jje), (Jz, Jze)):
+        assert np.abs(got[0].cpu().numpy() - exp).max() < 1e-5 * np.abs(exp).max()
+    assert (v[0].cpu().numpy() == ve).all()
+    assert np.abs(x1[0].cpu().numpy() - c).max() < TOL_PX
+
+
+def test_flow_mag_point_cloud_reproject(prob):
+    t = problem_tensors(prob)
+    fm = pops.flow_mag(SE3(t["poses"]), t["patches"], t["intrinsics"], t["ii"], t["jj"], t["kk"], beta=0.5)
+    exp = O.flow_mag(prob["poses"], prob["patches"], prob["intrinsics"], prob["ii"], prob["jj"],
+                     prob["kk"], beta=0.5)
+    assert np.abs(fm[0].cpu().numpy() - exp).max() < 2 * TOL_PX
+    K = prob["patches"].shape[0]
+    ix = torch.arange(K, device="cuda") // prob["M"]
+    pc = pops.point_cloud_centers(SE3(t["poses"]), t["patches"], t["intrinsics"], ix)
+    pe = O.point_cloud_centers(prob["poses"], prob["patches"], prob["intrinsics"], ix.cpu().numpy())
+    assert np.abs(pc.cpu().numpy() - pe).max() < 1e-5 * np.abs(pe).max()
+    # the torch-plumbing variant of point_cloud agrees at the centre pixel
+    full = pops.point_cloud(SE3(t["poses"]), t["patches"], t["intrinsics"], ix)
+    ctr = full[0, :, 1, 1, :3] / full[0, :, 1, 1, 3:]
+    assert (ctr - pc).abs().max().item() < 1e-4 * np.abs(pe).max()
+    rp = fastba.reproject(t["poses"], t["patches"], t["intrinsics"], t["ii"], t["jj"], t["kk"])
+    re = O.reproject(prob["poses"], prob["patches"], prob["intrinsics"], prob["ii"], prob["jj"], prob["kk"])
+    assert rp.shape == (1, prob["E"], 2, 3, 3)
+    assert np.abs(rp[0].cpu().numpy() - re).max() < TOL_PX
+
+
+def test_empty_graph(prob):
+    t = problem_tensors(prob)
+    e = torch.zeros(0, dtype=torch.long, device="cuda")
+    assert pops.transform(SE3(t["poses"]), t["patches"], t["intrinsics"], e, e, e).shape == (1, 0, 3, 3, 2)
+    assert fastba.reproject(t["poses"], t["patches"], t["intrinsics"], e, e, e).shape == (1, 0, 2, 3, 3)

@@ -1,0 +1,122 @@
+"""GPU: differential tests against the REFERENCE's own compiled CUDA ops (oracle/_ref, built by
+oracle/build_ref.py from /root/reference in the authoring container).  These pin both the product
+and the numpy oracle to the real reference on identical inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import build_ref, ref_ops as O
+from rampvo_b200 import altcorr, fastba, synth
+from tests.util import perturb_poses, problem_tensors, rel_err, targets_from_reprojection
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ref_corr():
+    m = build_ref.load_ref("cuda_corr_ref")
+    if m is None:
+        pytest.skip("oracle/_ref/cuda_corr_ref.so not built")
+    return m
+
+
+@pytest.fixture(scope="module")
+def ref_ba():
+    m = build_ref.load_ref("cuda_ba_ref")
+    if m is None:
+        pytest.skip("oracle/_ref/cuda_ba_ref.so not built")
+    return m
+
+
+def test_patchify_forward_vs_reference(ref_corr):
+    rng = np.random.default_rng(0)
+    for dt in (torch.float32, torch.float16):
+        net = torch.randn(1, 128, 120, 160, device="cuda").to(dt)
+        coords = torch.from_numpy(np.stack([rng.uniform(-2, 162, 96), rng.uniform(-2, 122, 96)], -1)
+                                  .astype(np.float32)).cuda()[None]
+        for R in (0, 1):
+            ref, = ref_corr.patchify_forward(net, coords, R)
+            got, = altcorr.patchify_forward(net, coords, R)
+            assert (ref == got).all()
+            assert (O.patchify_raw(net.cpu().numpy(), coords.cpu().numpy(), R) == ref.cpu().numpy()).all()
+
+
+def test_corr_forward_vs_reference(ref_corr):
+    """fp32: same arithmetic (sequential fp32 accumulation) -> 1e-6 of the output scale.
+    fp16: the reference accumulates and blends in fp16 (correlation_kernel.cu:121-130,223-224), the
+    product in fp32 -> both must sit within fp16 accumulation error of the float64 oracle, ours closer."""
+    rng = np.random.default_rng(1)
+    Np, Nf, C, H, W, P, E = 64, 8, 128, 60, 80, 3, 1500
+    f1 = torch.randn(1, Np, C, P, P, device="cuda") / C ** 0.5
+    f2 = torch.randn(1, Nf, C, H, W, device="cuda") / C ** 0.5
+    ii = torch.from_numpy(rng.integers(0, Np, E)).cuda()
+    jj = torch.from_numpy(rng.integers(0, Nf, E)).cuda()
+    ctr = np.stack([rng.uniform(-5, W + 5, E), rng.uniform(-5, H + 5, E)], 1)
+    g = np.arange(P) - 1
+    c = np.zeros((E, 2, P, P), np.float32)
+    c[:, 0] = ctr[:, 0, None, None] + g[None, None, :] * 1.03
+    c[:, 1] = ctr[:, 1, None, None] + g[None, :, None] * 0.97
+    coords = torch.from_numpy(c).cuda()[None]
+    for R in (1, 3):
+        ref, = ref_corr.forward(f1, f2, coords, ii, jj, R)
+        got = altcorr.corr(f1, f2, coords, ii, jj, R)
+        assert ref.shape == got.shape
+        assert (ref - got).abs().max().item() < 2e-6 * max(1.0, ref.abs().max().item())
+    exp = O.corr(f1[0].cpu().numpy(), f2[0].cpu().numpy(), c, ii.cpu().numpy(), jj.cpu().numpy(), 3)
+    ref16, = ref_corr.forward(f1.half(), f2.half(), coords, ii, jj, 3)
+    got16 = altcorr.corr(f1.half(), f2.half(), coords, ii, jj, 3)
+    exp16 = O.corr(f1[0].half().cpu().numpy(), f2[0].half().cpu().numpy(), c, ii.cpu().numpy(),
+                   jj.cpu().numpy(), 3)
+    e_ref = np.abs(ref16[0].float().cpu().numpy() - exp16).max()
+    e_got = np.abs(got16[0].float().cpu().numpy() - exp16).max()
+    assert e_got <= 1e-3 and e_got <= e_ref + 1e-6
+    assert e_ref < 2e-2          # the oracle is a valid ground truth for the reference's fp16 path too
+    # channels-last tensor-core path on the same data
+    f1c = f1.half().permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+    f2c = f2.half().permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+    got_tc = altcorr.corr(f1c, f2c, coords, ii, jj, 3)
+    assert np.abs(got_tc[0].float().cpu().numpy() - exp16).max() <= 1e-3
+    del exp
+
+
+def test_neighbors_and_reproject_vs_reference(ref_ba):
+    prob = synth.make_problem("default", 40, seed=2)
+    t = problem_tensors(prob)
+    rix, rjx = ref_ba.neighbors(t["kk"], t["jj"])
+    ix, jx = fastba.neighbors(t["kk"], t["jj"])
+    assert (rix == ix).all() and (rjx == jx).all()                      # bit-exact index work
+    r = ref_ba.reproject(t["poses"], t["patches"], t["intrinsics"], t["ii"], t["jj"], t["kk"])
+    g = fastba.reproject(t["poses"], t["patches"], t["intrinsics"], t["ii"], t["jj"], t["kk"])
+    assert (r - g).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("config,n_frames", [("cfg1", 8), ("default", 40)])
+def test_ba_vs_reference(ref_ba, config, n_frames):
+    """fp32 BA poses / depths within 1e-4 rel of cuda_ba on identical inputs (north_star tolerance)."""
+    prob = synth.make_problem(config, n_frames, seed=3)
+    tgt = targets_from_reprojection(prob, O)
+    prob["poses"] = perturb_poses(prob)
+    tg = torch.from_numpy(tgt).cuda()[None]
+    wg = torch.from_numpy(prob["weight"]).cuda()[None]
+    lm = torch.tensor([1e-4], device="cuda")
+    for iters in (1, 2):
+        a = problem_tensors(prob)
+        b = problem_tensors(prob)
+        ref_ba.forward(a["poses"], a["patches"], a["intrinsics"], tg, wg, lm, a["ii"], a["jj"],
+                       a["kk"], prob["M"], prob["t0"], prob["t1"], iters, False)
+        fastba.BA(b["poses"], b["patches"], b["intrinsics"], tg, wg, lm, b["ii"], b["jj"], b["kk"],
+                  prob["t0"], prob["t1"], prob["M"], iters)
+        assert rel_err(b["poses"].cpu().numpy(), a["poses"].cpu().numpy()) < 1e-4
+        assert rel_err(b["patches"][0, :, 2].cpu().numpy(), a["patches"][0, :, 2].cpu().numpy()) < 1e-4
+        # and the float64 oracle agrees with the reference to the same tolerance
+        pe, qe = O.ba(prob["poses"], prob["patches"], prob["intrinsics"], tgt, prob["weight"], 1e-4,
+                      prob["ii"], prob["jj"], prob["kk"], prob["t0"], prob["t1"], iterations=iters)
+        assert rel_err(a["poses"][0].cpu().numpy(), pe) < 1e-4
+    # structure-only branch
+    a = problem_tensors(prob)
+    b = problem_tensors(prob)
+    ref_ba.forward(a["poses"], a["patches"], a["intrinsics"], tg, wg, lm, a["ii"], a["jj"], a["kk"],
+                   prob["M"], 3, 3, 2, False)
+    fastba.BA(b["poses"], b["patches"], b["intrinsics"], tg, wg, lm, b["ii"], b["jj"], b["kk"], 3, 3,
+              prob["M"], 2)
+    assert rel_err(b["patches"][0, :, 2].cpu().numpy(), a["patches"][0, :, 2].cpu().numpy()) < 1e-4
