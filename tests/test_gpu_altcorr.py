@@ -79,8 +79,8 @@ def test_corr_fp32_nchw_matches_oracle(radius):
     """Reference layout (NCHW, fp32): generic kernel, fp32 accumulate; tolerance 1e-5 of the output scale."""
     rng = np.random.default_rng(3)
     C, H, W, P = 32, 24, 30, 3
-    f1 = rng.standard_normal((1, 20, C, P, P)).astype(np.float32) / np.sqrt(C)
-    f2 = rng.standard_normal((1, 4, C, H, W)).astype(np.float32) / np.sqrt(C)
+    f1 = (rng.standard_normal((1, 20, C, P, P)) / np.sqrt(C)).astype(np.float32)
+    f2 = (rng.standard_normal((1, 4, C, H, W)) / np.sqrt(C)).astype(np.float32)
     ii, jj, coords = _corr_case(rng, 300, 20, 4, C, H, W, P)
     got = altcorr.corr(torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda(),
                        torch.from_numpy(coords).cuda()[None], torch.from_numpy(ii).cuda(),
