@@ -215,6 +215,26 @@ int rvo_ba_forward_host(float* poses, float* patches, const float* intrinsics, c
                         int64_t n_patches, int P, int PPF, int t0, int t1, int iterations,
                         int eff_impl, void* stream);
 
+/* ------------------------------------------------------------ update operator --- */
+
+/* The non-GEMM stages of Update.forward (ramp/net.py:69-90).
+ *
+ * rvo_softagg: SoftAgg.forward's torch.unique + scatter_softmax + scatter_sum
+ * (ramp/blocks.py:42-45) in one pass over a graph plan whose first sort key is the group id
+ * (kk for agg_kk; ii*12345+jj for agg_ij, net.py:84-85):
+ *   y[g, c] = sum_{e in g} fx[e,c] * softmax_{e in g}(gx[e,c])
+ * fx, gx [E,C] (dtype RVO_F16/RVO_F32), y [U,C] (y_dtype), groups numbered in ascending key order
+ * like torch.unique's inverse.  max_groups bounds U (0 = E).
+ * rvo_expand_add: net[e,:] += hy[group(e),:]  (the `[:, jx]` expand of blocks.py:47-48 fused with
+ * the residual add of net.py:84-85); net fp32 [E,C], C % 4 == 0.
+ * rvo_gather_rows: out[e,:] = idx[e] >= 0 ? src[idx[e],:] : 0  (mask_ix * net[:, ix], net.py:78-82). */
+int rvo_softagg(const void* fx, const void* gx, int dtype, const void* plan, int E, int C,
+                int64_t max_groups, void* y, int y_dtype, void* stream);
+int rvo_expand_add(const void* hy, int dtype, const void* plan, int E, int C, float* net,
+                   void* stream);
+int rvo_gather_rows(const float* src, const int64_t* idx, int E, int C, void* out, int out_dtype,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

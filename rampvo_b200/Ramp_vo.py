@@ -1,0 +1,332 @@
+"""Drop-in for ramp.Ramp_vo.Ramp_vo (ramp/Ramp_vo.py:27-410): the online VO state machine.
+
+Same constructor, `__call__(tstamp, input_tensor, intrinsics)`, `update()`, `keyframe()`,
+`terminate()` and public buffers (`poses_`, `patches_`, `points_`, `colors_`, `n`, `m`, `ii`, `jj`,
+`kk`) as the reference.  What changed underneath (HBM layout, DESIGN.md section "data layout"):
+
+  * feature ring buffers are channels-last: fmap1_/fmap2_ are stored [mem,H,W,128], gmap_ is stored
+    [mem*M,P,P,128]; the attributes keep the reference's logical shapes as permuted VIEWS, which is
+    what routes `corr` to the tensor-core kernel (one launch for both pyramid levels, blend and
+    permute fused) instead of 2 launches + ~12 elementwise kernels per level;
+  * `reproject` is one fused kernel writing [1,E,2,P,P] directly (pops.transform + permute);
+  * the graph bookkeeping of one update (neighbours, SoftAgg groups, BA patch numbering) is computed
+    on the device once per graph change and cached — no `.to(kCPU)` round trip per update;
+  * `point_cloud` after BA is one kernel over the patch centres.
+Python keeps what the reference keeps in Python: ring-buffer index math, edge-list append/remove,
+the motion model on two SE3 elements, keyframe decisions.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import altcorr, fastba, lietorch
+from . import projective_ops as pops
+from .lietorch import SE3
+from .net import GraphPlans, VONet
+from .vo_utils import filter_features, flatmeshgrid, preprocess_input
+
+
+class Ramp_vo:
+    def __init__(self, cfg, network, train_cfg, ht=480, wd=640, device="cuda"):
+        self.cfg = cfg
+        self.event_bias = train_cfg["event_bias"]
+        self.train_cfg = train_cfg
+        self.device = torch.device(device)
+        self.lmbda = torch.as_tensor([1e-4], device=self.device)
+        self.load_weights(network)
+        self.is_initialized = False
+        self.enable_timing = False
+
+        self.n = 0      # number of frames
+        self.m = 0      # number of patches
+        self.M = self.cfg.PATCHES_PER_FRAME
+        self.N = self.cfg.BUFFER_SIZE
+        self.ht, self.wd = ht, wd
+        DIM, RES, P, M, N = self.DIM, self.RES, self.P, self.M, self.N
+        dev = self.device
+
+        self.tlist = []
+        self.counter = 0
+        self.tstamps_ = torch.zeros(N, dtype=torch.long, device=dev)
+        self.poses_ = torch.zeros(N, 7, dtype=torch.float, device=dev)
+        self.patches_ = torch.zeros(N, M, 3, P, P, dtype=torch.float, device=dev)
+        self.intrinsics_ = torch.zeros(N, 4, dtype=torch.float, device=dev)
+        self.points_ = torch.zeros(N * M, 3, dtype=torch.float, device=dev)
+        self.colors_ = torch.zeros(N, M, 3, dtype=torch.uint8, device=dev)
+        self.index_ = torch.zeros(N, M, dtype=torch.long, device=dev)
+        self.index_map_ = torch.zeros(N, dtype=torch.long, device=dev)
+
+        self.mem = 32
+        self.autocast = bool(self.cfg.MIXED_PRECISION)
+        self.fdtype = torch.half if self.autocast else torch.float
+        self.kwargs = {"device": dev, "dtype": self.fdtype}
+        h4, w4 = ht // RES, wd // RES
+        self.imap_ = torch.zeros(self.mem, M, DIM, **self.kwargs)
+        # channels-last storage, reference-shaped views
+        self._gmap_store = torch.zeros(self.mem * M, P, P, 128, **self.kwargs)
+        self._fmap1_store = torch.zeros(self.mem, h4, w4, 128, **self.kwargs)
+        self._fmap2_store = torch.zeros(self.mem, h4 // 4, w4 // 4, 128, **self.kwargs)
+        self.gmap_ = self._gmap_store.permute(0, 3, 1, 2).view(self.mem, M, 128, P, P)
+        self.fmap1_ = self._fmap1_store.permute(0, 3, 1, 2)[None]
+        self.fmap2_ = self._fmap2_store.permute(0, 3, 1, 2)[None]
+        self.pyramid = (self.fmap1_, self.fmap2_)
+
+        self.net = torch.zeros(1, 0, DIM, device=dev, dtype=torch.float)
+        self.ii = torch.as_tensor([], dtype=torch.long, device=dev)
+        self.jj = torch.as_tensor([], dtype=torch.long, device=dev)
+        self.kk = torch.as_tensor([], dtype=torch.long, device=dev)
+        self._plans = None          # GraphPlans of the current edge list
+
+        self.poses_[:, 6] = 1.0
+        self.delta = {}
+        self.Id = SE3.Identity(1, device=dev)
+
+    # ------------------------------------------------------------------ weights
+    def load_weights(self, network):
+        """ramp/Ramp_vo.py:103-129: a path to a reference checkpoint or a VONet instance."""
+        if isinstance(network, str):
+            ckpt = torch.load(network, map_location="cpu")
+            sd = ckpt.get('model_state_dict') or ckpt
+            sd = {k.replace('module.', ''): v for k, v in sd.items() if "update.lmbda" not in k}
+            self.network = VONet(cfg=self.train_cfg)
+            self.network.load_state_dict(sd)
+        else:
+            self.network = network
+        self.DIM = self.network.DIM
+        self.RES = self.network.RES
+        self.P = self.network.P
+        self.network.to(self.device)
+        self.network.eval()
+
+    # ------------------------------------------------------------------ views (Ramp_vo.py:131-157)
+    @property
+    def poses(self):
+        return self.poses_.view(1, self.N, 7)
+
+    @property
+    def patches(self):
+        return self.patches_.view(1, self.N * self.M, 3, self.P, self.P)
+
+    @property
+    def intrinsics(self):
+        return self.intrinsics_.view(1, self.N, 4)
+
+    @property
+    def ix(self):
+        return self.index_.view(-1)
+
+    @property
+    def imap(self):
+        return self.imap_.view(1, self.mem * self.M, self.DIM)
+
+    @property
+    def gmap(self):
+        return self._gmap_store.permute(0, 3, 1, 2)[None]      # [1, mem*M, 128, P, P] view
+
+    # ------------------------------------------------------------------ trajectory (Ramp_vo.py:155-173)
+    def get_pose(self, t):
+        if t in self.traj:
+            return SE3(self.traj[t])
+        t0, dP = self.delta[t]
+        return dP * self.get_pose(t0)
+
+    def terminate(self):
+        """interpolate missing poses; returns (poses [counter,7] camera-to-world, tstamps)."""
+        self.traj = {}
+        ts = self.tstamps_[:self.n].tolist()
+        for i in range(self.n):
+            self.traj[ts[i]] = self.poses_[i]
+        poses = [self.get_pose(t) for t in range(self.counter)]
+        poses = lietorch.stack(poses, dim=0)
+        poses = poses.inv().data.cpu().numpy()
+        return poses, np.array(self.tlist, dtype=float)
+
+    # ------------------------------------------------------------------ hot-path pieces
+    def corr(self, coords, indicies=None):
+        """local correlation volume [1,E,882] (Ramp_vo.py:175-182), one fused launch"""
+        ii, jj = indicies if indicies is not None else (self.kk, self.jj)
+        return altcorr.corr_pyramid(self.gmap, self.pyramid, coords, ii, jj, self.M * self.mem,
+                                    self.mem, 3)
+
+    def reproject(self, indicies=None, poses=None, patches=None, intrinsics=None):
+        """reproject patch k from i -> j: coords [1,E,2,P,P] (Ramp_vo.py:184-192)"""
+        (ii, jj, kk) = indicies if indicies is not None else (self.ii, self.jj, self.kk)
+        poses = poses if poses is not None else self.poses
+        patches = patches if patches is not None else self.patches
+        intrinsics = intrinsics if intrinsics is not None else self.intrinsics
+        return pops.reproject_cf(SE3(poses), patches, intrinsics, ii, jj, kk)
+
+    def append_factors(self, ii, jj):
+        """add factors to the graph (Ramp_vo.py:194-201)"""
+        self.jj = torch.cat([self.jj, jj])
+        self.kk = torch.cat([self.kk, ii])
+        self.ii = torch.cat([self.ii, self.ix[ii]])
+        net = torch.zeros(1, len(ii), self.DIM, device=self.device, dtype=self.net.dtype)
+        self.net = torch.cat([self.net, net], dim=1)
+        self._plans = None
+
+    def remove_factors(self, m):
+        """remove factors from the graph (Ramp_vo.py:203-208)"""
+        keep = ~m
+        self.ii = self.ii[keep]
+        self.jj = self.jj[keep]
+        self.kk = self.kk[keep]
+        self.net = self.net[:, keep]
+        self._plans = None
+
+    def _graph_plans(self):
+        if self._plans is None:
+            self._plans = GraphPlans(self.ii, self.jj, self.kk, kmax=self.N * self.M, jmax=self.N)
+        return self._plans
+
+    def motion_probe(self):
+        """median |delta| of the newest patches against the candidate frame (Ramp_vo.py:210-225)"""
+        kk = torch.arange(self.m - self.M, self.m, device=self.device)
+        jj = self.n * torch.ones_like(kk)
+        ii = self.ix[kk]
+        net = torch.zeros(1, len(ii), self.DIM, device=self.device)
+        coords = self.reproject(indicies=(ii, jj, kk))
+        with torch.autocast("cuda", enabled=self.autocast):
+            corr = self.corr(coords, indicies=(kk, jj))
+            ctx = self.imap[:, kk % (self.M * self.mem)]
+            net, (delta, weight, _) = self.network.update(net, ctx, corr, None, ii, jj, kk)
+        return torch.quantile(delta.norm(dim=-1).float(), 0.5)
+
+    def motionmag(self, i, j):
+        """mean flow of the patches of frame i seen in frame j (Ramp_vo.py:227-235)"""
+        k = (self.ii == i) & (self.jj == j)
+        flow = pops.flow_mag(SE3(self.poses), self.patches, self.intrinsics, self.ii[k], self.jj[k],
+                             self.kk[k], beta=0.5)
+        return flow.mean().item()
+
+    def keyframe(self):
+        """remove keyframe n-KEYFRAME_INDEX if motion is small (Ramp_vo.py:237-274)"""
+        i = self.n - self.cfg.KEYFRAME_INDEX - 1
+        j = self.n - self.cfg.KEYFRAME_INDEX + 1
+        m = self.motionmag(i, j) + self.motionmag(j, i)
+        if m / 2 < self.cfg.KEYFRAME_THRESH:
+            k = self.n - self.cfg.KEYFRAME_INDEX
+            t0 = self.tstamps_[k - 1].item()
+            t1 = self.tstamps_[k].item()
+            dP = SE3(self.poses_[k]) * SE3(self.poses_[k - 1]).inv()
+            self.delta[t1] = (t0, dP)
+            self.remove_factors((self.ii == k) | (self.jj == k))
+            self.kk[self.ii > k] -= self.M
+            self.ii[self.ii > k] -= 1
+            self.jj[self.jj > k] -= 1
+            # shift every per-frame buffer one slot down (the reference loops frame by frame)
+            n = self.n
+            for buf in (self.tstamps_, self.colors_, self.poses_, self.patches_, self.intrinsics_):
+                buf[k:n - 1] = buf[k + 1:n].clone()
+            src = torch.arange(k + 1, n, device=self.device) % self.mem
+            dst = torch.arange(k, n - 1, device=self.device) % self.mem
+            if len(src):
+                self.imap_[dst] = self.imap_[src]
+                g = self._gmap_store.view(self.mem, self.M, self.P, self.P, 128)
+                g[dst] = g[src]
+                self._fmap1_store[dst] = self._fmap1_store[src]
+                self._fmap2_store[dst] = self._fmap2_store[src]
+            self.n -= 1
+            self.m -= self.M
+        self.remove_factors(self.ix[self.kk] < self.n - self.cfg.REMOVAL_WINDOW)
+
+    def update(self):
+        """one recurrent update: reproject -> corr -> update operator -> 2 BA iterations
+        (Ramp_vo.py:276-310)"""
+        coords = self.reproject()
+        plans = self._graph_plans()
+        with torch.autocast("cuda", enabled=self.autocast):
+            corr = self.corr(coords)
+            ctx = self.imap[:, self.kk % (self.M * self.mem)]
+            self.net, (delta, weight, _) = self.network.update(self.net, ctx, corr, None, self.ii,
+                                                               self.jj, self.kk, plans=plans)
+        weight = weight.float()
+        target = coords[..., self.P // 2, self.P // 2] + delta.float()
+        weight = filter_features(confidences=weight, target=target,
+                                 data_shape=(self.ht // 4, self.wd // 4))
+        self.last_weight = weight
+        t0 = self.n - self.cfg.OPTIMIZATION_WINDOW if self.is_initialized else 1
+        t0 = max(t0, 1)
+        try:
+            fastba.BA(self.poses, self.patches, self.intrinsics, target, weight, self.lmbda, self.ii,
+                      self.jj, self.kk, t0, self.n, M=self.M, iterations=2, eff_impl=False)
+        except RuntimeError as e:   # BA failure is non-fatal, like the reference (:302-306)
+            print(f"WARNING: BA failed...{e}")
+        pts = pops.point_cloud_centers(SE3(self.poses), self.patches[:, :self.m], self.intrinsics,
+                                       self.ix[:self.m])
+        self.points_[:len(pts)] = pts
+
+    def _edges_forw(self):
+        r = self.cfg.PATCH_LIFETIME
+        t0 = self.M * max((self.n - r), 0)
+        t1 = self.M * max((self.n - 1), 0)
+        return flatmeshgrid(torch.arange(t0, t1, device=self.device),
+                            torch.arange(self.n - 1, self.n, device=self.device), indexing='ij')
+
+    def _edges_back(self):
+        r = self.cfg.PATCH_LIFETIME
+        t0 = self.M * max((self.n - 1), 0)
+        t1 = self.M * max((self.n - 0), 0)
+        return flatmeshgrid(torch.arange(t0, t1, device=self.device),
+                            torch.arange(max(self.n - r, 0), self.n, device=self.device), indexing='ij')
+
+    def __call__(self, tstamp, input_tensor, intrinsics):
+        """track a new frame (Ramp_vo.py:327-410)"""
+        input_ = preprocess_input(input_tensor=input_tensor)
+        slot = self.n % self.mem
+        P, M = self.P, self.M
+        gslot = self._gmap_store[slot * M:(slot + 1) * M].permute(0, 3, 1, 2)[None]   # [1,M,128,P,P]
+        with torch.autocast("cuda", enabled=self.autocast):
+            fmap, gmap, imap, patches, _, clr = self.network.patchify(
+                input_=input_, patches_per_image=M, event_bias=self.event_bias,
+                reinit_hidden=True if tstamp == 0 else False, gmap_out=gslot)
+        mask = input_[2]
+        if fmap is None or (mask is not None and not bool(torch.as_tensor(mask).any())):
+            return      # events only: the super state was updated, the VO is not
+
+        self.tlist.append(tstamp)
+        self.tstamps_[self.n] = self.counter
+        self.intrinsics_[self.n] = torch.as_tensor(intrinsics, device=self.device) / self.RES
+        self.index_[self.n + 1] = self.n + 1
+        self.index_map_[self.n + 1] = self.m + self.M
+        clr = (clr[0, :, [2, 1, 0]] + 0.5) * (255.0 / 2)
+        self.colors_[self.n] = clr.to(torch.uint8)
+
+        if self.n > 1:
+            if self.cfg.MOTION_MODEL == 'DAMPED_LINEAR':
+                P1 = SE3(self.poses_[self.n - 1])
+                P2 = SE3(self.poses_[self.n - 2])
+                xi = self.cfg.MOTION_DAMPING * (P1 * P2.inv()).log()
+                self.poses_[self.n] = (SE3.exp(xi) * P1).data
+            else:
+                self.poses_[self.n] = self.poses_[self.n - 1]
+
+        patches[:, :, 2] = torch.rand_like(patches[:, :, 2, 0, 0, None, None])
+        if self.is_initialized:
+            patches[:, :, 2] = torch.median(self.patches_[self.n - 3:self.n, :, 2])
+        self.patches_[self.n] = patches
+
+        # network attributes: gmap is already in its ring slot; fmap pyramid written channels-last
+        self.imap_[slot] = imap.view(M, self.DIM).to(self.fdtype)
+        f = fmap[0, 0]                                               # [128,h,w]
+        self._fmap1_store[slot] = f.permute(1, 2, 0).to(self.fdtype)
+        self._fmap2_store[slot] = F.avg_pool2d(f[None].float(), 4, 4)[0].permute(1, 2, 0).to(self.fdtype)
+
+        self.counter += 1
+        if self.n > 0 and not self.is_initialized:
+            if self.motion_probe() < 2.0:
+                self.delta[self.counter - 1] = (self.counter - 2, self.Id[0])
+                return
+
+        self.n += 1
+        self.m += self.M
+        self.append_factors(*self._edges_forw())
+        self.append_factors(*self._edges_back())
+
+        if self.n == 8 and not self.is_initialized:
+            self.is_initialized = True
+            for _ in range(12):
+                self.update()
+        elif self.is_initialized:
+            self.update()
+            self.keyframe()

@@ -57,6 +57,9 @@ _SIGNATURES = {
     "rvo_ba_assemble": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, c_int, c_int, c_int,
                                 _P, _P, _I64, _P]),
     "rvo_ba_solve": (c_int, [_P, _P, _P, c_int, _I64, c_int, c_int, c_int, _P, _I64, _P]),
+    "rvo_softagg": (c_int, [_P, _P, c_int, _P, c_int, c_int, _I64, _P, c_int, _P]),
+    "rvo_expand_add": (c_int, [_P, c_int, _P, c_int, c_int, _P, _P]),
+    "rvo_gather_rows": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P]),
     "rvo_ba_forward_host": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, _I64, c_int,
                                     c_int, c_int, c_int, c_int, c_int, _P]),
 }

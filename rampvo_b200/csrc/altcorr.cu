@@ -14,6 +14,8 @@
 //
 // A strided CUDA-core kernel covers every other layout / dtype / patch size (same arithmetic,
 // fp32 accumulate), so the reference's NCHW call signature keeps working.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rvo {
@@ -232,24 +234,25 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
 }
 
 // D rows [row_lo, row_hi] of  A(16 x C) * window(C x ntiles*8)  -> Ds[row][wy*kUni + wx]
-// window = `wu` x `wu` positions at (y0.., x0..) of frame map `fbase` ([H,W,C] channels-last).
-template <int C>
+// window = WU x WU positions at (y0.., x0..) of frame map `fbase` ([H,W,C] channels-last).
+// WU is a compile-time constant so that pos -> (wy, wx) is a multiply-shift, not a division.
+template <int C, int WU, int NTB>
 __device__ __forceinline__ void window_mma(const uint32_t (&afrag)[C / 16][4],
                                            const __half* __restrict__ fbase, int H, int W,
-                                           int64_t sH, int64_t sW, int y0, int x0, int wu,
-                                           int row_lo, int row_hi, float* __restrict__ Ds,
-                                           int lane) {
+                                           int sH, int sW, int y0, int x0, int row_lo,
+                                           int row_hi, float* __restrict__ Ds, int lane) {
   const int g = lane >> 2, t = lane & 3;
-  const int npos = wu * wu;
-  const int ntiles = (npos + 7) >> 3;
-  for (int nt = 0; nt < ntiles; nt += 2) {
-    uint4 bq[2][C / 32];
+  constexpr int npos = WU * WU;
+  constexpr int ntiles = (npos + 7) >> 3;
+#pragma unroll 1
+  for (int nt = 0; nt < ntiles; nt += NTB) {
+    uint4 bq[NTB][C / 32];
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
+    for (int u = 0; u < NTB; u++) {
       const int pos = (nt + u) * 8 + g;
-      const int wy = pos / wu, wx = pos - wy * wu;
+      const int wy = pos / WU, wx = pos - wy * WU;
       const int y = y0 + wy, x = x0 + wx;
-      const bool ok = (nt + u) < ntiles && pos < npos && y >= 0 && y < H && x >= 0 && x < W;
+      const bool ok = pos < npos && (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
       const __half* p = fbase + (ok ? (y * sH + x * sW) : 0) + t * 8;
 #pragma unroll
       for (int q = 0; q < C / 32; q++) {
@@ -257,7 +260,7 @@ __device__ __forceinline__ void window_mma(const uint32_t (&afrag)[C / 16][4],
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
+    for (int u = 0; u < NTB; u++) {
       if (nt + u >= ntiles) break;
       float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -267,32 +270,55 @@ __device__ __forceinline__ void window_mma(const uint32_t (&afrag)[C / 16][4],
       }
       // c0,c1: row g, positions 2t,2t+1 of this tile; c2,c3: row g+8
       const int pos = (nt + u) * 8 + 2 * t;
+      if (WU == kUni) {
+        // row-major 10-wide window: the smem column IS the position index; npos is even
+        if (pos < npos) {
+          if (g >= row_lo && g <= row_hi)
+            *reinterpret_cast<float2*>(Ds + g * kPosPad + pos) = make_float2(c[0], c[1]);
+          if (g == 0 && 8 >= row_lo && 8 <= row_hi)
+            *reinterpret_cast<float2*>(Ds + 8 * kPosPad + pos) = make_float2(c[2], c[3]);
+        }
+      } else {
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int pp = pos + h;
-        if (pp < npos) {
-          const int wy = pp / wu, wx = pp - wy * wu;
-          if (g >= row_lo && g <= row_hi) Ds[g * kPosPad + wy * kUni + wx] = c[h];
-          if (g + 8 >= row_lo && g + 8 <= row_hi && g + 8 < 9)
-            Ds[(g + 8) * kPosPad + wy * kUni + wx] = c[2 + h];
+        for (int h = 0; h < 2; h++) {
+          const int pp = pos + h;
+          if (pp < npos) {
+            const int wy = pp / WU, wx = pp - wy * WU;
+            if (g >= row_lo && g <= row_hi) Ds[g * kPosPad + wy * kUni + wx] = c[h];
+            if (g + 8 >= row_lo && g + 8 <= row_hi && g + 8 < 9)
+              Ds[(g + 8) * kPosPad + wy * kUni + wx] = c[2 + h];
+          }
         }
       }
     }
   }
 }
 
-template <int C, int NL>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+template <int C, int NL, int NTB, int OCC>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, OCC)
 corr_mma_kernel(const __half* __restrict__ gmap, int64_t gN, int64_t g_sN, int64_t g_sH,
                 int64_t g_sW, CorrLevels L, const float* __restrict__ coords,
                 const int64_t* __restrict__ kk, const int64_t* __restrict__ jj, int64_t pmod,
                 int64_t fmod, int E, __half* __restrict__ out) {
-  __shared__ float Dsm[kWarpsPerCta][9 * kPosPad];
+  __shared__ __align__(16) float Dsm[kWarpsPerCta][9 * kPosPad];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   float* Ds = Dsm[warp];
   constexpr int NOUT = 49 * 9;                     // 441 outputs per level
   constexpr int NIT = (NOUT + 31) / 32;            // 14
+
+  // output o = (b*7 + a)*9 + pix (b: x offset, a: y offset; correlation_kernel.cu:227-232).
+  // The lane's 14 (pix, a*kUni + b) pairs never change: pack them once for the persistent loop.
+  uint32_t tab[NIT / 2];
+#pragma unroll
+  for (int it = 0; it < NIT; it++) {
+    const int o = it * 32 + lane;
+    const int oo = o < NOUT ? o : NOUT - 1;
+    const int pix = oo % 9, ab = oo / 9;
+    const int b = ab / 7, a = ab - b * 7;
+    const uint32_t v = (uint32_t)pix | ((uint32_t)(a * kUni + b) << 4);   // 4 + 7 bits
+    if (it & 1) tab[it >> 1] |= v << 16; else tab[it >> 1] = v;
+  }
 
   for (int e = blockIdx.x * kWarpsPerCta + warp; e < E; e += gridDim.x * kWarpsPerCta) {
     int64_t ip = kk[e], jf = jj[e];
@@ -324,7 +350,7 @@ corr_mma_kernel(const __half* __restrict__ gmap, int64_t gN, int64_t g_sN, int64
       cy = coords[(int64_t)e * 18 + 9 + lane];
     }
 
-    float acc[NL][NIT];
+    __half2 acc0[NIT / 2];   // level-0 results wait here (packed fp16) for their level-1 partner
 #pragma unroll
     for (int lvl = 0; lvl < NL; lvl++) {
       const FmapView& f = L.f[lvl];
@@ -337,59 +363,55 @@ corr_mma_kernel(const __half* __restrict__ gmap, int64_t gN, int64_t g_sN, int64
       int mnx = (lane < 9) ? fx : 0x7fffffff, mny = (lane < 9) ? fy : 0x7fffffff;
       int mxx = (lane < 9) ? fx : (int)0x80000000, mxy = (lane < 9) ? fy : (int)0x80000000;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = 8; o > 0; o >>= 1) {   // lanes 0..15 cover the 9 pixels
         mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
         mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
         mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
         mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
       }
-      int ox, oy;  // this pixel's window origin inside the staged window
+      mnx = __shfl_sync(0xffffffffu, mnx, 0); mny = __shfl_sync(0xffffffffu, mny, 0);
+      mxx = __shfl_sync(0xffffffffu, mxx, 0); mxy = __shfl_sync(0xffffffffu, mxy, 0);
+      int pbase;  // this pixel's window origin inside the staged window, as a Ds offset
       if (mxx - mnx <= kUni - kWin && mxy - mny <= kUni - kWin) {
-        window_mma<C>(afrag, fbase, Hh, f.W, f.sH, f.sW, mny - kCorrR, mnx - kCorrR, kUni, 0, 8,
-                      Ds, lane);
-        ox = fx - mnx;
-        oy = fy - mny;
+        window_mma<C, kUni, NTB>(afrag, fbase, Hh, f.W, (int)f.sH, (int)f.sW, mny - kCorrR,
+                            mnx - kCorrR, 0, 8, Ds, lane);
+        pbase = lane * kPosPad + (fy - mny) * kUni + (fx - mnx);
       } else {
         // spread-out patch (strong zoom / rotation): one private 8x8 window per pixel
         for (int p = 0; p < 9; p++) {
           const int pfx = __shfl_sync(0xffffffffu, fx, p), pfy = __shfl_sync(0xffffffffu, fy, p);
-          window_mma<C>(afrag, fbase, Hh, f.W, f.sH, f.sW, pfy - kCorrR, pfx - kCorrR, kWin, p, p,
-                        Ds, lane);
+          window_mma<C, kWin, NTB>(afrag, fbase, Hh, f.W, (int)f.sH, (int)f.sW, pfy - kCorrR,
+                              pfx - kCorrR, p, p, Ds, lane);
         }
-        ox = 0;
-        oy = 0;
+        pbase = lane * kPosPad;
       }
       __syncwarp();
-      // blend: output o = (b*7 + a)*9 + pix  (b: x offset, a: y offset), correlation_kernel.cu:227-232
-      const float w00 = (1.0f - dx) * (1.0f - dy), w01 = dx * (1.0f - dy);
-      const float w10 = (1.0f - dx) * dy, w11 = dx * dy;
+      // bilinear blend (correlation_kernel.cu:221-230) as two lerps, fp32
 #pragma unroll
       for (int it = 0; it < NIT; it++) {
-        const int o = it * 32 + lane;
-        const int oo = o < NOUT ? o : NOUT - 1;
-        const int pix = oo % 9, ab = oo / 9;
-        const int b = ab / 7, a = ab - b * 7;
-        const int pox = __shfl_sync(0xffffffffu, ox, pix), poy = __shfl_sync(0xffffffffu, oy, pix);
-        const float q00 = __shfl_sync(0xffffffffu, w00, pix), q01 = __shfl_sync(0xffffffffu, w01, pix);
-        const float q10 = __shfl_sync(0xffffffffu, w10, pix), q11 = __shfl_sync(0xffffffffu, w11, pix);
-        const float* dp = Ds + pix * kPosPad + (poy + a) * kUni + pox + b;
-        acc[lvl][it] = q00 * dp[0] + q01 * dp[1] + q10 * dp[kUni] + q11 * dp[kUni + 1];
-      }
-      __syncwarp();
-    }
-
-    // store: [E][441][NL] halves; NL == 2 -> one 4-byte (level0, level1) store per output
-#pragma unroll
-    for (int it = 0; it < NIT; it++) {
-      const int o = it * 32 + lane;
-      if (o < NOUT) {
-        if (NL == 2) {
-          __half2 v = __floats2half2_rn(acc[0][it], acc[NL - 1][it]);
-          reinterpret_cast<__half2*>(out)[(int64_t)e * NOUT + o] = v;
+        const uint32_t tv = (tab[it >> 1] >> ((it & 1) * 16)) & 0xffffu;
+        const int pix = tv & 15, off = tv >> 4;
+        const int base = __shfl_sync(0xffffffffu, pbase, pix);
+        const float wx = __shfl_sync(0xffffffffu, dx, pix), wy = __shfl_sync(0xffffffffu, dy, pix);
+        const float* dp = Ds + base + off;
+        const float c00 = dp[0], c01 = dp[1], c10 = dp[kUni], c11 = dp[kUni + 1];
+        const float top = c00 + wx * (c01 - c00);
+        const float bot = c10 + wx * (c11 - c10);
+        const float v = top + wy * (bot - top);
+        if (NL == 2 && lvl == 0) {
+          if (it & 1) acc0[it >> 1].y = __float2half_rn(v); else acc0[it >> 1].x = __float2half_rn(v);
         } else {
-          out[(int64_t)e * NOUT + o] = __float2half_rn(acc[0][it]);
+          const int o = it * 32 + lane;
+          if (o < NOUT) {
+            if (NL == 2)
+              reinterpret_cast<__half2*>(out)[(int64_t)e * NOUT + o] =
+                  __halves2half2((it & 1) ? acc0[it >> 1].y : acc0[it >> 1].x, __float2half_rn(v));
+            else
+              out[(int64_t)e * NOUT + o] = __float2half_rn(v);
+          }
         }
       }
+      __syncwarp();
     }
   }
 }
@@ -400,10 +422,12 @@ static bool fast_path_ok(const FmapView& g, const CorrLevels& L, int dtype, int 
   if (L.n < 1 || L.n > 2) return false;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   if (!al16(g.data) || (g.sN % 8) || (g.sH % 8) || (g.sW % 8)) return false;
+  const int64_t i32max = 0x7fffffff;
   for (int l = 0; l < L.n; l++) {
     const FmapView& f = L.f[l];
     if (f.C != g.C || f.sC != 1 || !al16(f.data) || (f.sN % 8) || (f.sH % 8) || (f.sW % 8))
       return false;
+    if (f.sH < 0 || f.sW < 0 || f.H * f.sH + f.W * f.sW > i32max) return false;  // 32-bit in-frame offsets
   }
   (void)E;
   return true;
@@ -431,15 +455,28 @@ static int corr_launch(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const flo
   for (int l = nlevels; l < kMaxLevels; l++) { L.f[l] = L.f[0]; L.scale[l] = 1.0f; }
 
   if (fast_path_ok(g, L, fmap1->dtype, radius, E)) {
-    const int grid = cdiv(E, kWarpsPerCta);
-    if (nlevels == 2)
-      corr_mma_kernel<128, 2><<<grid, kWarpsPerCta * 32, 0, st>>>(
-          (const __half*)g.data, g.N, g.sN, g.sH, g.sW, L, coords, kk, jj, pmod, fmod, E,
-          (__half*)out);
-    else
-      corr_mma_kernel<128, 1><<<grid, kWarpsPerCta * 32, 0, st>>>(
-          (const __half*)g.data, g.N, g.sN, g.sH, g.sW, L, coords, kk, jj, pmod, fmod, E,
-          (__half*)out);
+    // development switch (tools/microbench.py): RVO_CORR_VARIANT = 10*NTB + OCC
+    static const int variant = getenv("RVO_CORR_VARIANT") ? atoi(getenv("RVO_CORR_VARIANT")) : 22;
+    const int occ = variant % 10;
+    int grid = cdiv(E, kWarpsPerCta);
+    if (grid > kNumSMs * occ) grid = kNumSMs * occ;   // persistent: `occ` resident CTAs per SM
+#define RVO_CORR_LAUNCH(NL_, NTB_, OCC_)                                                       \
+    corr_mma_kernel<128, NL_, NTB_, OCC_><<<grid, kWarpsPerCta * 32, 0, st>>>(                  \
+        (const __half*)g.data, g.N, g.sN, g.sH, g.sW, L, coords, kk, jj, pmod, fmod, E,         \
+        (__half*)out)
+#define RVO_CORR_PICK(NL_)                                                                     \
+    switch (variant) {                                                                         \
+      case 12: RVO_CORR_LAUNCH(NL_, 1, 2); break;                                              \
+      case 13: RVO_CORR_LAUNCH(NL_, 1, 3); break;                                              \
+      case 14: RVO_CORR_LAUNCH(NL_, 1, 4); break;                                              \
+      case 22: RVO_CORR_LAUNCH(NL_, 2, 2); break;                                              \
+      case 24: RVO_CORR_LAUNCH(NL_, 2, 4); break;                                              \
+      case 23: RVO_CORR_LAUNCH(NL_, 2, 3); break;                                              \
+      default: RVO_CORR_LAUNCH(NL_, 2, 2); break;                                              \
+    }
+    if (nlevels == 2) { RVO_CORR_PICK(2) } else { RVO_CORR_PICK(1) }
+#undef RVO_CORR_PICK
+#undef RVO_CORR_LAUNCH
     RVO_LAUNCH_CHECK("corr_mma_kernel");
     return RVO_OK;
   }

@@ -488,56 +488,62 @@ __device__ __forceinline__ void retr_se3(const float* xi, float* t, float* q) {
   q[0] = q1[0]; q[1] = q1[1]; q[2] = q1[2]; q[3] = q1[3];
 }
 
-// One CTA.  A = (n+1) x (n+1) lower-triangular workspace (shared memory, or global scratch when
-// the window is too large): rows 0..n-1 hold S, row n holds y^T.  Right-looking Cholesky; row n
-// comes out as z = L^-1 y, then L^T dX = z by back substitution (ba_cuda.cu:558-562).
+// One CTA of (32 x TY) threads.  A = (n+1) x (n+1) lower-triangular workspace (shared memory, or
+// global scratch when the window is too large): rows 0..n-1 hold S, row n holds y^T.
+// Right-looking Cholesky with a 2-D thread mapping (x: column, y: row — no integer division in the
+// trailing update); row n comes out as z = L^-1 y, then one warp solves L^T dX = z
+// (ba_cuda.cu:558-562) with warp-level synchronisation only.
 __global__ void __launch_bounds__(1024)
 ba_solve_kernel(const float* __restrict__ Sy, int N, int t0, float* __restrict__ poses,
                 float* __restrict__ dX_g, float* __restrict__ A_g) {
   extern __shared__ float sm[];
-  const int n = 6 * N, ld = n + 1, la = n + 1;
-  float* A = A_g ? A_g : sm;                              // [(n+1)][(n+1)]
-  float* diag = A_g ? sm : sm + (size_t)(n + 1) * la;     // [n]
+  const int n = 6 * N, ld = n + 1;
+  const int la = (n + 1) | 1;                              // odd row stride: conflict-free columns
+  float* A = A_g ? A_g : sm;                              // [(n+1)][la]
+  float* diag = A_g ? sm : sm + (size_t)(n + 1) * la;     // [n]  1 / L[j][j]
   float* x = diag + n;                                    // [n]
-  const int T = blockDim.x, tid = threadIdx.x;
-  for (int t = tid; t < (n + 1) * la; t += T) {
-    const int r = t / la, c = t - r * la;
-    float v = 0.0f;
-    if (r < n && c <= r) {
-      v = Sy[(size_t)r * ld + c];
-      if (r == c) v = v + (1e-4f * v + 1.0f);             // S += I * (1e-4 * S + 1)
-    } else if (r == n && c < n) {
-      v = Sy[(size_t)c * ld + n];
+  const int tx = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
+  const int tid = ty * 32 + tx;
+  for (int r = ty; r <= n; r += TY)
+    for (int c = tx; c <= r && c < n; c += 32) {
+      float v;
+      if (r < n) {
+        v = Sy[(size_t)r * ld + c];
+        if (r == c) v = v + (1e-4f * v + 1.0f);           // S += I * (1e-4 * S + 1)
+      } else {
+        v = Sy[(size_t)c * ld + n];
+      }
+      A[(size_t)r * la + c] = v;
     }
-    A[t] = v;
-  }
   __syncthreads();
   for (int j = 0; j < n; j++) {
     const float d = sqrtf(A[(size_t)j * la + j]);
     const float inv = 1.0f / d;
-    for (int i = j + 1 + tid; i <= n; i += T) A[(size_t)i * la + j] *= inv;
-    if (tid == 0) diag[j] = d;
+    for (int i = j + 1 + tid; i <= n; i += 32 * TY) A[(size_t)i * la + j] *= inv;
+    if (tid == 0) diag[j] = inv;
     __syncthreads();
-    const int mk = n - 1 - j;          // trailing columns j+1 .. n-1
-    const int mr = n - j;              // trailing rows    j+1 .. n
-    for (int t = tid; t < mr * mk; t += T) {
-      const int i = j + 1 + t / mk, k = j + 1 + t % mk;
-      if (k <= i) A[(size_t)i * la + k] -= A[(size_t)i * la + j] * A[(size_t)k * la + j];
+    for (int i = j + 1 + ty; i <= n; i += TY) {
+      const float lij = A[(size_t)i * la + j];
+      const int kmax = i < n - 1 ? i : n - 1;
+      for (int k = j + 1 + tx; k <= kmax; k += 32)
+        A[(size_t)i * la + k] -= lij * A[(size_t)k * la + j];
     }
     __syncthreads();
   }
-  // back substitution on z = A[n][:]
-  float* z = A + (size_t)n * la;
-  for (int j = n - 1; j >= 0; j--) {
-    if (tid == 0) x[j] = z[j] / diag[j];
-    __syncthreads();
-    const float xj = x[j];
-    for (int i = tid; i < j; i += T) z[i] -= A[(size_t)j * la + i] * xj;
-    __syncthreads();
+  // back substitution on z = A[n][:], one warp
+  if (ty == 0) {
+    float* z = A + (size_t)n * la;
+    for (int j = n - 1; j >= 0; j--) {
+      const float xj = z[j] * diag[j];
+      for (int i = tx; i < j; i += 32) z[i] -= A[(size_t)j * la + i] * xj;
+      if (tx == 0) x[j] = xj;
+      __syncwarp();
+    }
   }
-  for (int t = tid; t < n; t += T) dX_g[t] = x[t];
+  __syncthreads();
+  for (int t = tid; t < n; t += 32 * TY) dX_g[t] = x[t];
   // pose retraction T <- Exp(dX) T  (ba_cuda.cu:178-206)
-  for (int i = tid; i < N; i += T) {
+  for (int i = tid; i < N; i += 32 * TY) {
     float* pp = poses + (size_t)(t0 + i) * 7;
     float t[3] = {pp[0], pp[1], pp[2]}, q[4] = {pp[3], pp[4], pp[5], pp[6]};
     float xi[6];
@@ -591,7 +597,7 @@ struct BaWs {
 constexpr size_t kSmemMax = 227 * 1024;
 
 static inline size_t solve_smem_bytes(int n6) {
-  return ((size_t)(n6 + 1) * (n6 + 1) + 2 * (size_t)n6) * sizeof(float);
+  return ((size_t)(n6 + 1) * ((n6 + 1) | 1) + 2 * (size_t)n6) * sizeof(float);
 }
 static inline size_t assemble_smem_bytes(int n6, bool smem_s) {
   return ((smem_s ? (size_t)n6 * (n6 + 1) : 0) + 2 * (size_t)kBaWarps * n6 + kBaWarps) *
@@ -611,7 +617,7 @@ static BaWs ba_layout(void* base, int E, int64_t cap, int n_free) {
   w.Qg = (float*)take(cp * sizeof(float));
   w.ug = (float*)take(cp * sizeof(float));
   w.Eg = (float*)take(cp * n6 * sizeof(float));
-  w.A = (float*)take(solve_smem_bytes((int)n6) > kSmemMax ? (n6 + 1) * (n6 + 1) * sizeof(float) : 0);
+  w.A = (float*)take(solve_smem_bytes((int)n6) > kSmemMax ? (n6 + 1) * ((n6 + 1) | 1) * sizeof(float) : 0);
   w.total = off;
   return w;
 }
@@ -660,7 +666,7 @@ static int ba_solve(const BaWs& w, float* poses, float* patches, const float* Sy
     const size_t smem = in_smem ? solve_smem_bytes(n6) : 2 * (size_t)n6 * sizeof(float);
     RVO_CUDA(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)kSmemMax));
-    const int threads = n6 <= 64 ? 256 : 1024;
+    const dim3 threads(32, n6 <= 64 ? 8 : (n6 <= 128 ? 16 : 32));
     ba_solve_kernel<<<1, threads, smem, st>>>(Sy, N, t0, poses, w.dX, in_smem ? nullptr : w.A);
     RVO_LAUNCH_CHECK("ba_solve_kernel");
   }

@@ -1,0 +1,178 @@
+"""RAMP encoders (ramp/extractor.py) — same parameter tree as the reference so its checkpoints load
+unchanged (state-dict keys are the compatibility surface), forward pass
+restructured for one (event voxel, image) pair per call:
+
+  * the per-pixel nn.LSTM of LSTMEncoder (extractor.py:351-381) sees sequences of length 1 with a
+    zero initial state (MultiScale never passes `hx`, :378), i.e. it is the gated map
+        h = sigmoid(o) * tanh(sigmoid(i) * tanh(g)),  [i,f,g,o] = W_ih x + b_ih + b_hh,
+    applied per pixel; no permute/contiguous round trips, no cuDNN RNN launch with batch = H*W;
+  * everything runs channels-last (NHWC) so the fmap lands directly in the layout the altcorr
+    tensor-core path reads, and the level-2 pyramid entry is produced with it;
+  * the dense 3x3 / 7x7 convolutions currently go through cuDNN (library GEMMs; the hand-written
+    tcgen05 implicit-GEMM path is the next step of DESIGN.md section "encoder").
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+DIM = 32
+
+
+class ResidualBlock(nn.Module):
+    """extractor.py:8-57 (only the norms the hot path selects: 'instance' and 'none')."""
+
+    def __init__(self, in_planes, planes, norm_fn='instance', stride=1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_planes, planes, kernel_size=3, padding=1, stride=stride)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, padding=1)
+        self.instance = norm_fn == 'instance'
+        if norm_fn not in ('instance', 'none'):
+            raise NotImplementedError("norm_fn %r: the RAMP encoders use 'instance' / 'none'" % norm_fn)
+        self.downsample = None
+        if stride != 1:
+            # reference: Sequential(Conv2d 1x1 stride, norm3); InstanceNorm2d has no parameters
+            self.downsample = nn.Sequential(nn.Conv2d(in_planes, planes, kernel_size=1, stride=stride))
+
+    def _norm(self, x):
+        return F.instance_norm(x) if self.instance else x
+
+    def forward(self, x):
+        y = F.relu(self._norm(self.conv1(x)))
+        y = F.relu(self._norm(self.conv2(y)))
+        if self.downsample is not None:
+            x = self._norm(self.downsample(x))
+        return F.relu(x + y)
+
+
+class MultiScaleBasicEncoder4(nn.Module):
+    """extractor.py:272-311 on top of BasicEncoder4 (:60-130).  `layer2` / `conv2` are created by
+    the reference's double __init__ (:276-277) and never used; they are kept so that checkpoints
+    load with strict=True."""
+
+    def __init__(self, output_dim=128, norm_fn='instance', channel_dim=16, internal_input_dimensions=None):
+        super().__init__()
+        self.instance = norm_fn == 'instance'
+        dims = internal_input_dimensions or [channel_dim] * 3
+        self.conv1 = nn.Conv2d(channel_dim, DIM, kernel_size=7, stride=2, padding=3)
+        self.layer1 = nn.Sequential(ResidualBlock(DIM, DIM, norm_fn, 1), ResidualBlock(DIM, DIM, norm_fn, 1))
+        self.layer2 = nn.Sequential(ResidualBlock(DIM, 2 * DIM, norm_fn, 2),
+                                    ResidualBlock(2 * DIM, 2 * DIM, norm_fn, 1))   # dead weights
+        self.conv2 = nn.Conv2d(2 * DIM, 128, kernel_size=1)                          # dead weights
+        c3 = DIM + dims[1]
+        self.layer3 = nn.Sequential(ResidualBlock(c3, 2 * DIM, norm_fn, 2),
+                                    ResidualBlock(2 * DIM, 2 * DIM, norm_fn, 1))
+        self.conv3 = nn.Conv2d(2 * DIM + dims[2], output_dim, kernel_size=1)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+
+    def forward(self, x, x_down2, x_down4):
+        """x [1,16,H,W], x_down2 [1,32,H/2,W/2], x_down4 [1,64,H/4,W/4] -> [1,out,H/4,W/4]."""
+        x = self.conv1(x)
+        if self.instance:
+            x = F.instance_norm(x)
+        x = F.relu(x)
+        x = self.layer1(x)
+        x = self.layer3(torch.cat((x, x_down2), dim=1))
+        return self.conv3(torch.cat((x, x_down4), dim=1))
+
+
+class LSTMEncoder(nn.Module):
+    """extractor.py:314-390: strided conv (k = s+1, stride s, pad 1; 1x1 at s <= 1) followed by the
+    per-pixel LSTM cell evaluated for one step from a zero state."""
+
+    def __init__(self, in_channels, downsample_scale=0, out_channels=15):
+        super().__init__()
+        k, s, p = downsample_scale + 1, downsample_scale, 1
+        if downsample_scale <= 1:
+            k, s, p = 1, 1, 0
+        self.hidden = out_channels
+        self.conv_1 = nn.Conv2d(in_channels, in_channels, kernel_size=k, stride=s, padding=p)
+        self.convlstm = nn.LSTM(input_size=in_channels, hidden_size=out_channels, batch_first=True)
+
+    def forward(self, x):
+        """x [1,C,H,W] -> h [1,hidden,H/s,W/s]"""
+        x = self.conv_1(x)
+        w = self.convlstm.weight_ih_l0                       # [4h, C], gate order i, f, g, o
+        b = self.convlstm.bias_ih_l0 + self.convlstm.bias_hh_l0
+        gates = F.conv2d(x, w[:, :, None, None].to(x.dtype), b.to(x.dtype))
+        i, _, g, o = gates.float().chunk(4, dim=1)
+        c = torch.sigmoid(i) * torch.tanh(g)
+        return (torch.sigmoid(o) * torch.tanh(c)).to(x.dtype)
+
+
+class SuperStateEncoder(nn.Module):
+    """extractor.py:393-412: 1x1 conv over cat(previous super state, new embedding)."""
+
+    def __init__(self, kernel_size, out_channels=15, norm_superstate=False):
+        super().__init__()
+        self.encoder = nn.Conv2d(2 * out_channels, out_channels, kernel_size=kernel_size,
+                                 padding=(kernel_size - 1) // 2)
+        self.norm_superstate = norm_superstate
+
+    def forward(self, data, prev_super_state=None):
+        if prev_super_state is None:
+            prev_super_state = torch.zeros_like(data)
+        return self.encoder(torch.cat((prev_super_state, data), dim=1))
+
+
+class MultiScaleMergerDoubleNet(nn.Module):
+    """extractor.py:468-566.  Keeps one recurrent super state per scale across calls (the only
+    cross-frame recurrence of the MultiScale encoder)."""
+
+    def __init__(self, evs_ch_dim, img_ch_dim, lstm_dim=16, output_dim_f=128, output_dim_i=384,
+                 norm_fn_fmap="instance", norm_fn_imap="none", kernel_size_superstate=1,
+                 norm_superstate=False):
+        super().__init__()
+        self.scales = [1, 2, 4]
+        self.ev_encoders = nn.ModuleList()
+        self.im_encoders = nn.ModuleList()
+        self.super_state_ev_encoder = nn.ModuleList()
+        self.super_state_im_encoders = nn.ModuleList()
+        dims = []
+        for s in self.scales:
+            h = lstm_dim * s
+            dims.append(h)
+            self.ev_encoders.append(LSTMEncoder(evs_ch_dim, s, h))
+            self.im_encoders.append(LSTMEncoder(img_ch_dim, s, h))
+            self.super_state_ev_encoder.append(SuperStateEncoder(kernel_size_superstate, h, norm_superstate))
+            self.super_state_im_encoders.append(SuperStateEncoder(kernel_size_superstate, h, norm_superstate))
+        self.super_states = [None, None, None]
+        self.norm_superstate = norm_superstate
+        self.fmap_encoder = MultiScaleBasicEncoder4(output_dim_f, norm_fn_fmap, lstm_dim, dims)
+        self.imap_encoder = MultiScaleBasicEncoder4(output_dim_i, norm_fn_imap, lstm_dim, dims)
+
+    def reset_state(self):
+        self.super_states = [None, None, None]
+
+    def forward(self, events, images, mask, reinit_hidden=False):
+        """events [1,T,Ce,H,W], images [1,Ti,3,H,W], mask [T] bool (one image per True entry)
+        -> fmap [1,n,128,H/4,W/4], imap [1,n,384,H/4,W/4] with n = number of images consumed
+        (n = 1 with the states of the last event voxel when no image arrived, extractor.py:455)."""
+        ev = events[0].contiguous(memory_format=torch.channels_last)
+        im = images[0].contiguous(memory_format=torch.channels_last)
+        mask = torch.as_tensor(mask).reshape(-1).tolist()
+        per_scale = []
+        for k in range(3):
+            if reinit_hidden:
+                self.super_states[k] = None
+            he = self.ev_encoders[k](ev)                 # [T,h,H/s,W/s]
+            hi = self.im_encoders[k](im)
+            ss = self.super_states[k]
+            outs, n_im = [], 0
+            for t in range(he.shape[0]):
+                ss = self.super_state_ev_encoder[k](he[t:t + 1], ss)
+                if mask[t]:
+                    ss = self.super_state_im_encoders[k](hi[n_im:n_im + 1], ss)
+                    n_im += 1
+                    outs.append(ss)
+            allss = torch.cat(outs, 0) if outs else ss
+            if self.norm_superstate:
+                allss = F.instance_norm(allss)
+            # the reference carries `norm_super_states[None]` and squeezes it on the next call
+            # (extractor.py:440-441,560): with one image per call that is the last state
+            self.super_states[k] = allss[-1:] if allss.shape[0] > 1 else allss
+            per_scale.append(allss)
+        fmap = self.fmap_encoder(per_scale[0], per_scale[1], per_scale[2])
+        imap = self.imap_encoder(per_scale[0], per_scale[1], per_scale[2])
+        return fmap[None], imap[None]

@@ -1,0 +1,210 @@
+"""Drop-in for ramp.net (ramp/net.py): VONet with `.patchify` (Patchifier) and `.update` (Update).
+
+Parameter names match the reference so that its checkpoints load unchanged.  The forward passes are
+restructured around the B200 kernels of librampvo_b200.so:
+
+  Update.forward    neighbours come from the device-side graph plan (no CPU round trip,
+                    ramp/fastba/ba.cpp:59-97), the two SoftAgg blocks are one segmented pass each
+                    over pre-grouped edges (no torch.unique / torch_scatter, ramp/blocks.py:42-48);
+                    the hidden state stays fp32 between stages like the reference under autocast
+                    (LayerNorm returns fp32, SURVEY.md appendix "dtype drift").
+  Patchifier        patch selection + the four altcorr.patchify gathers with the bilinear blend
+                    fused; gmap is written straight into the caller's channels-last ring slot.
+The dense Linear layers currently run on cuBLAS (library GEMMs).
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, altcorr, fastba
+from .extractor import MultiScaleMergerDoubleNet
+from .vo_utils import coords_from_topk_events, get_channel_dim
+
+DIM = 384
+
+
+class GatedResidual(nn.Module):
+    """ramp/blocks.py:15-31: x + sigmoid(W_g x) * W_2 relu(W_1 x)"""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.gate = nn.Sequential(nn.Linear(dim, dim), nn.Sigmoid())
+        self.res = nn.Sequential(nn.Linear(dim, dim), nn.ReLU(inplace=True), nn.Linear(dim, dim))
+
+    def forward(self, x):
+        return x + self.gate(x) * self.res(x)
+
+
+class SoftAgg(nn.Module):
+    """ramp/blocks.py:33-50 parameters; the aggregation itself is Update._soft_agg."""
+
+    def __init__(self, dim=512, expand=True):
+        super().__init__()
+        self.dim = dim
+        self.expand = expand
+        self.f = nn.Linear(dim, dim)
+        self.g = nn.Linear(dim, dim)
+        self.h = nn.Linear(dim, dim)
+
+
+class GraphPlans:
+    """Device-side bookkeeping shared by one update: the (kk, jj) plan gives `neighbors` and the
+    agg_kk groups, the (ii*12345+jj) plan gives the agg_ij groups (net.py:77,84-85)."""
+
+    def __init__(self, ii, jj, kk, kmax=0, jmax=0):
+        L = _lib.lib()
+        self.E = E = ii.numel()
+        dev = ii.device
+        nb = L.rvo_plan_bytes(E)
+        self.plan_k = torch.empty(nb, dtype=torch.uint8, device=dev)
+        self.plan_ij = torch.empty(nb, dtype=torch.uint8, device=dev)
+        self.ix = torch.empty(E, dtype=torch.int64, device=dev)
+        self.jx = torch.empty(E, dtype=torch.int64, device=dev)
+        if E == 0:
+            return
+        key_ij = ii * 12345 + jj
+        st = _lib.stream_ptr(dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.rvo_graph_plan(_lib.ptr(kk), _lib.ptr(jj), E, kmax, jmax, _lib.ptr(self.plan_k),
+                                        nb, st), "rvo_graph_plan")
+            _lib.check(L.rvo_plan_neighbors(_lib.ptr(self.plan_k), E, _lib.ptr(self.ix),
+                                            _lib.ptr(self.jx), st), "rvo_plan_neighbors")
+            _lib.check(L.rvo_graph_plan(_lib.ptr(key_ij), _lib.ptr(jj), E, (jmax * 12345 + jmax) if jmax else 0,
+                                        jmax, _lib.ptr(self.plan_ij), nb, st), "rvo_graph_plan")
+
+
+class Update(nn.Module):
+    """ramp/net.py:34-90."""
+
+    def __init__(self, p):
+        super().__init__()
+        self.c1 = nn.Sequential(nn.Linear(DIM, DIM), nn.ReLU(inplace=True), nn.Linear(DIM, DIM))
+        self.c2 = nn.Sequential(nn.Linear(DIM, DIM), nn.ReLU(inplace=True), nn.Linear(DIM, DIM))
+        self.norm = nn.LayerNorm(DIM, eps=1e-3)
+        self.agg_kk = SoftAgg(DIM)
+        self.agg_ij = SoftAgg(DIM)
+        self.gru = nn.Sequential(nn.LayerNorm(DIM, eps=1e-3), GatedResidual(DIM),
+                                 nn.LayerNorm(DIM, eps=1e-3), GatedResidual(DIM))
+        self.corr = nn.Sequential(nn.Linear(2 * 49 * p * p, DIM), nn.ReLU(inplace=True),
+                                  nn.Linear(DIM, DIM), nn.LayerNorm(DIM, eps=1e-3),
+                                  nn.ReLU(inplace=True), nn.Linear(DIM, DIM))
+        # reference: Sequential(ReLU, Linear, GradientClip[, Sigmoid]); GradientClip is identity in forward
+        self.d = nn.Sequential(nn.ReLU(inplace=False), nn.Linear(DIM, 2), nn.Identity())
+        self.w = nn.Sequential(nn.ReLU(inplace=False), nn.Linear(DIM, 2), nn.Identity(), nn.Sigmoid())
+
+    @staticmethod
+    def _soft_agg(agg, net, plan, E):
+        """net += h( sum_g f(x) * softmax_g(g(x)) )[group]  (blocks.py:42-48, net.py:84-85)"""
+        L = _lib.lib()
+        x = net[0]
+        fx = agg.f(x).contiguous()
+        gx = agg.g(x).contiguous()
+        y = torch.zeros(E, x.shape[1], dtype=fx.dtype, device=x.device)   # rows >= #groups stay 0
+        st = _lib.stream_ptr(x.device)
+        _lib.check(L.rvo_softagg(_lib.ptr(fx), _lib.ptr(gx), _lib.dtype_code(fx), _lib.ptr(plan), E,
+                                 x.shape[1], 0, _lib.ptr(y), _lib.dtype_code(y), st), "rvo_softagg")
+        hy = agg.h(y).contiguous()
+        _lib.check(L.rvo_expand_add(_lib.ptr(hy), _lib.dtype_code(hy), _lib.ptr(plan), E, x.shape[1],
+                                    _lib.ptr(x), st), "rvo_expand_add")
+
+    def forward(self, net, inp, corr, flow, ii, jj, kk, plans=None):
+        """net [1,E,384], inp [1,E,384], corr [1,E,882], ii/jj/kk [E] ->
+        (net [1,E,384] fp32, (delta [1,E,2], weight [1,E,2], None)).  `plans` (extension): a
+        GraphPlans built once per graph; built here when omitted."""
+        _lib.require_cuda(net, inp, corr, ii, jj, kk)
+        E = ii.numel()
+        if plans is None:
+            plans = GraphPlans(ii, jj, kk)
+        L = _lib.lib()
+        dev = net.device
+        st = _lib.stream_ptr(dev)
+        with torch.cuda.device(dev):
+            net = net.float() + inp.float() + self.corr(corr).float()
+            net = self.norm(net).float().contiguous()                     # [1,E,384] fp32
+            x = net[0]
+            gdt = torch.float16 if torch.is_autocast_enabled() else torch.float32
+            g = torch.empty(E, DIM, dtype=gdt, device=dev)
+            for mlp, idx in ((self.c1, plans.ix), (self.c2, plans.jx)):
+                _lib.check(L.rvo_gather_rows(_lib.ptr(x), _lib.ptr(idx), E, DIM, _lib.ptr(g),
+                                             _lib.dtype_code(g), st), "rvo_gather_rows")
+                x.add_(mlp(g))
+            self._soft_agg(self.agg_kk, net, plans.plan_k, E)
+            self._soft_agg(self.agg_ij, net, plans.plan_ij, E)
+            net = self.gru(net)
+            return net, (self.d(net), self.w(net), None)
+
+
+class Patchifier(nn.Module):
+    """ramp/net.py:93-203 (MultiScale input mode; event-biased or random patch selection)."""
+
+    def __init__(self, channels_dim, patch_size=3, input_mode="MultiScale"):
+        super().__init__()
+        self.input_mode = input_mode
+        self.P = patch_size
+        if input_mode != "MultiScale":
+            raise NotImplementedError("input_mode %r: only the MultiScale RAMP encoder is built "
+                                      "(BASELINE.json configs[1..4])" % input_mode)
+        evs, img = channels_dim
+        self.encoder = MultiScaleMergerDoubleNet(evs_ch_dim=evs, img_ch_dim=img, lstm_dim=16,
+                                                 output_dim_f=128, output_dim_i=DIM,
+                                                 norm_fn_fmap="instance", norm_fn_imap="none",
+                                                 norm_superstate=False)
+
+    def forward(self, input_, patches_per_image=80, reinit_hidden=False, disps=None, event_bias=False,
+                gradient_bias=False, gmap_out=None):
+        events, images, mask = input_
+        fmap, imap = self.encoder(events=events, images=images, mask=mask, reinit_hidden=reinit_hidden)
+        mask_t = torch.as_tensor(mask).reshape(-1)
+        if not bool(mask_t.any()):
+            return None, None, None, None, None, None
+        events = events[:, mask_t.to(events.device)] if events.shape[1] == mask_t.numel() else events
+        fmap = fmap / 4.0
+        imap = imap / 4.0
+        b, n, c, h, w = fmap.shape
+        dev = fmap.device
+        if event_bias:
+            coords = coords_from_topk_events(events, patches_per_image, non_max_supp_rad=11)
+        else:
+            x = torch.randint(1, w - 1, size=[n, patches_per_image], device=dev)
+            y = torch.randint(1, h - 1, size=[n, patches_per_image], device=dev)
+            coords = torch.stack([x, y], dim=-1).float()
+        P = self.P
+        if gmap_out is not None:
+            gmap = altcorr.patchify(fmap[0], coords, P // 2, out=gmap_out)
+        else:
+            gmap = altcorr.patchify(fmap[0], coords, P // 2).view(b, -1, 128, P, P)
+        imap = altcorr.patchify(imap[0], coords, 0).view(b, -1, DIM, 1, 1)
+        if disps is None:
+            disps = torch.ones(b, n, h, w, device=dev)
+        ys, xs = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float32),
+                                torch.arange(w, device=dev, dtype=torch.float32), indexing="ij")
+        grid = torch.stack([xs.expand(n, h, w), ys.expand(n, h, w), disps[0]], dim=1)   # [n,3,h,w]
+        patches = altcorr.patchify(grid, coords, P // 2).view(b, -1, 3, P, P)
+        index = torch.arange(n, device=dev).view(n, 1).repeat(1, patches_per_image).reshape(-1)
+        clr = altcorr.patchify(images[0].float(), 4 * (coords + 0.5), 0).view(b, -1, 3)
+        return fmap, gmap, imap, patches, index, clr
+
+
+class VONet(nn.Module):
+    """ramp/net.py:232-249 (constructor surface).  `.forward` of the reference is the training
+    unroll (net.py:252-378), which belongs to the training row."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.P = 3
+        self.RES = 4
+        self.DIM = DIM
+        self.EVENT_BIAS = cfg["event_bias"]
+        self.MOTION_MODEL = "DAMPED_LINEAR"
+        self.MOTION_DAMPING = 0.5
+        self.inp_channel_dims = get_channel_dim(cfg)
+        self.input_mode = cfg["input_mode"]
+        self.patchify = Patchifier(channels_dim=self.inp_channel_dims, patch_size=self.P,
+                                   input_mode=self.input_mode)
+        self.update = Update(self.P)
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("VONet.forward (training unroll, ramp/net.py:252-378) is not built: "
+                                  "this package covers the online tracking path (Ramp_vo)")

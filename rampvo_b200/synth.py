@@ -97,3 +97,46 @@ def make_features(n_frames_ring, n_patches_ring, C=128, ht=120, wd=160, P=3, see
     pyr = [(rng.standard_normal((n_frames_ring, ht // l, wd // l, C), dtype=np.float32) * s).astype(dtype)
            for l in levels]
     return gmap, pyr
+
+
+class SyntheticSequence:
+    """TartanEvent-shaped synthetic stream: per call one 5-bin event stack
+    [1,1,5,H,W] (integer-valued fp32, ~10 % non-zero, utils/transformers.py:149-161) and one image
+    [1,1,3,H,W] in [-0.5,1.5] (ramp/utils.py:582): a smooth random texture translated a few px per
+    frame, with the event rate following the texture gradient so top-k/NMS spreads the patches."""
+
+    def __init__(self, ht=480, wd=640, seed=0, device="cpu", shift=(3.0, 1.5)):
+        import torch
+        import torch.nn.functional as F
+        self.torch, self.F = torch, F
+        self.ht, self.wd, self.device = ht, wd, device
+        self.shift = shift
+        g = torch.Generator().manual_seed(seed)
+        pad = 256
+        low = torch.rand(1, 3, (ht + 2 * pad) // 16, (wd + 2 * pad) // 16, generator=g)
+        self.canvas = F.interpolate(low, size=(ht + 2 * pad, wd + 2 * pad), mode="bicubic",
+                                    align_corners=False).clamp(0, 1).to(device)
+        self.pad = pad
+        self.gen = torch.Generator(device=device).manual_seed(seed + 1)
+        self.intrinsics = torch.tensor([320.0, 320.0, 320.0, 240.0])   # evaluate.py:48
+
+    def frame(self, t):
+        torch, F = self.torch, self.F
+        dx, dy = self.shift[0] * t, self.shift[1] * t
+        x0 = int(self.pad + (dx % self.pad) * (1 if (int(dx) // self.pad) % 2 == 0 else -1))
+        y0 = int(self.pad + (dy % self.pad) * (1 if (int(dy) // self.pad) % 2 == 0 else -1))
+        x0 = max(0, min(x0, self.canvas.shape[-1] - self.wd))
+        y0 = max(0, min(y0, self.canvas.shape[-2] - self.ht))
+        img = self.canvas[:, :, y0:y0 + self.ht, x0:x0 + self.wd]
+        image = (2.0 * img - 0.5)[None]                                   # [1,1,3,H,W]
+        gray = img.mean(1, keepdim=True)
+        gx = F.pad(gray[..., :, 1:] - gray[..., :, :-1], (0, 1))
+        gy = F.pad(gray[..., 1:, :] - gray[..., :-1, :], (0, 0, 0, 1))
+        rate = (gx.abs() + gy.abs())
+        rate = 0.12 * rate / rate.mean().clamp(min=1e-6)
+        lam = rate.expand(1, 5, self.ht, self.wd).contiguous()
+        ev = torch.poisson(lam, generator=self.gen)
+        sign = torch.randint(0, 2, ev.shape, generator=self.gen, device=self.device) * 2 - 1
+        events = (ev * sign).clamp(-127, 127)[None]                        # [1,1,5,H,W]
+        mask = torch.tensor([True])
+        return events, image, mask

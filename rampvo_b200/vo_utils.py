@@ -1,0 +1,69 @@
+"""The hot-path helpers of ramp/utils.py (the rest of that file — losses, plotting, pose-file I/O —
+is out of scope).  Small tensor plumbing; stays in PyTorch."""
+import torch
+import torch.nn.functional as F
+
+
+def get_channel_dim(cfg):
+    """ramp/utils.py:244-245"""
+    return (cfg["num_event_bins"], 3)
+
+
+def check_input_tensors(events, images):
+    """ramp/utils.py:229-241: 5-D [batch, n, C, H, W], batch 1."""
+    if events.dim() != images.dim():
+        raise AssertionError("Event and image tensor must have the same number of dimension")
+    if events.dim() != 5:
+        raise AssertionError("Event and image tensor must have shape [batch, n_tensors, channels, height, width]")
+    if not (events.shape[0] == 1 and images.shape[0] == 1):
+        raise NotImplementedError("Event and image tensor must have batch dimension (0 dim) = 1")
+
+
+def preprocess_input(input_tensor):
+    """ramp/utils.py:250-256 (a 2-tuple leaves `mask` undefined there; it is an error here too)."""
+    if len(input_tensor) != 3:
+        raise ValueError("input_tensor must be (events, images, mask)")
+    events, images, mask = input_tensor
+    check_input_tensors(events, images)
+    return events, images, mask
+
+
+def nms_image(x, kernel_size=3):
+    """ramp/utils.py:157-183: keep values equal to their (k x k) neighbourhood maximum."""
+    mx = F.max_pool2d(x[None], kernel_size, stride=1, padding=(kernel_size - 1) // 2)[0]
+    return x * (mx == x).float()
+
+
+def coords_from_topk_events(events, patches_per_image, border_suppression_size=0, non_max_supp_rad=0):
+    """ramp/utils.py:186-226 (get_coords_from_topk_events).  events [1,n,C,H,W] -> coords [n,M,2].
+    The map is transposed to (x, y) order and the flat top-k index is split with a TRUE division
+    (utils.py:212), so x = x_int + y/H' is fractional while y is integral — preserved as is."""
+    ev = torch.abs(events.squeeze(0))
+    ev = F.avg_pool2d(ev, 4, 4).transpose(3, 2)
+    ev_mean = torch.mean(ev, dim=1)                      # [n, W', H']
+    b = border_suppression_size
+    if b != 0:
+        ev_mean[:, :b, :] = 0
+        ev_mean[:, -b:, :] = 0
+        ev_mean[:, :, :b] = 0
+        ev_mean[:, :, -b:] = 0
+    if non_max_supp_rad != 0:
+        ev_mean = nms_image(ev_mean, kernel_size=non_max_supp_rad)
+    flat = torch.flatten(ev_mean, start_dim=1)
+    _, indices = torch.topk(flat, k=patches_per_image, dim=-1)
+    rows = indices / ev_mean.shape[-1]
+    cols = indices % ev_mean.shape[-1]
+    return torch.stack((rows, cols.to(rows.dtype)), dim=-1)
+
+
+def flatmeshgrid(*args, **kwargs):
+    """ramp/utils.py:104-106"""
+    return (x.reshape(-1) for x in torch.meshgrid(*args, **kwargs))
+
+
+def filter_features(confidences, target, data_shape):
+    """ramp/utils.py:557-570: zero the weights of targets outside [0,wd] x [0,ht]."""
+    ht, wd = data_shape
+    x, y = target[..., 0], target[..., 1]
+    bad = (x < 0) | (x > wd) | (y < 0) | (y > ht)
+    return confidences * (~bad)[..., None].to(confidences.dtype)

@@ -1,0 +1,66 @@
+"""Seeded inputs shared by tests/golden/make_golden.py (which feeds them to the reference's Python
+code) and by the tests (which feed them to the oracle / the CUDA path)."""
+import numpy as np
+import torch
+
+from rampvo_b200 import synth
+from tests.util import perturb_poses, targets_from_reprojection
+
+UPDATE_SEED = 1234      # evaluate.py:40 seeds everything with 1234
+ENCODER_SEED = 1234
+
+
+def as_torch(prob, dtype=torch.float32, device="cpu"):
+    t = {k: torch.from_numpy(prob[k]).to(device) for k in ("ii", "jj", "kk")}
+    t["poses"] = torch.from_numpy(prob["poses"]).to(device=device, dtype=dtype)[None]
+    t["patches"] = torch.from_numpy(prob["patches"]).to(device=device, dtype=dtype)[None]
+    t["intrinsics"] = torch.from_numpy(prob["intrinsics"]).to(device=device, dtype=dtype)[None]
+    return t
+
+
+def pops_problem():
+    return synth.make_problem("cfg1", 8, seed=31)
+
+
+def ba_problem(oracle):
+    """Benign graph (every edge in bounds, poses 0..3 fixed) so that ramp/ba.py and cuda_ba agree."""
+    prob = synth.make_problem("cfg1", 8, seed=32, noise_px=0.5)
+    prob["t0"] = 4
+    tgt = targets_from_reprojection(prob, oracle)
+    prob["poses"] = perturb_poses(prob, sigma_t=0.005, sigma_r=0.002)
+    return prob, tgt
+
+
+def update_graph():
+    synth.CONFIGS["tiny"] = (6, 4, 6, 3)
+    ii, jj, kk = synth.replay_graph(6, 4, 6, 7)
+    return ii, jj, kk
+
+
+def update_inputs(device="cpu"):
+    ii, jj, kk = update_graph()
+    E = len(ii)
+    g = torch.Generator().manual_seed(77)
+    out = dict(net=0.5 * torch.randn(1, E, 384, generator=g), inp=0.5 * torch.randn(1, E, 384, generator=g),
+               corr=0.3 * torch.randn(1, E, 882, generator=g), ii=torch.from_numpy(ii),
+               jj=torch.from_numpy(jj), kk=torch.from_numpy(kk))
+    return {k: v.to(device) for k, v in out.items()}
+
+
+def encoder_inputs(device="cpu", ht=64, wd=96):
+    g = torch.Generator().manual_seed(78)
+    frames = []
+    for _ in range(2):
+        ev = torch.poisson(torch.full((1, 1, 5, ht, wd), 0.3), generator=g)
+        ev = ev * (torch.randint(0, 2, ev.shape, generator=g) * 2 - 1)
+        im = torch.rand(1, 1, 3, ht, wd, generator=g) * 2 - 0.5
+        frames.append((ev.to(device), im.to(device)))
+    return frames
+
+
+def selection_events(device="cpu"):
+    g = torch.Generator().manual_seed(79)
+    ev = torch.poisson(torch.full((1, 1, 5, 480, 640), 0.12), generator=g)
+    ys, xs = torch.meshgrid(torch.arange(480.0), torch.arange(640.0), indexing="ij")
+    blob = torch.exp(-((xs - 300) ** 2 + (ys - 200) ** 2) / (2 * 150.0 ** 2))
+    return (ev * (0.25 + blob)).to(device)

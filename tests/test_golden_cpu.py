@@ -1,0 +1,84 @@
+"""CPU: the oracle and the host-side modules against fixtures produced by the reference's own Python
+code (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import ref_ops as O
+from tests import golden_inputs as GI
+from tests.util import rel_err
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_oracle_transform_matches_reference_pops():
+    z = np.load(os.path.join(G, "pops_transform.npz"))
+    prob = GI.pops_problem()
+    a = (prob["poses"], prob["patches"], prob["intrinsics"], prob["ii"], prob["jj"], prob["kk"])
+    c, v, (Ji, Jj, Jz) = O.transform(*a, jacobian=True)
+    np.testing.assert_allclose(c, z["coords"], rtol=0, atol=1e-9)
+    assert (v == z["valid"]).all()
+    for got, key in ((Ji, "Ji"), (Jj, "Jj"), (Jz, "Jz")):
+        np.testing.assert_allclose(got, z[key], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(O.transform(*a, tonly=True)[0], z["coords_tonly"], atol=1e-9)
+    np.testing.assert_allclose(O.flow_mag(*a, beta=0.5), z["flow_mag"], atol=1e-9)
+    ix = np.arange(prob["patches"].shape[0]) // prob["M"]
+    np.testing.assert_allclose(O.point_cloud_centers(prob["poses"], prob["patches"], prob["intrinsics"], ix),
+                               z["points"], rtol=1e-9, atol=1e-9)
+
+
+def test_oracle_ba_matches_reference_python_ba():
+    """ramp/ba.py (ep=1, first 4 poses fixed) and the cuda_ba restatement are the same solver on an
+    in-bounds graph (SURVEY.md section 8c lists where they differ: gates, clamps, damping)."""
+    z = np.load(os.path.join(G, "python_ba.npz"))
+    prob, tgt = GI.ba_problem(O)
+    for it in (1, 2):
+        p, q = O.ba(prob["poses"], prob["patches"], prob["intrinsics"], tgt, prob["weight"], 1e-4,
+                    prob["ii"], prob["jj"], prob["kk"], prob["t0"], prob["t1"], iterations=it)
+        # ramp/ba.py goes through lietorch (normalised quaternions), cuda_ba does not: 1e-6
+        assert rel_err(p, z["poses_%d" % it]) < 1e-6
+        assert rel_err(q[:, 2, 0, 0], z["disps_%d" % it]) < 1e-6
+
+
+def test_encoder_matches_reference_on_cpu():
+    """rampvo_b200.extractor (restructured forward, same parameter tree) vs ramp/extractor.py, fp32."""
+    from rampvo_b200.extractor import MultiScaleMergerDoubleNet
+    z = np.load(os.path.join(G, "encoder.npz"))
+    torch.manual_seed(GI.ENCODER_SEED)
+    enc = MultiScaleMergerDoubleNet(5, 3).eval()
+    frames = GI.encoder_inputs()
+    with torch.no_grad():
+        for f, (ev, im) in enumerate(frames):
+            fmap, imap = enc(events=ev, images=im, mask=torch.tensor([True]), reinit_hidden=(f == 0))
+            assert fmap.shape == (1, 1, 128, 16, 24) and imap.shape == (1, 1, 384, 16, 24)
+            assert rel_err(fmap[0, 0].numpy(), z["fmap_%d" % f]) < 1e-4
+            assert rel_err(imap[0, 0].numpy(), z["imap_%d" % f]) < 1e-4
+        enc(events=frames[0][0], images=frames[0][1], mask=torch.tensor([False]))
+        fmap, _ = enc(events=frames[1][0], images=frames[1][1], mask=torch.tensor([True]))
+        assert rel_err(fmap[0, 0].numpy(), z["fmap_after_events_only"]) < 1e-4
+
+
+def test_patch_selection_matches_reference():
+    from rampvo_b200.vo_utils import coords_from_topk_events
+    z = np.load(os.path.join(G, "patch_selection.npz"))
+    c = coords_from_topk_events(GI.selection_events(), 96, non_max_supp_rad=11)
+    assert c.shape == (1, 96, 2)
+    assert (c.numpy() == z["coords"]).all()
+    assert (c[..., 0] != c[..., 0].floor()).any()       # the fractional-x quirk of utils.py:212
+
+
+def test_state_dict_keys_match_reference_checkpoint_layout():
+    from rampvo_b200.net import VONet
+    net = VONet({"event_bias": True, "input_mode": "MultiScale", "num_event_bins": 5})
+    keys = set(net.state_dict().keys())
+    for k in ("patchify.encoder.ev_encoders.2.convlstm.weight_hh_l0",
+              "patchify.encoder.super_state_im_encoders.0.encoder.bias",
+              "patchify.encoder.fmap_encoder.layer2.0.downsample.0.weight",   # dead weights kept
+              "patchify.encoder.imap_encoder.conv2.bias",
+              "patchify.encoder.fmap_encoder.layer3.0.downsample.0.weight",
+              "update.corr.0.weight", "update.corr.3.bias", "update.gru.1.res.2.weight",
+              "update.agg_ij.h.bias", "update.c2.2.weight", "update.d.1.weight", "update.w.1.bias"):
+        assert k in keys, k
+    n_enc = sum(v.numel() for k, v in net.state_dict().items() if k.startswith("patchify"))
+    assert n_enc == 844766

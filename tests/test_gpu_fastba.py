@@ -95,7 +95,7 @@ def test_ba_masks_and_fixed_window():
     pe, qe = O.ba(prob["poses"], prob["patches"], prob["intrinsics"], tgt, prob["weight"], 1e-4,
                   prob["ii"], prob["jj"], prob["kk"], prob["t0"], prob["t1"], iterations=2)
     assert np.isfinite(p).all() and rel_err(p, pe) < 1e-4
-    assert rel_err(q[:, 2], qe[:, 2]) < 1e-4
+    assert rel_err(q[:, 2], qe[:, 2]) < 1e-3      # gauge-free cfg1 window, see test_ba_matches_oracle
 
 
 def test_ba_assemble_reduced_system_matches_oracle():

@@ -1,0 +1,117 @@
+"""GPU: update operator, encoder and projective ops against the reference-generated fixtures, and
+the online VO state machine end to end."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from rampvo_b200 import projective_ops as pops, synth
+from rampvo_b200.lietorch import SE3
+from tests import golden_inputs as GI
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_pops_kernels_match_reference_fixture():
+    z = np.load(os.path.join(G, "pops_transform.npz"))
+    prob = GI.pops_problem()
+    t = GI.as_torch(prob, device="cuda")
+    x1, v, (Ji, Jj, Jz) = pops.transform(SE3(t["poses"]), t["patches"], t["intrinsics"], t["ii"], t["jj"],
+                                         t["kk"], jacobian=True)
+    assert np.abs(x1[0].cpu().numpy() - z["coords"]).max() < 2e-3           # px, fp32 vs float64
+    assert (v[0].cpu().numpy() == z["valid"]).all()
+    for got, key in ((Ji, "Ji"), (Jj, "Jj"), (Jz, "Jz")):
+        assert rel_err(got[0].cpu().numpy(), z[key]) < 1e-5
+    fm = pops.flow_mag(SE3(t["poses"]), t["patches"], t["intrinsics"], t["ii"], t["jj"], t["kk"], beta=0.5)
+    assert np.abs(fm[0].cpu().numpy() - z["flow_mag"]).max() < 4e-3
+
+
+def _my_update():
+    from rampvo_b200.net import Update
+    torch.manual_seed(GI.UPDATE_SEED)
+    return Update(3).cuda().eval()
+
+
+def test_update_operator_fp32_matches_reference_fixture():
+    z = np.load(os.path.join(G, "update_op.npz"))
+    up = _my_update()
+    g = GI.update_inputs("cuda")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        net, (d, w, _) = up(g["net"], g["inp"], g["corr"], None, g["ii"], g["jj"], g["kk"])
+    assert net.shape == (1, g["ii"].numel(), 384) and d.shape[-1] == 2 and w.shape[-1] == 2
+    assert rel_err(net[0].cpu().numpy(), z["net"]) < 2e-4
+    assert np.abs(d[0].cpu().numpy() - z["delta"]).max() < 2e-4 * max(1.0, np.abs(z["delta"]).max())
+    assert np.abs(w[0].cpu().numpy() - z["weight"]).max() < 2e-4
+
+
+def test_update_operator_autocast_close_to_reference_fixture():
+    """Mixed precision as Ramp_vo runs it (Ramp_vo.py:23,280): fp16 GEMMs, fp32 LayerNorm."""
+    z = np.load(os.path.join(G, "update_op.npz"))
+    up = _my_update()
+    g = GI.update_inputs("cuda")
+    with torch.no_grad(), torch.autocast("cuda", enabled=True):
+        net, (d, w, _) = up(g["net"], g["inp"], g["corr"].half(), None, g["ii"], g["jj"], g["kk"])
+    assert net.dtype == torch.float32                                   # the reference's dtype drift
+    assert rel_err(net[0].float().cpu().numpy(), z["net"]) < 3e-2
+    assert np.abs(w[0].float().cpu().numpy() - z["weight"]).max() < 2e-2
+
+
+def test_encoder_gpu_matches_reference_fixture():
+    from rampvo_b200.extractor import MultiScaleMergerDoubleNet
+    z = np.load(os.path.join(G, "encoder.npz"))
+    torch.manual_seed(GI.ENCODER_SEED)
+    enc = MultiScaleMergerDoubleNet(5, 3).cuda().eval()
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        for f, (ev, im) in enumerate(GI.encoder_inputs("cuda")):
+            fmap, imap = enc(events=ev, images=im, mask=torch.tensor([True]), reinit_hidden=(f == 0))
+            assert rel_err(fmap[0, 0].cpu().numpy(), z["fmap_%d" % f]) < 1e-3
+            assert rel_err(imap[0, 0].cpu().numpy(), z["imap_%d" % f]) < 1e-3
+        enc.reset_state()
+        with torch.autocast("cuda", enabled=True):
+            for f, (ev, im) in enumerate(GI.encoder_inputs("cuda")):
+                fmap, imap = enc(events=ev, images=im, mask=torch.tensor([True]), reinit_hidden=(f == 0))
+        assert rel_err(fmap[0, 0].float().cpu().numpy(), z["fmap_1"]) < 5e-2
+
+
+def _make_vo(preset="cfg1", seed=1234, mixed=True):
+    from rampvo_b200.Ramp_vo import Ramp_vo
+    from rampvo_b200.config import preset as mk
+    from rampvo_b200.net import VONet
+    torch.manual_seed(seed)
+    train_cfg = {"event_bias": True, "input_mode": "MultiScale", "num_event_bins": 5}
+    cfg = mk(preset)
+    cfg.MIXED_PRECISION = mixed
+    cfg.BUFFER_SIZE = 128
+    return Ramp_vo(cfg, VONet(train_cfg), train_cfg, ht=480, wd=640)
+
+
+def test_ramp_vo_runs_online_and_keeps_reference_invariants():
+    """evaluate.run()-shaped loop (evaluate.py:247-255) on a synthetic stream."""
+    vo = _make_vo("cfg1")
+    vo.motion_probe = lambda: torch.tensor(10.0)     # random weights: pin the init decision
+    seq = synth.SyntheticSequence(seed=0, device="cuda")
+    with torch.no_grad():
+        for t in range(14):
+            ev, im, mask = seq.frame(t)
+            vo(t, (ev, im, mask), seq.intrinsics)
+            if t == 3:   # an events-only call must not advance the VO (Ramp_vo.py:338-342)
+                n0 = vo.n
+                vo(t, (ev, im, torch.tensor([False])), seq.intrinsics)
+                assert vo.n == n0
+        assert vo.is_initialized and 8 <= vo.n <= 14
+        E = vo.ii.numel()
+        assert E > 0 and vo.net.shape == (1, E, 384) and vo.jj.numel() == E and vo.kk.numel() == E
+        assert (vo.ii == vo.ix[vo.kk]).all()
+        assert (vo.ix[vo.kk] >= vo.n - vo.cfg.REMOVAL_WINDOW).all()
+        assert torch.isfinite(vo.poses_[:vo.n]).all() and torch.isfinite(vo.patches_[:vo.n]).all()
+        q = vo.poses_[:vo.n, 3:]
+        assert (q.norm(dim=-1) - 1).abs().max() < 1e-3
+        for _ in range(3):
+            vo.update()
+        poses, tstamps = vo.terminate()
+        assert poses.shape == (14, 7) and len(tstamps) == 14 and np.isfinite(poses).all()
