@@ -46,6 +46,9 @@ int rvo_abi_version(void);
 const char* rvo_last_error(void);
 /* compute capability of the current device as major*10+minor (100 on B200); <0 on error */
 int rvo_device_cc(void);
+/* number of kernels this library has launched so far in this process (library-internal cub sort /
+ * scan passes are not counted) */
+uint64_t rvo_launch_count(void);
 
 /* A strided view of a 4-D feature tensor, logical dims [N, C, H, W], strides in ELEMENTS.
  * Channels-last storage (sC == 1) selects the tensor-core fast path of rvo_corr_*. */

@@ -30,6 +30,7 @@ _SIGNATURES = {
     "rvo_abi_version": (c_int, []),
     "rvo_last_error": (c_char_p, []),
     "rvo_device_cc": (c_int, []),
+    "rvo_launch_count": (ctypes.c_uint64, []),
     "rvo_patchify_forward": (c_int, [POINTER(FMap), _P, c_int, c_int, _P, _P]),
     "rvo_patchify_bilinear": (c_int, [POINTER(FMap), _P, c_int, c_int, _P, c_int, _I64, _I64, _I64,
                                       _I64, _I64, _P]),

@@ -28,8 +28,13 @@ int cuda_fail(cudaError_t e, const char* what);
     if (e__ != cudaSuccess) return ::rvo::cuda_fail(e__, #call);  \
   } while (0)
 
+// every kernel launch of this library goes through RVO_LAUNCH_CHECK: it also feeds the launch
+// counter behind rvo_launch_count() (bench.py's "gpu_launches").
+extern unsigned long long g_launches;
+
 #define RVO_LAUNCH_CHECK(name)                                          \
   do {                                                                  \
+    ::rvo::g_launches++;                                                \
     cudaError_t e__ = cudaGetLastError();                               \
     if (e__ != cudaSuccess) return ::rvo::cuda_fail(e__, name);         \
   } while (0)

@@ -6,6 +6,7 @@
 namespace rvo {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -25,6 +26,8 @@ int cuda_fail(cudaError_t e, const char* what) {
 extern "C" int rvo_abi_version(void) { return RVO_ABI_VERSION; }
 
 extern "C" const char* rvo_last_error(void) { return rvo::g_err; }
+
+extern "C" uint64_t rvo_launch_count(void) { return rvo::g_launches; }
 
 extern "C" int rvo_device_cc(void) {
   int dev = 0, major = 0, minor = 0;

@@ -82,3 +82,44 @@ def test_state_dict_keys_match_reference_checkpoint_layout():
         assert k in keys, k
     n_enc = sum(v.numel() for k, v in net.state_dict().items() if k.startswith("patchify"))
     assert n_enc == 844766
+
+
+def test_oracle_network_restatement_matches_reference_fixtures():
+    """oracle/ref_vo.py (the CPU baseline path: nn.LSTM plumbing, index-op scatter softmax) against
+    the reference's Update / encoder outputs."""
+    from oracle import ref_vo
+    from rampvo_b200.extractor import MultiScaleMergerDoubleNet
+    from rampvo_b200.net import Update
+    z = np.load(os.path.join(G, "update_op.npz"))
+    torch.manual_seed(GI.UPDATE_SEED)
+    p = {k: v.detach() for k, v in Update(3).state_dict().items()}
+    g = GI.update_inputs()
+    net, d, w = ref_vo.update_operator(p, g["net"][0], g["inp"][0], g["corr"][0], g["ii"], g["jj"], g["kk"])
+    assert rel_err(net.numpy(), z["net"]) < 1e-5
+    assert rel_err(d.numpy(), z["delta"]) < 1e-4 and rel_err(w.numpy(), z["weight"]) < 1e-5
+
+    z = np.load(os.path.join(G, "encoder.npz"))
+    torch.manual_seed(GI.ENCODER_SEED)
+    sd = {"patchify.encoder." + k: v for k, v in MultiScaleMergerDoubleNet(5, 3).state_dict().items()}
+    enc = ref_vo.Encoder(sd)
+    for f, (ev, im) in enumerate(GI.encoder_inputs()):
+        fmap, imap = enc(ev, im, [True], reinit_hidden=(f == 0))
+        assert rel_err(fmap[0, 0].numpy(), z["fmap_%d" % f]) < 1e-5
+        assert rel_err(imap[0, 0].numpy(), z["imap_%d" % f]) < 1e-5
+
+
+def test_oracle_torch_corr_matches_numpy_corr():
+    from oracle import ref_vo
+    from rampvo_b200 import synth
+    rng = np.random.default_rng(3)
+    gmap, pyr = synth.make_features(4, 24, C=32, ht=24, wd=32, seed=3, dtype=np.float32)
+    E = 60
+    kk, jj = rng.integers(0, 24, E), rng.integers(0, 4, E)
+    coords = rng.uniform(-4, 36, (E, 2, 1, 1)).astype(np.float32) + rng.normal(0, 0.6, (E, 2, 3, 3)).astype(np.float32)
+    g = gmap.transpose(0, 3, 1, 2)
+    p = [x.transpose(0, 3, 1, 2) for x in pyr]
+    exp = O.corr_pyramid(g, p, coords, kk, jj, 0, 0, 3)
+    got = ref_vo.corr_pyramid_torch(torch.from_numpy(g.copy()), [torch.from_numpy(x.copy()) for x in p],
+                                    torch.from_numpy(coords), torch.from_numpy(kk), torch.from_numpy(jj),
+                                    chunk=17)
+    assert np.abs(got.numpy() - exp).max() < 1e-5
