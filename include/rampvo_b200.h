@@ -91,10 +91,13 @@ int rvo_corr_forward(const rvo_fmap_t* fmap1, const rvo_fmap_t* fmap2, const flo
 /* Ramp_vo.corr (ramp/Ramp_vo.py:175-182): both pyramid levels in ONE launch.
  *   level l reads pyr[l] at coords * scale[l]  (scale = 1, 0.25 on the hot path)
  *   patch index = kk[e] % pmod, frame index = jj[e] % fmod (ring buffers; pass 0 for no modulo)
- *   out [E, 7,7,P,P, nlevels] flattened to [E, 49*P*P*nlevels] (= 882) of fmap1's dtype. */
+ *   out [E, 7,7,P,P, nlevels] flattened to [E, 49*P*P*nlevels] (= 882) of fmap1's dtype, rows
+ *   out_ld elements apart (0 = dense; the update operator uses 896 so that its first GEMM sees a
+ *   K that is a multiple of 8 — the pad columns are never written). */
 int rvo_corr_pyramid(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const float* scale,
                      int nlevels, const float* coords, const int64_t* kk, const int64_t* jj,
-                     int64_t pmod, int64_t fmod, int E, int radius, void* out, void* stream);
+                     int64_t pmod, int64_t fmod, int E, int radius, void* out, int64_t out_ld,
+                     void* stream);
 
 /* Host-buffer variant of rvo_corr_pyramid: every pointer (also inside the rvo_fmap_t views) is
  * HOST memory; copies in, launches, copies the [E,882] result back, synchronises. */
@@ -146,6 +149,47 @@ int rvo_flow_mag(const float* poses, const float* patches, const float* intrinsi
                  const int64_t* ii, const int64_t* jj, const int64_t* kk, int E, int P,
                  float beta, float* out, void* stream);
 
+/* ------------------------------------------------------------------ encoder ------ */
+
+/* Normalisation / activation / residual glue of the encoder CNNs (ramp/extractor.py:8-57,
+ * 288-311) on channels-last fp16 activations [npix, C] (C % 8 == 0):
+ *   rvo_in_stats  sums[0..C) = per-channel sum, sums[C..2C) = sum of squares over the npix pixels
+ *                 (InstanceNorm2d statistics, biased variance, extractor.py:30-34);
+ *   rvo_in_apply  out = relu( R + relu(T) ) with T = IN(t) when sums_t != NULL else t, and
+ *                 R = IN(res) / res / absent — the tail of ResidualBlock.forward (extractor.py:47-57)
+ *                 and of conv1 -> norm1 -> relu1 (:295-297) in one pass.  eps = 1e-5. */
+int rvo_in_stats(const void* x16, int64_t npix, int C, float* sums, void* stream);
+int rvo_in_apply(const void* t16, const float* sums_t, const void* res16, const float* sums_res,
+                 int64_t npix, int C, float eps, void* out16, void* stream);
+
+/* One scale of the recurrent multi-scale stem (MultiScaleMergerDoubleNet.forward,
+ * ramp/extractor.py:540-560) for one event stack [Ce,H,W] f32 and one image [Ci,H,W] f32: strided
+ * conv_1 (k, stride, pad; :326-345) -> per-pixel LSTM cell for one step from a zero state
+ * (:351-381) for both modalities -> super state ss <- W_ev [ss ; h_ev] + b and, when use_image,
+ * ss <- W_im [ss ; h_im] + b (:404-411,446-452).  ss_prev16 (NULL = zeros) and ss_out16 are
+ * channels-last fp16 [Ho,Wo,h], h in {16,32,64}.  `params` is one packed f32 buffer whose layout
+ * rvo_stem_params_layout reports: offsets of conv_1 weight/bias (events), conv_1 weight/bias
+ * (image), LSTM [i|g|o] rows of weight_ih and (bias_ih + bias_hh) (events), the same (image),
+ * TRANSPOSED [2h,h] super-state weight and bias (events), the same (image). */
+int rvo_stem_params_layout(int Ce, int Ci, int k, int h, int* offsets12, int* total);
+int rvo_stem_forward(const float* params, int Ce, int Ci, int k, int stride, int pad, int h,
+                     const float* events, const float* image, int H, int W, const void* ss_prev16,
+                     int use_image, void* ss_out16, void* stream);
+
+/* ------------------------------------------------------- VO state-machine helpers */
+
+/* The damped-linear motion model of Ramp_vo.__call__ (ramp/Ramp_vo.py:356-363):
+ * poses[n] = Exp(damping * Log(P1 * P2^-1)) * P1, P1 = poses[n-1], P2 = poses[n-2], with the
+ * lietorch formulas (so3.h:115-215, se3.h:36-47,124-142).  One launch instead of ~150 tensor ops. */
+int rvo_motion_model(float* poses, int n, float damping, void* stream);
+
+/* Ramp_vo.keyframe's two motionmag calls (ramp/Ramp_vo.py:227-241) in one launch:
+ * out4 = [sum flow_mag over edges (fi->fj), pixel count, sum over edges (fj->fi), pixel count];
+ * mean = sum / count on the host side (flow_mag: ramp/projective_ops.py:108-118). */
+int rvo_pair_flow(const float* poses, const float* patches, const float* intrinsics,
+                  const int64_t* ii, const int64_t* jj, const int64_t* kk, int E, int P, int64_t fi,
+                  int64_t fj, float beta, float* out4, void* stream);
+
 /* ------------------------------------------------------------- patch-graph plan -- */
 
 /* The bookkeeping the reference redoes with torch::_unique + host loops in every call
@@ -193,6 +237,15 @@ int rvo_ba_forward(float* poses, float* patches, const float* intrinsics, const 
                    int t0, int t1, int iterations, int eff_impl, void* ws, int64_t ws_bytes,
                    void* stream);
 
+/* rvo_ba_forward with the edge grouping taken from an existing rvo_graph_plan(kk, jj, ...) — the
+ * update operator of the same frame already built it (neighbors / SoftAgg groups), so the sort is
+ * not repeated. */
+int rvo_ba_forward_planned(float* poses, float* patches, const float* intrinsics,
+                           const float* target, const float* weight, const float* lmbda,
+                           const int64_t* ii, const int64_t* jj, const void* plan, int E,
+                           int64_t n_poses, int64_t n_patches, int P, int t0, int t1, int iterations,
+                           void* ws, int64_t ws_bytes, void* stream);
+
 /* One Gauss-Newton iteration in three steps, split where a patch graph sharded by source frame
  * needs its all-reduce:
  *   rvo_ba_plan      once per graph: sort / group the edges into `ws`;
@@ -237,6 +290,35 @@ int rvo_expand_add(const void* hy, int dtype, const void* plan, int E, int C, fl
                    void* stream);
 int rvo_gather_rows(const float* src, const int64_t* idx, int E, int C, void* out, int out_dtype,
                     void* stream);
+
+/* Fused row kernels of the mixed-precision update operator (C = 384; fp16 GEMM operands, fp32
+ * hidden state and LayerNorm, eps 1e-3 — the dtypes Update.forward has under autocast,
+ * ramp/Ramp_vo.py:280, SURVEY.md appendix "dtype drift").  Each replaces 3-8 elementwise / cast /
+ * LayerNorm launches of the reference:
+ *   rvo_up_ln_relu        y16 = relu(LN(x16))                               net.py:54-56
+ *   rvo_up_add3_ln        net = LN(net + imap16[idx % mod] + h16)           net.py:74-75, Ramp_vo.py:282
+ *   rvo_up_add_cast       net += t16 [; net16 = half(net)]                  net.py:81-82
+ *   rvo_up_softagg_fg     rvo_softagg on a fused [E,2C] = [f(x) | g(x)] GEMM output; rows of y past the
+ *                         last group are zeroed                             blocks.py:42-45
+ *   rvo_up_expand_add_ln  net[e] += hy16[group(e)]; then either net16 = half(net) (x32 == NULL) or
+ *                         x32 = LN(net), x16 = half(x32)                    blocks.py:47-48, net.py:84-87
+ *   rvo_up_gated_tail     y = x32 + sigmoid(a16) * r16 (blocks.py:30-31); mode 0: out32 = LN(y),
+ *                         out16 = half(out32); mode 1: out32 = y, delta = Wd relu(y) + bd,
+ *                         weight = sigmoid(Ww relu(y) + bw) with Wd, Ww [2,C] (net.py:63-67,90) */
+int rvo_up_ln_relu(const void* x16, const float* gamma, const float* beta, int E, int C, void* y16,
+                   void* stream);
+int rvo_up_add3_ln(const float* net_in, const void* imap16, const int64_t* idx, int64_t mod,
+                   const void* h16, const float* gamma, const float* beta, int E, int C,
+                   float* net_out, void* stream);
+int rvo_up_add_cast(float* net, const void* t16, int E, int C, void* net16, void* stream);
+int rvo_up_softagg_fg(const void* fg16, const void* plan, int E, int C, int64_t max_groups, void* y16,
+                      void* stream);
+int rvo_up_expand_add_ln(const void* hy16, const void* plan, int E, int C, float* net, void* net16,
+                         const float* gamma, const float* beta, float* x32, void* x16, void* stream);
+int rvo_up_gated_tail(const float* x32, const void* a16, const void* r16, int E, int C, int mode,
+                      const float* gamma, const float* beta, float* out32, void* out16,
+                      const float* Wd, const float* bd, const float* Ww, const float* bw, float* delta,
+                      float* weight, void* stream);
 
 #ifdef __cplusplus
 }

@@ -19,15 +19,89 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from . import altcorr, fastba, lietorch
+from . import _lib, altcorr, fastba, lietorch
 from . import projective_ops as pops
 from .lietorch import SE3
 from .net import GraphPlans, VONet
 from .vo_utils import filter_features, flatmeshgrid, preprocess_input
 
 
+class _PatchifyGraph:
+    """CUDA graph of `network.patchify` for the steady case (one event stack + one image per call):
+    encoder -> /4 -> patch selection -> the four patch gathers -> pyramid level 2, ~450 kernel
+    launches replayed as one.  Static input / output / recurrent-state buffers; the caller copies the
+    outputs into the ring-buffer slot of the frame."""
+
+    def __init__(self, vo):
+        self.vo = vo
+        dev, M, P = vo.device, vo.M, vo.P
+        h4, w4 = vo.ht // vo.RES, vo.wd // vo.RES
+        nb = vo.train_cfg["num_event_bins"]
+        self.ev = torch.zeros(1, 1, nb, vo.ht, vo.wd, device=dev)
+        self.im = torch.zeros(1, 1, 3, vo.ht, vo.wd, device=dev)
+        self.mask = torch.tensor([True])
+        self.gmap = torch.zeros(M, P, P, 128, device=dev, dtype=vo.fdtype)      # channels-last staging
+        self.f1 = torch.zeros(h4, w4, 128, device=dev, dtype=vo.fdtype)
+        self.f2 = torch.zeros(h4 // 4, w4 // 4, 128, device=dev, dtype=vo.fdtype)
+        self.imap = torch.zeros(M, vo.DIM, device=dev, dtype=vo.fdtype)
+        self.patches = torch.zeros(1, M, 3, P, P, device=dev)
+        self.clr = torch.zeros(1, M, 3, device=dev)
+        enc = vo.network.patchify.encoder
+        self.state = None
+        self.graph = None
+        # warm up on a side stream (cuDNN / cuBLAS handles, lazy module init), then capture
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        saved = list(enc.super_states)
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                enc.super_states = [None, None, None]
+                self._body(first=True)
+            self.state = [t.detach().clone() for t in enc.super_states]
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        enc.super_states = list(self.state)
+        with torch.cuda.graph(self.graph):
+            self._body(first=False)
+            for buf, new in zip(self.state, enc.super_states):
+                buf.copy_(new)
+        enc.super_states = saved
+        for b in self.state:
+            b.zero_()
+
+    @torch.no_grad()
+    def _body(self, first):
+        vo = self.vo
+        gslot = self.gmap.permute(0, 3, 1, 2)[None]
+        with torch.autocast("cuda", enabled=vo.autocast):
+            fmap, gmap, imap, patches, _, clr = vo.network.patchify(
+                input_=(self.ev, self.im, self.mask), patches_per_image=vo.M, event_bias=vo.event_bias,
+                reinit_hidden=False, gmap_out=gslot)
+        f = fmap[0, 0]
+        self.f1.copy_(f.permute(1, 2, 0))
+        self.f2.copy_(F.avg_pool2d(f[None].float(), 4, 4)[0].permute(1, 2, 0))
+        self.imap.copy_(imap.view(vo.M, vo.DIM))
+        self.patches.copy_(patches)
+        self.clr.copy_(clr)
+
+    def run(self, events, images, reinit):
+        enc = self.vo.network.patchify.encoder
+        if reinit:
+            for b in self.state:
+                b.zero_()
+        else:   # pick up a state left by an eager (events-only) call
+            for b, cur in zip(self.state, enc.super_states):
+                if cur is not None and cur is not b:
+                    b.copy_(cur)
+        self.ev.copy_(events)
+        self.im.copy_(images)
+        self.graph.replay()
+        enc.super_states = list(self.state)
+
+
 class Ramp_vo:
-    def __init__(self, cfg, network, train_cfg, ht=480, wd=640, device="cuda"):
+    def __init__(self, cfg, network, train_cfg, ht=480, wd=640, device="cuda", use_graphs=True):
         self.cfg = cfg
         self.event_bias = train_cfg["event_bias"]
         self.train_cfg = train_cfg
@@ -76,6 +150,9 @@ class Ramp_vo:
         self.jj = torch.as_tensor([], dtype=torch.long, device=dev)
         self.kk = torch.as_tensor([], dtype=torch.long, device=dev)
         self._plans = None          # GraphPlans of the current edge list
+        self.use_graphs = use_graphs
+        self._pgraph = None         # _PatchifyGraph, captured at the first frame
+        self._corr_buf = None       # [1, capacity, 896] correlation rows (882 used)
 
         self.poses_[:, 6] = 1.0
         self.delta = {}
@@ -145,8 +222,16 @@ class Ramp_vo:
     def corr(self, coords, indicies=None):
         """local correlation volume [1,E,882] (Ramp_vo.py:175-182), one fused launch"""
         ii, jj = indicies if indicies is not None else (self.kk, self.jj)
+        E = ii.numel()
+        # rows padded to 896 halves (pad columns stay zero) so the first GEMM of the update operator
+        # has K % 8 == 0; the returned tensor is the [1,E,882] view of it
+        buf = self._corr_buf
+        if buf is None or buf.shape[1] < E:
+            buf = self._corr_buf = torch.zeros(1, max(E, 1) * 5 // 4 + 256, 896, dtype=self.fdtype,
+                                               device=self.device)
+        out = buf[:, :E, :882]
         return altcorr.corr_pyramid(self.gmap, self.pyramid, coords, ii, jj, self.M * self.mem,
-                                    self.mem, 3)
+                                    self.mem, 3, out=out)
 
     def reproject(self, indicies=None, poses=None, patches=None, intrinsics=None):
         """reproject patch k from i -> j: coords [1,E,2,P,P] (Ramp_vo.py:184-192)"""
@@ -176,9 +261,13 @@ class Ramp_vo:
 
     def _graph_plans(self):
         if self._plans is None:
-            self._plans = GraphPlans(self.ii, self.jj, self.kk, kmax=self.N * self.M, jmax=self.N)
+            frames = self.cfg.REMOVAL_WINDOW + 2        # source frames that can still own edges
+            self._plans = GraphPlans(self.ii, self.jj, self.kk, kmax=self.N * self.M, jmax=self.N,
+                                     max_patches=frames * self.M,
+                                     max_pairs=frames * (2 * self.cfg.PATCH_LIFETIME + 1))
         return self._plans
 
+    @torch.no_grad()
     def motion_probe(self):
         """median |delta| of the newest patches against the candidate frame (Ramp_vo.py:210-225)"""
         kk = torch.arange(self.m - self.M, self.m, device=self.device)
@@ -203,7 +292,16 @@ class Ramp_vo:
         """remove keyframe n-KEYFRAME_INDEX if motion is small (Ramp_vo.py:237-274)"""
         i = self.n - self.cfg.KEYFRAME_INDEX - 1
         j = self.n - self.cfg.KEYFRAME_INDEX + 1
-        m = self.motionmag(i, j) + self.motionmag(j, i)
+        # motionmag(i, j) + motionmag(j, i) in one launch and one device->host read
+        out4 = torch.empty(4, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().rvo_pair_flow(
+                _lib.ptr(self.poses_), _lib.ptr(self.patches_), _lib.ptr(self.intrinsics_),
+                _lib.ptr(self.ii), _lib.ptr(self.jj), _lib.ptr(self.kk), self.ii.numel(), self.P, i, j,
+                0.5, _lib.ptr(out4), _lib.stream_ptr(self.device)), "rvo_pair_flow")
+        s1, c1, s2, c2 = out4.tolist()
+        nan = float("nan")      # the reference takes the mean of an empty selection (nan) too
+        m = (s1 / c1 if c1 else nan) + (s2 / c2 if c2 else nan)
         if m / 2 < self.cfg.KEYFRAME_THRESH:
             k = self.n - self.cfg.KEYFRAME_INDEX
             t0 = self.tstamps_[k - 1].item()
@@ -230,6 +328,7 @@ class Ramp_vo:
             self.m -= self.M
         self.remove_factors(self.ix[self.kk] < self.n - self.cfg.REMOVAL_WINDOW)
 
+    @torch.no_grad()
     def update(self):
         """one recurrent update: reproject -> corr -> update operator -> 2 BA iterations
         (Ramp_vo.py:276-310)"""
@@ -237,7 +336,7 @@ class Ramp_vo:
         plans = self._graph_plans()
         with torch.autocast("cuda", enabled=self.autocast):
             corr = self.corr(coords)
-            ctx = self.imap[:, self.kk % (self.M * self.mem)]
+            ctx = (self.imap_, self.kk, self.M * self.mem)     # imap[:, kk % (M*mem)], gather fused
             self.net, (delta, weight, _) = self.network.update(self.net, ctx, corr, None, self.ii,
                                                                self.jj, self.kk, plans=plans)
         weight = weight.float()
@@ -249,7 +348,8 @@ class Ramp_vo:
         t0 = max(t0, 1)
         try:
             fastba.BA(self.poses, self.patches, self.intrinsics, target, weight, self.lmbda, self.ii,
-                      self.jj, self.kk, t0, self.n, M=self.M, iterations=2, eff_impl=False)
+                      self.jj, self.kk, t0, self.n, M=self.M, iterations=2, eff_impl=False,
+                      plan=plans.plan_k)
         except RuntimeError as e:   # BA failure is non-fatal, like the reference (:302-306)
             print(f"WARNING: BA failed...{e}")
         pts = pops.point_cloud_centers(SE3(self.poses), self.patches[:, :self.m], self.intrinsics,
@@ -270,19 +370,35 @@ class Ramp_vo:
         return flatmeshgrid(torch.arange(t0, t1, device=self.device),
                             torch.arange(max(self.n - r, 0), self.n, device=self.device), indexing='ij')
 
+    @torch.no_grad()
     def __call__(self, tstamp, input_tensor, intrinsics):
         """track a new frame (Ramp_vo.py:327-410)"""
         input_ = preprocess_input(input_tensor=input_tensor)
         slot = self.n % self.mem
         P, M = self.P, self.M
-        gslot = self._gmap_store[slot * M:(slot + 1) * M].permute(0, 3, 1, 2)[None]   # [1,M,128,P,P]
-        with torch.autocast("cuda", enabled=self.autocast):
-            fmap, gmap, imap, patches, _, clr = self.network.patchify(
-                input_=input_, patches_per_image=M, event_bias=self.event_bias,
-                reinit_hidden=True if tstamp == 0 else False, gmap_out=gslot)
-        mask = input_[2]
-        if fmap is None or (mask is not None and not bool(torch.as_tensor(mask).any())):
-            return      # events only: the super state was updated, the VO is not
+        events, images, mask = input_
+        mask_l = torch.as_tensor(mask).reshape(-1).tolist()
+        graphable = (self.use_graphs and events.shape[1] == 1 and images.shape[1] == 1 and mask_l == [True]
+                     and tuple(events.shape[-2:]) == (self.ht, self.wd))
+        if graphable:
+            if self._pgraph is None:
+                self._pgraph = _PatchifyGraph(self)
+            g = self._pgraph
+            g.run(events, images, reinit=(tstamp == 0))
+            self._gmap_store[slot * M:(slot + 1) * M] = g.gmap
+            patches, clr, imap_new, f1_new, f2_new = g.patches.clone(), g.clr, g.imap, g.f1, g.f2
+        else:
+            gslot = self._gmap_store[slot * M:(slot + 1) * M].permute(0, 3, 1, 2)[None]   # [1,M,128,P,P]
+            with torch.autocast("cuda", enabled=self.autocast):
+                fmap, gmap, imap, patches, _, clr = self.network.patchify(
+                    input_=input_, patches_per_image=M, event_bias=self.event_bias,
+                    reinit_hidden=True if tstamp == 0 else False, gmap_out=gslot)
+            if fmap is None:
+                return      # events only: the super state was updated, the VO is not
+            f = fmap[0, 0]                                               # [128,h,w]
+            imap_new = imap.view(M, self.DIM)
+            f1_new = f.permute(1, 2, 0)
+            f2_new = F.avg_pool2d(f[None].float(), 4, 4)[0].permute(1, 2, 0)
 
         self.tlist.append(tstamp)
         self.tstamps_[self.n] = self.counter
@@ -294,10 +410,10 @@ class Ramp_vo:
 
         if self.n > 1:
             if self.cfg.MOTION_MODEL == 'DAMPED_LINEAR':
-                P1 = SE3(self.poses_[self.n - 1])
-                P2 = SE3(self.poses_[self.n - 2])
-                xi = self.cfg.MOTION_DAMPING * (P1 * P2.inv()).log()
-                self.poses_[self.n] = (SE3.exp(xi) * P1).data
+                with torch.cuda.device(self.device):
+                    _lib.check(_lib.lib().rvo_motion_model(_lib.ptr(self.poses_), self.n,
+                                                           float(self.cfg.MOTION_DAMPING),
+                                                           _lib.stream_ptr(self.device)), "rvo_motion_model")
             else:
                 self.poses_[self.n] = self.poses_[self.n - 1]
 
@@ -307,10 +423,9 @@ class Ramp_vo:
         self.patches_[self.n] = patches
 
         # network attributes: gmap is already in its ring slot; fmap pyramid written channels-last
-        self.imap_[slot] = imap.view(M, self.DIM).to(self.fdtype)
-        f = fmap[0, 0]                                               # [128,h,w]
-        self._fmap1_store[slot] = f.permute(1, 2, 0).to(self.fdtype)
-        self._fmap2_store[slot] = F.avg_pool2d(f[None].float(), 4, 4)[0].permute(1, 2, 0).to(self.fdtype)
+        self.imap_[slot] = imap_new.to(self.fdtype)
+        self._fmap1_store[slot] = f1_new.to(self.fdtype)
+        self._fmap2_store[slot] = f2_new.to(self.fdtype)
 
         self.counter += 1
         if self.n > 0 and not self.is_initialized:

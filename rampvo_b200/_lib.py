@@ -36,7 +36,7 @@ _SIGNATURES = {
                                       _I64, _I64, _P]),
     "rvo_corr_forward": (c_int, [POINTER(FMap), POINTER(FMap), _P, _P, _P, c_int, c_int, _P, _P]),
     "rvo_corr_pyramid": (c_int, [POINTER(FMap), POINTER(FMap), POINTER(c_float), c_int, _P, _P, _P,
-                                 _I64, _I64, c_int, c_int, _P, _P]),
+                                 _I64, _I64, c_int, c_int, _P, _I64, _P]),
     "rvo_corr_pyramid_host": (c_int, [POINTER(FMap), POINTER(FMap), POINTER(c_float), c_int, _P, _P,
                                       _P, _I64, _I64, c_int, c_int, _P, _P]),
     "rvo_transform": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
@@ -44,6 +44,13 @@ _SIGNATURES = {
     "rvo_reproject": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P, _P]),
     "rvo_point_cloud": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P]),
     "rvo_flow_mag": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P, _P]),
+    "rvo_in_stats": (c_int, [_P, _I64, c_int, _P, _P]),
+    "rvo_in_apply": (c_int, [_P, _P, _P, _P, _I64, c_int, c_float, _P, _P]),
+    "rvo_stem_params_layout": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    "rvo_stem_forward": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P,
+                                 c_int, _P, _P]),
+    "rvo_motion_model": (c_int, [_P, c_int, c_float, _P]),
+    "rvo_pair_flow": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _I64, _I64, c_float, _P, _P]),
     "rvo_plan_bytes": (_I64, [c_int]),
     "rvo_graph_plan": (c_int, [_P, _P, c_int, _I64, _I64, _P, _I64, _P]),
     "rvo_plan_groups": (c_int, [_P, c_int, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(_P),
@@ -54,6 +61,8 @@ _SIGNATURES = {
     "rvo_ba_ws_bytes": (_I64, [c_int, _I64, c_int]),
     "rvo_ba_forward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, _I64, c_int, c_int,
                                c_int, c_int, c_int, c_int, _P, _I64, _P]),
+    "rvo_ba_forward_planned": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, _I64, c_int,
+                                       c_int, c_int, c_int, _P, _I64, _P]),
     "rvo_ba_plan": (c_int, [_P, _P, c_int, _I64, _I64, c_int, _P, _I64, _P]),
     "rvo_ba_assemble": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, c_int, c_int, c_int,
                                 _P, _P, _I64, _P]),
@@ -61,6 +70,13 @@ _SIGNATURES = {
     "rvo_softagg": (c_int, [_P, _P, c_int, _P, c_int, c_int, _I64, _P, c_int, _P]),
     "rvo_expand_add": (c_int, [_P, c_int, _P, c_int, c_int, _P, _P]),
     "rvo_gather_rows": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P]),
+    "rvo_up_ln_relu": (c_int, [_P, _P, _P, c_int, c_int, _P, _P]),
+    "rvo_up_add3_ln": (c_int, [_P, _P, _P, _I64, _P, _P, _P, c_int, c_int, _P, _P]),
+    "rvo_up_add_cast": (c_int, [_P, _P, c_int, c_int, _P, _P]),
+    "rvo_up_softagg_fg": (c_int, [_P, _P, c_int, c_int, _I64, _P, _P]),
+    "rvo_up_expand_add_ln": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "rvo_up_gated_tail": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                  _P, _P]),
     "rvo_ba_forward_host": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, _I64, c_int,
                                     c_int, c_int, c_int, c_int, c_int, _P]),
 }

@@ -117,8 +117,11 @@ def corr_pyramid(gmap, pyramid, coords, kk, jj, pmod=0, fmod=0, radius=3, scales
     coords = coords.to(torch.float32).contiguous()
     kk = kk.to(torch.int64).contiguous()
     jj = jj.to(torch.int64).contiguous()
+    row = d * d * P * P * nl
     if out is None:
-        out = torch.empty(1, E, d * d * P * P * nl, dtype=gmap.dtype, device=gmap.device)
+        out = torch.empty(1, E, row, dtype=gmap.dtype, device=gmap.device)
+    ld = out.stride(-2) if out.numel() else row      # padded rows allowed (pad columns untouched)
+    assert out.shape[-1] >= row and out.stride(-1) == 1
     v1 = _lib.fmap_view(gmap[0])
     arr = (_lib.FMap * nl)(*[_lib.fmap_view(p[0]) for p in pyramid])
     for p in pyramid:
@@ -128,6 +131,6 @@ def corr_pyramid(gmap, pyramid, coords, kk, jj, pmod=0, fmod=0, radius=3, scales
     with torch.cuda.device(gmap.device):
         _lib.check(_lib.lib().rvo_corr_pyramid(ctypes.byref(v1), arr, sc, nl, _lib.ptr(coords),
                                                _lib.ptr(kk), _lib.ptr(jj), pmod, fmod, E, radius,
-                                               _lib.ptr(out), _lib.stream_ptr()),
+                                               _lib.ptr(out), ld, _lib.stream_ptr()),
                    "rvo_corr_pyramid")
     return out

@@ -160,7 +160,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 corr_generic_kernel(FmapView g, CorrLevels L, const float* __restrict__ coords,
                     const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, int64_t pmod,
-                    int64_t fmod, int E, int R, T* __restrict__ out) {
+                    int64_t fmod, int E, int R, T* __restrict__ out, int64_t out_ld) {
   extern __shared__ float smem[];
   const int D = 2 * R + 2, d = D - 1;
   const int P = g.H, PP = P * P;
@@ -203,7 +203,7 @@ corr_generic_kernel(FmapView g, CorrLevels L, const float* __restrict__ coords,
                       (dx * (1.0f - dy)) * win[a * D + b + 1] +
                       ((1.0f - dx) * dy) * win[(a + 1) * D + b] +
                       (dx * dy) * win[(a + 1) * D + b + 1];
-      out[(((int64_t)e * d * d + q) * PP + pix) * L.n + lvl] = from_f32<T>(v);
+      out[(int64_t)e * out_ld + ((int64_t)q * PP + pix) * L.n + lvl] = from_f32<T>(v);
     }
     __syncwarp();
   }
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, OCC)
 corr_mma_kernel(const __half* __restrict__ gmap, int64_t gN, int64_t g_sN, int64_t g_sH,
                 int64_t g_sW, CorrLevels L, const float* __restrict__ coords,
                 const int64_t* __restrict__ kk, const int64_t* __restrict__ jj, int64_t pmod,
-                int64_t fmod, int E, __half* __restrict__ out) {
+                int64_t fmod, int E, __half* __restrict__ out, int64_t out_ld) {
   __shared__ __align__(16) float Dsm[kWarpsPerCta][9 * kPosPad];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -404,10 +404,10 @@ corr_mma_kernel(const __half* __restrict__ gmap, int64_t gN, int64_t g_sN, int64
           const int o = it * 32 + lane;
           if (o < NOUT) {
             if (NL == 2)
-              reinterpret_cast<__half2*>(out)[(int64_t)e * NOUT + o] =
+              reinterpret_cast<__half2*>(out + (int64_t)e * out_ld)[o] =
                   __halves2half2((it & 1) ? acc0[it >> 1].y : acc0[it >> 1].x, __float2half_rn(v));
             else
-              out[(int64_t)e * NOUT + o] = __float2half_rn(v);
+              out[(int64_t)e * out_ld + o] = __float2half_rn(v);
           }
         }
       }
@@ -435,13 +435,19 @@ static bool fast_path_ok(const FmapView& g, const CorrLevels& L, int dtype, int 
 
 static int corr_launch(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const float* scale,
                        int nlevels, const float* coords, const int64_t* kk, const int64_t* jj,
-                       int64_t pmod, int64_t fmod, int E, int radius, void* out,
+                       int64_t pmod, int64_t fmod, int E, int radius, void* out, int64_t out_ld,
                        cudaStream_t st, const char* who) {
   RVO_CHECK_ARG(E >= 0, "%s: E=%d", who, E);
   RVO_CHECK_ARG(fmap1 && pyr && nlevels >= 1 && nlevels <= kMaxLevels, "%s: bad levels", who);
   RVO_CHECK_ARG(radius >= 0 && radius <= 7, "%s: radius %d unsupported", who, radius);
   if (E == 0) return RVO_OK;
   RVO_CHECK_ARG(coords && kk && jj && out && fmap1->data, "%s: null pointer", who);
+  {
+    const int64_t row = (int64_t)(2 * radius + 1) * (2 * radius + 1) * fmap1->H * fmap1->W * nlevels;
+    if (out_ld <= 0) out_ld = row;
+    RVO_CHECK_ARG(out_ld >= row, "%s: output row stride %lld < %lld", who, (long long)out_ld,
+                  (long long)row);
+  }
   RVO_CHECK_ARG(fmap1->H == fmap1->W && fmap1->H >= 1 && fmap1->H <= 9, "%s: patch size", who);
   FmapView g = view_of(fmap1);
   CorrLevels L;
@@ -454,7 +460,8 @@ static int corr_launch(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const flo
   }
   for (int l = nlevels; l < kMaxLevels; l++) { L.f[l] = L.f[0]; L.scale[l] = 1.0f; }
 
-  if (fast_path_ok(g, L, fmap1->dtype, radius, E)) {
+  if (fast_path_ok(g, L, fmap1->dtype, radius, E) &&
+      (nlevels == 1 || (out_ld % 2 == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0))) {
     // development switch (tools/microbench.py): RVO_CORR_VARIANT = 10*NTB + OCC
     static const int variant = getenv("RVO_CORR_VARIANT") ? atoi(getenv("RVO_CORR_VARIANT")) : 22;
     const int occ = variant % 10;
@@ -463,7 +470,7 @@ static int corr_launch(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const flo
 #define RVO_CORR_LAUNCH(NL_, NTB_, OCC_)                                                       \
     corr_mma_kernel<128, NL_, NTB_, OCC_><<<grid, kWarpsPerCta * 32, 0, st>>>(                  \
         (const __half*)g.data, g.N, g.sN, g.sH, g.sW, L, coords, kk, jj, pmod, fmod, E,         \
-        (__half*)out)
+        (__half*)out, out_ld)
 #define RVO_CORR_PICK(NL_)                                                                     \
     switch (variant) {                                                                         \
       case 12: RVO_CORR_LAUNCH(NL_, 1, 2); break;                                              \
@@ -487,10 +494,10 @@ static int corr_launch(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const flo
   if (grid > (int64_t)kNumSMs * 64) grid = (int64_t)kNumSMs * 64;
   if (fmap1->dtype == RVO_F16)
     corr_generic_kernel<__half><<<(int)grid, 256, smem, st>>>(g, L, coords, kk, jj, pmod, fmod, E,
-                                                              radius, (__half*)out);
+                                                              radius, (__half*)out, out_ld);
   else if (fmap1->dtype == RVO_F32)
     corr_generic_kernel<float><<<(int)grid, 256, smem, st>>>(g, L, coords, kk, jj, pmod, fmod, E,
-                                                             radius, (float*)out);
+                                                             radius, (float*)out, out_ld);
   else
     RVO_CHECK_ARG(false, "%s: dtype %d unsupported", who, fmap1->dtype);
   RVO_LAUNCH_CHECK("corr_generic_kernel");
@@ -553,15 +560,15 @@ extern "C" int rvo_corr_forward(const rvo_fmap_t* fmap1, const rvo_fmap_t* fmap2
                                 const float* coords, const int64_t* ii, const int64_t* jj, int E,
                                 int radius, void* out, void* stream) {
   const float one = 1.0f;
-  return corr_launch(fmap1, fmap2, &one, 1, coords, ii, jj, 0, 0, E, radius, out,
+  return corr_launch(fmap1, fmap2, &one, 1, coords, ii, jj, 0, 0, E, radius, out, 0,
                      (cudaStream_t)stream, "rvo_corr_forward");
 }
 
 extern "C" int rvo_corr_pyramid(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const float* scale,
                                 int nlevels, const float* coords, const int64_t* kk,
                                 const int64_t* jj, int64_t pmod, int64_t fmod, int E, int radius,
-                                void* out, void* stream) {
-  return corr_launch(fmap1, pyr, scale, nlevels, coords, kk, jj, pmod, fmod, E, radius, out,
+                                void* out, int64_t out_ld, void* stream) {
+  return corr_launch(fmap1, pyr, scale, nlevels, coords, kk, jj, pmod, fmod, E, radius, out, out_ld,
                      (cudaStream_t)stream, "rvo_corr_pyramid");
 }
 
@@ -603,7 +610,7 @@ extern "C" int rvo_corr_pyramid_host(const rvo_fmap_t* fmap1, const rvo_fmap_t* 
   const size_t out_bytes = (size_t)E * d * d * PP * nlevels * es;
   if (rc == RVO_OK && (ce = cudaMalloc(&d_out, out_bytes ? out_bytes : 1)) != cudaSuccess) fail(ce, "cudaMalloc");
   if (rc == RVO_OK)
-    rc = corr_launch(&v1, vp, scale, nlevels, d_coords, d_kk, d_jj, pmod, fmod, E, radius, d_out, st,
+    rc = corr_launch(&v1, vp, scale, nlevels, d_coords, d_kk, d_jj, pmod, fmod, E, radius, d_out, 0, st,
                      "rvo_corr_pyramid_host");
   if (rc == RVO_OK && (ce = cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess) fail(ce, "D2H");
   cudaError_t se = cudaStreamSynchronize(st);

@@ -1,0 +1,351 @@
+// encoder_ops.cu — the normalisation / activation / residual glue of the RAMP encoder CNNs
+// (ramp/extractor.py:8-57, 288-311) on channels-last fp16 activations, for sm_100a.
+//
+// The reference runs InstanceNorm2d, ReLU and the residual add as separate NCHW passes (and cuDNN
+// inserts NCHW<->NHWC transposes around them).  Here a ResidualBlock is conv -> stats -> apply:
+//   in_stats   per-channel sum / sum of squares over H*W (one read of the activation, fp32
+//              accumulation, one atomicAdd per channel per CTA);
+//   in_apply   out = relu( [IN](res) + relu( [IN](t) ) )  — normalisation of the conv output, ReLU,
+//              the (optionally normalised) shortcut and the final ReLU in ONE pass, 16-byte vectors.
+// Bound: HBM/L2 (2 reads + 1 write of the activation per ResidualBlock half instead of ~8).
+#include "common.cuh"
+
+namespace rvo {
+
+// x: [npix, C] fp16, C = 8 * vec with vec a power of two <= 32 (C in {8,...,256}).
+// sums[0..C) += sum, sums[C..2C) += sum of squares.  Lane l of a warp owns channel octet l % vec of
+// pixel l / vec (+ strides): partial sums are reduced across the lanes that share an octet with
+// xor-shuffles, across the CTA's warps through shared memory, then one atomicAdd per channel.
+__global__ void __launch_bounds__(256)
+in_stats_kernel(const __half* __restrict__ x, int64_t npix, int C, float* __restrict__ sums) {
+  __shared__ float part[8][2 * 256];      // [warp][2C]
+  const int vec = C / 8;
+  const int rows = blockDim.x / vec;      // pixels handled concurrently by the CTA
+  const int v = threadIdx.x % vec, r = threadIdx.x / vec;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { s[i] = 0.f; q[i] = 0.f; }
+  for (int64_t p = (int64_t)blockIdx.x * rows + r; p < npix; p += (int64_t)gridDim.x * rows) {
+    const uint4 u = reinterpret_cast<const uint4*>(x + p * C)[v];
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float2 f = __half22float2(h[i]);
+      s[2 * i] += f.x; q[2 * i] += f.x * f.x;
+      s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    for (int o = 16; o >= vec; o >>= 1) {
+      s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+      q[i] += __shfl_xor_sync(0xffffffffu, q[i], o);
+    }
+  }
+  if (lane < vec) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      part[warp][lane * 8 + i] = s[i];
+      part[warp][C + lane * 8 + i] = q[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) a += part[w][c];
+    atomicAdd(&sums[c], a);
+  }
+}
+
+// out = relu( R + relu(T) ),  T = IN(t) if st else t,  R = (res ? (sr ? IN(res) : res) : none)
+__global__ void __launch_bounds__(256)
+in_apply_kernel(const __half* __restrict__ t, const float* __restrict__ st,
+                const __half* __restrict__ res, const float* __restrict__ sr, int64_t npix, int C,
+                float eps, __half* __restrict__ out) {
+  extern __shared__ float tab[];          // mean_t, rstd_t, mean_r, rstd_r  [4][C]
+  const float inv = 1.0f / (float)npix;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float m = 0.f, rs = 1.f;
+    if (st) { m = st[c] * inv; rs = rsqrtf(fmaxf(st[C + c] * inv - m * m, 0.f) + eps); }
+    tab[c] = m; tab[C + c] = rs;
+    m = 0.f; rs = 1.f;
+    if (sr) { m = sr[c] * inv; rs = rsqrtf(fmaxf(sr[C + c] * inv - m * m, 0.f) + eps); }
+    tab[2 * C + c] = m; tab[3 * C + c] = rs;
+  }
+  __syncthreads();
+  const int vec = C / 8;
+  const int64_t total = npix * vec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % vec) * 8;
+    const uint4 ut = reinterpret_cast<const uint4*>(t)[i];
+    uint4 ur = make_uint4(0, 0, 0, 0);
+    if (res) ur = reinterpret_cast<const uint4*>(res)[i];
+    const __half2* ht = reinterpret_cast<const __half2*>(&ut);
+    const __half2* hr = reinterpret_cast<const __half2*>(&ur);
+    uint4 uo;
+    __half2* ho = reinterpret_cast<__half2*>(&uo);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float2 a = __half22float2(ht[k]);
+      const int c = c0 + 2 * k;
+      float v0 = fmaxf((a.x - tab[c]) * tab[C + c], 0.f);
+      float v1 = fmaxf((a.y - tab[c + 1]) * tab[C + c + 1], 0.f);
+      if (res) {
+        const float2 b = __half22float2(hr[k]);
+        v0 = fmaxf((b.x - tab[2 * C + c]) * tab[3 * C + c] + v0, 0.f);
+        v1 = fmaxf((b.y - tab[2 * C + c + 1]) * tab[3 * C + c + 1] + v1, 0.f);
+      }
+      ho[k] = __floats2half2_rn(v0, v1);
+    }
+    reinterpret_cast<uint4*>(out)[i] = uo;
+  }
+}
+
+}  // namespace rvo
+
+using namespace rvo;
+
+extern "C" int rvo_in_stats(const void* x16, int64_t npix, int C, float* sums, void* stream) {
+  RVO_CHECK_ARG(npix >= 0 && C >= 8 && C <= 256 && (C & (C - 1)) == 0,
+                "rvo_in_stats: npix=%lld C=%d (C must be a power of two in [8,256])", (long long)npix, C);
+  RVO_CHECK_ARG(x16 && sums, "rvo_in_stats: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  RVO_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
+  if (npix == 0) return RVO_OK;
+  const int rows = 256 / (C / 8);
+  int64_t grid = (npix + rows - 1) / rows;
+  if (grid > kNumSMs * 4) grid = kNumSMs * 4;
+  in_stats_kernel<<<(int)grid, 256, 0, st>>>((const __half*)x16, npix, C, sums);
+  RVO_LAUNCH_CHECK("in_stats_kernel");
+  return RVO_OK;
+}
+
+extern "C" int rvo_in_apply(const void* t16, const float* sums_t, const void* res16,
+                            const float* sums_res, int64_t npix, int C, float eps, void* out16,
+                            void* stream) {
+  RVO_CHECK_ARG(npix >= 0 && C >= 8 && C % 8 == 0 && C <= 512, "rvo_in_apply: npix=%lld C=%d",
+                (long long)npix, C);
+  RVO_CHECK_ARG(t16 && out16, "rvo_in_apply: null pointer");
+  RVO_CHECK_ARG(res16 || !sums_res, "rvo_in_apply: shortcut statistics without a shortcut");
+  if (npix == 0) return RVO_OK;
+  int64_t grid = (npix * (C / 8) + 255) / 256;
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  in_apply_kernel<<<(int)grid, 256, 4 * (size_t)C * sizeof(float), (cudaStream_t)stream>>>(
+      (const __half*)t16, sums_t, (const __half*)res16, sums_res, npix, C, eps, (__half*)out16);
+  RVO_LAUNCH_CHECK("in_apply_kernel");
+  return RVO_OK;
+}
+
+// ------------------------------------------------------------------ recurrent stem ----
+//
+// One scale of MultiScaleMergerDoubleNet.forward (ramp/extractor.py:540-560) for ONE event stack and
+// ONE image: for both modalities the strided conv_1 (:326-345), the per-pixel LSTM cell evaluated
+// for a single step from a zero state (:351-381; gates i, g, o only — f multiplies c0 = 0), then the
+// recurrent super state  ss <- W_ev [ss ; h_ev] + b,  ss <- W_im [ss ; h_im] + b  (:404-411,
+// :446-452).  The reference spends ~20 launches per scale on this (two convs, two cuDNN RNN calls
+// with batch = H*W plus permute/contiguous round trips, cats and two 1x1 convs); here it is one
+// kernel: a CTA owns 64 output pixels, keeps every parameter of the scale in shared memory and
+// chains the two small GEMMs ([64 x 2h] x [2h x h]) through shared memory.  fp32 arithmetic,
+// channels-last fp16 state in / out.
+namespace rvo {
+
+constexpr int kStemPix = 64;
+constexpr int kStemThreads = 256;
+
+struct StemParams {
+  int Ce, Ci, k, stride, pad, h;
+  int H, W, Ho, Wo;
+  // offsets (in floats) into the packed parameter buffer
+  int o_wce, o_bce, o_wci, o_bci, o_wge, o_bge, o_wgi, o_bgi, o_wse, o_bse, o_wsi, o_bsi, n_params;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+template <int HID>
+__global__ void __launch_bounds__(kStemThreads)
+stem_kernel(StemParams sp, const float* __restrict__ params, const float* __restrict__ events,
+            const float* __restrict__ image, const __half* __restrict__ ss_prev, int use_image,
+            __half* __restrict__ ss_out) {
+  extern __shared__ float sm[];
+  constexpr int LD = 2 * HID + 1;                 // padded row stride of the GEMM inputs
+  float* P = sm;                                  // packed parameters
+  float* xin = P + sp.n_params;                   // [8][64] conv_1 outputs (5 event + 3 image)
+  float* inA = xin + 8 * kStemPix;                // [64][LD] = [ss_prev | h_ev]
+  float* inB = inA + kStemPix * LD;               // [64][LD] = [ss_1    | h_im]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < sp.n_params; i += kStemThreads) P[i] = params[i];
+  const int npix = sp.Ho * sp.Wo;
+  const int p0 = blockIdx.x * kStemPix;
+  __syncthreads();
+
+  // phase 1: conv_1 of both modalities
+  {
+    const int px = tid & 63, grp = tid >> 6;
+    const int p = p0 + px;
+    if (p < npix && grp < 3) {
+      const int oy = p / sp.Wo, ox = p - oy * sp.Wo;
+      const bool ev = grp < 2;
+      const int Cin = ev ? sp.Ce : sp.Ci;
+      const float* src = ev ? events : image;
+      const float* Wc = P + (ev ? sp.o_wce : sp.o_wci);
+      const float* bc = P + (ev ? sp.o_bce : sp.o_bci);
+      const int c_lo = ev ? (grp == 0 ? 0 : 3) : 0;
+      const int c_hi = ev ? (grp == 0 ? min(3, Cin) : Cin) : Cin;
+      float acc[3] = {0.f, 0.f, 0.f};
+      for (int ci = 0; ci < Cin; ci++)
+        for (int ky = 0; ky < sp.k; ky++) {
+          const int iy = oy * sp.stride - sp.pad + ky;
+          if (iy < 0 || iy >= sp.H) continue;
+          for (int kx = 0; kx < sp.k; kx++) {
+            const int ix = ox * sp.stride - sp.pad + kx;
+            if (ix < 0 || ix >= sp.W) continue;
+            const float v = src[((size_t)ci * sp.H + iy) * sp.W + ix];
+            for (int co = c_lo; co < c_hi; co++)
+              acc[co - c_lo] += v * Wc[((co * Cin + ci) * sp.k + ky) * sp.k + kx];
+          }
+        }
+      for (int co = c_lo; co < c_hi; co++)
+        xin[((ev ? 0 : 5) + co) * kStemPix + px] = acc[co - c_lo] + bc[co];
+    }
+  }
+  // previous super state -> inA[:, 0:h)
+  for (int i = tid; i < kStemPix * HID; i += kStemThreads) {
+    const int px = i / HID, c = i - px * HID;
+    const int p = p0 + px;
+    float v = 0.f;
+    if (ss_prev && p < npix) v = __half2float(ss_prev[(size_t)p * HID + c]);
+    inA[px * LD + c] = v;
+  }
+  __syncthreads();
+
+  // phase 2: LSTM cell, one step from a zero state: h = sig(o) * tanh(sig(i) * tanh(g))
+  for (int idx = tid; idx < 2 * kStemPix * HID; idx += kStemThreads) {
+    const int mod = idx / (kStemPix * HID);
+    const int rem = idx - mod * (kStemPix * HID);
+    const int j = rem / kStemPix, px = rem - j * kStemPix;
+    const int Cin = mod ? sp.Ci : sp.Ce;
+    const float* Wg = P + (mod ? sp.o_wgi : sp.o_wge);
+    const float* bg = P + (mod ? sp.o_bgi : sp.o_bge);
+    const float* xv = xin + (mod ? 5 : 0) * kStemPix + px;
+    float gi = bg[j], gg = bg[HID + j], go = bg[2 * HID + j];
+    for (int c = 0; c < Cin; c++) {
+      const float v = xv[c * kStemPix];
+      gi += v * Wg[j * Cin + c];
+      gg += v * Wg[(HID + j) * Cin + c];
+      go += v * Wg[(2 * HID + j) * Cin + c];
+    }
+    const float hval = sigmoidf_(go) * tanhf(sigmoidf_(gi) * tanhf(gg));
+    (mod ? inB : inA)[px * LD + HID + j] = hval;
+  }
+  __syncthreads();
+
+  // phases 3 / 4: ss <- W [ss ; h] + b, thread tile = R pixels x 4 channels
+  constexpr int C4 = HID / 4;                       // channel quads
+  constexpr int PXG = kStemThreads / C4;            // pixels covered per pass
+  constexpr int R = kStemPix / PXG;                 // passes (pixels per thread)
+  const int c4 = tid % C4, pxb = tid / C4;
+  for (int stage = 0; stage < 2; stage++) {
+    if (stage == 1 && !use_image) break;
+    const float* in = stage ? inB : inA;
+    const float* Wt = P + (stage ? sp.o_wsi : sp.o_wse);          // transposed [2h][h]
+    const float* bs = P + (stage ? sp.o_bsi : sp.o_bse);
+    float acc[R][4];
+#pragma unroll
+    for (int m = 0; m < R; m++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc[m][q] = bs[c4 * 4 + q];
+#pragma unroll 4
+    for (int k = 0; k < 2 * HID; k++) {
+      const float4 w = *reinterpret_cast<const float4*>(Wt + k * HID + c4 * 4);
+#pragma unroll
+      for (int m = 0; m < R; m++) {
+        const float a = in[(pxb + m * PXG) * LD + k];
+        acc[m][0] += a * w.x; acc[m][1] += a * w.y; acc[m][2] += a * w.z; acc[m][3] += a * w.w;
+      }
+    }
+    const bool last = (stage == 1) || !use_image;
+#pragma unroll
+    for (int m = 0; m < R; m++) {
+      const int px = pxb + m * PXG;
+      if (last) {
+        const int p = p0 + px;
+        if (p < npix) {
+          const __half2 a = __floats2half2_rn(acc[m][0], acc[m][1]);
+          const __half2 b = __floats2half2_rn(acc[m][2], acc[m][3]);
+          uint2 u;
+          u.x = *reinterpret_cast<const uint32_t*>(&a);
+          u.y = *reinterpret_cast<const uint32_t*>(&b);
+          *reinterpret_cast<uint2*>(ss_out + (size_t)p * HID + c4 * 4) = u;
+        }
+      } else {
+        // the reference stores the intermediate state in fp16 under autocast
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          inB[px * LD + c4 * 4 + q] = __half2float(__float2half_rn(acc[m][q]));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace rvo
+
+extern "C" int rvo_stem_forward(const float* params, int Ce, int Ci, int k, int stride, int pad, int h,
+                                const float* events, const float* image, int H, int W,
+                                const void* ss_prev16, int use_image, void* ss_out16, void* stream) {
+  RVO_CHECK_ARG(params && events && image && ss_out16, "rvo_stem_forward: null pointer");
+  RVO_CHECK_ARG(Ce >= 1 && Ce <= 5 && Ci >= 1 && Ci <= 3, "rvo_stem_forward: Ce=%d Ci=%d (<= 5 / <= 3)", Ce, Ci);
+  RVO_CHECK_ARG(h == 16 || h == 32 || h == 64, "rvo_stem_forward: hidden size %d (16/32/64)", h);
+  RVO_CHECK_ARG(k >= 1 && stride >= 1 && pad >= 0 && H > 0 && W > 0, "rvo_stem_forward: bad geometry");
+  StemParams sp;
+  sp.Ce = Ce; sp.Ci = Ci; sp.k = k; sp.stride = stride; sp.pad = pad; sp.h = h;
+  sp.H = H; sp.W = W;
+  sp.Ho = (H + 2 * pad - k) / stride + 1;
+  sp.Wo = (W + 2 * pad - k) / stride + 1;
+  int o = 0;
+  sp.o_wce = o; o += Ce * Ce * k * k;  sp.o_bce = o; o += Ce;
+  sp.o_wci = o; o += Ci * Ci * k * k;  sp.o_bci = o; o += Ci;
+  sp.o_wge = o; o += 3 * h * Ce;       sp.o_bge = o; o += 3 * h;
+  sp.o_wgi = o; o += 3 * h * Ci;       sp.o_bgi = o; o += 3 * h;
+  o = (o + 3) & ~3;                    // float4 alignment of the transposed state weights
+  sp.o_wse = o; o += 2 * h * h;        sp.o_bse = o; o += h;
+  o = (o + 3) & ~3;
+  sp.o_wsi = o; o += 2 * h * h;        sp.o_bsi = o; o += h;
+  sp.n_params = (o + 3) & ~3;
+  const size_t smem = ((size_t)sp.n_params + 8 * kStemPix + 2 * (size_t)kStemPix * (2 * h + 1)) * sizeof(float);
+  const int grid = (sp.Ho * sp.Wo + kStemPix - 1) / kStemPix;
+  cudaStream_t st = (cudaStream_t)stream;
+#define RVO_STEM(HID)                                                                              \
+  do {                                                                                             \
+    RVO_CUDA(cudaFuncSetAttribute(stem_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                  (int)smem));                                                     \
+    stem_kernel<HID><<<grid, kStemThreads, smem, st>>>(sp, params, events, image,                  \
+                                                       (const __half*)ss_prev16, use_image,        \
+                                                       (__half*)ss_out16);                         \
+  } while (0)
+  if (h == 16) RVO_STEM(16);
+  else if (h == 32) RVO_STEM(32);
+  else RVO_STEM(64);
+#undef RVO_STEM
+  RVO_LAUNCH_CHECK("stem_kernel");
+  return RVO_OK;
+}
+
+// layout of the packed parameter buffer (floats), for the host side
+extern "C" int rvo_stem_params_layout(int Ce, int Ci, int k, int h, int* offsets12, int* total) {
+  RVO_CHECK_ARG(offsets12 && total, "rvo_stem_params_layout: null pointer");
+  int o = 0, i = 0;
+  offsets12[i++] = o; o += Ce * Ce * k * k;  offsets12[i++] = o; o += Ce;
+  offsets12[i++] = o; o += Ci * Ci * k * k;  offsets12[i++] = o; o += Ci;
+  offsets12[i++] = o; o += 3 * h * Ce;       offsets12[i++] = o; o += 3 * h;
+  offsets12[i++] = o; o += 3 * h * Ci;       offsets12[i++] = o; o += 3 * h;
+  o = (o + 3) & ~3;
+  offsets12[i++] = o; o += 2 * h * h;        offsets12[i++] = o; o += h;
+  o = (o + 3) & ~3;
+  offsets12[i++] = o; o += 2 * h * h;        offsets12[i++] = o; o += h;
+  *total = (o + 3) & ~3;
+  return RVO_OK;
+}

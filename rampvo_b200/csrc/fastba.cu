@@ -666,7 +666,7 @@ static int ba_solve(const BaWs& w, float* poses, float* patches, const float* Sy
     const size_t smem = in_smem ? solve_smem_bytes(n6) : 2 * (size_t)n6 * sizeof(float);
     RVO_CUDA(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)kSmemMax));
-    const dim3 threads(32, n6 <= 64 ? 8 : (n6 <= 128 ? 16 : 32));
+    const dim3 threads(32, n6 <= 24 ? 8 : 32);
     ba_solve_kernel<<<1, threads, smem, st>>>(Sy, N, t0, poses, w.dX, in_smem ? nullptr : w.A);
     RVO_LAUNCH_CHECK("ba_solve_kernel");
   }
@@ -785,12 +785,12 @@ extern "C" int rvo_ba_solve(float* poses, float* patches, const float* Sy, int E
   return ba_solve(w, poses, patches, Sy ? Sy : w.Sy, cap, P, t0, t1, (cudaStream_t)stream);
 }
 
-extern "C" int rvo_ba_forward(float* poses, float* patches, const float* intrinsics,
-                              const float* target, const float* weight, const float* lmbda,
-                              const int64_t* ii, const int64_t* jj, const int64_t* kk, int E,
-                              int64_t n_poses, int64_t n_patches, int P, int PPF, int t0, int t1,
-                              int iterations, int eff_impl, void* ws, int64_t ws_bytes,
-                              void* stream) {
+static int ba_forward_impl(float* poses, float* patches, const float* intrinsics,
+                           const float* target, const float* weight, const float* lmbda,
+                           const int64_t* ii, const int64_t* jj, const int64_t* kk, int E,
+                           int64_t n_poses, int64_t n_patches, int P, int PPF, int t0, int t1,
+                           int iterations, int eff_impl, const void* ext_plan, void* ws,
+                           int64_t ws_bytes, void* stream) {
   (void)PPF; (void)eff_impl;  // block-sparse E is the only implementation; results do not depend on it
   int rc = ba_check("rvo_ba_forward", poses, patches, intrinsics, E, P, t0, t1);
   if (rc != RVO_OK) return rc;
@@ -798,14 +798,18 @@ extern "C" int rvo_ba_forward(float* poses, float* patches, const float* intrins
   RVO_CHECK_ARG(n_poses <= 0 || t1 <= n_poses, "rvo_ba_forward: t1=%d exceeds %lld poses", t1,
                 (long long)n_poses);
   if (E == 0 || iterations == 0) return RVO_OK;
-  RVO_CHECK_ARG(target && weight && lmbda && ii && jj && kk && ws, "rvo_ba_forward: null pointer");
+  RVO_CHECK_ARG(target && weight && lmbda && ii && jj && (kk || ext_plan) && ws, "rvo_ba_forward: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t cap = patch_cap(E, n_patches);
   BaWs w = ba_layout(ws, E, cap, t1 - t0);
   RVO_CHECK_ARG((int64_t)w.total <= ws_bytes, "rvo_ba_forward: workspace %lld < %lld bytes",
                 (long long)ws_bytes, (long long)w.total);
-  rc = build_plan(kk, jj, E, n_patches, n_poses, ws, (int64_t)w.plan.total, st, nullptr);
-  if (rc != RVO_OK) return rc;
+  if (ext_plan) {
+    w.plan = plan_layout(const_cast<void*>(ext_plan), E);   // reuse the caller's (kk, jj) plan
+  } else {
+    rc = build_plan(kk, jj, E, n_patches, n_poses, ws, (int64_t)w.plan.total, st, nullptr);
+    if (rc != RVO_OK) return rc;
+  }
   for (int it = 0; it < iterations; it++) {
     rc = ba_assemble(w, poses, patches, intrinsics, target, weight, lmbda, ii, jj, E, cap, P, t0, t1,
                      w.Sy, st);
@@ -814,6 +818,26 @@ extern "C" int rvo_ba_forward(float* poses, float* patches, const float* intrins
     if (rc != RVO_OK) return rc;
   }
   return RVO_OK;
+}
+
+extern "C" int rvo_ba_forward(float* poses, float* patches, const float* intrinsics,
+                              const float* target, const float* weight, const float* lmbda,
+                              const int64_t* ii, const int64_t* jj, const int64_t* kk, int E,
+                              int64_t n_poses, int64_t n_patches, int P, int PPF, int t0, int t1,
+                              int iterations, int eff_impl, void* ws, int64_t ws_bytes,
+                              void* stream) {
+  return ba_forward_impl(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, E, n_poses,
+                         n_patches, P, PPF, t0, t1, iterations, eff_impl, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int rvo_ba_forward_planned(float* poses, float* patches, const float* intrinsics,
+                                      const float* target, const float* weight, const float* lmbda,
+                                      const int64_t* ii, const int64_t* jj, const void* plan, int E,
+                                      int64_t n_poses, int64_t n_patches, int P, int t0, int t1,
+                                      int iterations, void* ws, int64_t ws_bytes, void* stream) {
+  RVO_CHECK_ARG(plan || E == 0, "rvo_ba_forward_planned: null plan");
+  return ba_forward_impl(poses, patches, intrinsics, target, weight, lmbda, ii, jj, nullptr, E, n_poses,
+                         n_patches, P, 0, t0, t1, iterations, 0, plan, ws, ws_bytes, stream);
 }
 
 extern "C" int rvo_ba_forward_host(float* poses, float* patches, const float* intrinsics,

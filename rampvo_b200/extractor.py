@@ -15,7 +15,44 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib
+
 DIM = 32
+CL = torch.channels_last
+
+
+def _fast(x):
+    """The fused channels-last fp16 path: CUDA, inference, mixed precision (Ramp_vo.py:23,331)."""
+    return x.is_cuda and torch.is_autocast_enabled() and not torch.is_grad_enabled()
+
+
+def _conv16(conv, x):
+    """cuDNN convolution on fp16 channels-last operands with cached fp16 weights."""
+    w = getattr(conv, "_w16", None)
+    if w is None:
+        w = conv._w16 = (conv.weight.detach().half().contiguous(memory_format=CL),
+                         conv.bias.detach().half())
+    with torch.autocast("cuda", enabled=False):
+        y = F.conv2d(x, w[0], w[1], stride=conv.stride, padding=conv.padding)
+    return y if y.is_contiguous(memory_format=CL) else y.contiguous(memory_format=CL)
+
+
+def _stats(t):
+    """InstanceNorm2d statistics of a [1,C,H,W] channels-last fp16 tensor -> device [2C] sums."""
+    C = t.shape[1]
+    sums = torch.empty(2 * C, dtype=torch.float32, device=t.device)
+    _lib.check(_lib.lib().rvo_in_stats(_lib.ptr(t), t.shape[2] * t.shape[3], C, _lib.ptr(sums),
+                                       _lib.stream_ptr(t.device)), "rvo_in_stats")
+    return sums
+
+
+def _apply(t, st=None, res=None, sr=None):
+    """relu( [IN](res) + relu( [IN](t) ) ) in one pass (rvo_in_apply)."""
+    out = torch.empty_like(t, memory_format=CL)
+    _lib.check(_lib.lib().rvo_in_apply(_lib.ptr(t), _lib.ptr(st), _lib.ptr(res), _lib.ptr(sr),
+                                       t.shape[2] * t.shape[3], t.shape[1], 1e-5, _lib.ptr(out),
+                                       _lib.stream_ptr(t.device)), "rvo_in_apply")
+    return out
 
 
 class ResidualBlock(nn.Module):
@@ -36,7 +73,20 @@ class ResidualBlock(nn.Module):
     def _norm(self, x):
         return F.instance_norm(x) if self.instance else x
 
+    def _forward_fast(self, x):
+        """x: [1,C,H,W] fp16 channels-last.  conv -> stats -> apply, twice."""
+        t = _conv16(self.conv1, x)
+        y = _apply(t, _stats(t) if self.instance else None)
+        t = _conv16(self.conv2, y)
+        st = _stats(t) if self.instance else None
+        if self.downsample is not None:
+            d = _conv16(self.downsample[0], x)
+            return _apply(t, st, d, _stats(d) if self.instance else None)
+        return _apply(t, st, x)
+
     def forward(self, x):
+        if _fast(x) and x.shape[0] == 1:
+            return self._forward_fast(x)
         y = F.relu(self._norm(self.conv1(x)))
         y = F.relu(self._norm(self.conv2(y)))
         if self.downsample is not None:
@@ -68,6 +118,13 @@ class MultiScaleBasicEncoder4(nn.Module):
 
     def forward(self, x, x_down2, x_down4):
         """x [1,16,H,W], x_down2 [1,32,H/2,W/2], x_down4 [1,64,H/4,W/4] -> [1,out,H/4,W/4]."""
+        if _fast(x) and x.shape[0] == 1:
+            h16 = lambda t: t.half().contiguous(memory_format=CL)
+            t = _conv16(self.conv1, h16(x))
+            x = _apply(t, _stats(t) if self.instance else None)
+            x = self.layer1(x)
+            x = self.layer3(torch.cat((x, h16(x_down2)), dim=1).contiguous(memory_format=CL))
+            return _conv16(self.conv3, torch.cat((x, h16(x_down4)), dim=1).contiguous(memory_format=CL))
         x = self.conv1(x)
         if self.instance:
             x = F.instance_norm(x)
@@ -145,13 +202,71 @@ class MultiScaleMergerDoubleNet(nn.Module):
     def reset_state(self):
         self.super_states = [None, None, None]
 
+    def _stem_params(self, k, device):
+        """Packed fp32 parameters of scale k in the layout rvo_stem_params_layout reports."""
+        cache = getattr(self, "_stem_cache", None)
+        if cache is None:
+            cache = self._stem_cache = {}
+        if k in cache and cache[k][0].device == device:
+            return cache[k]
+        import ctypes
+        ev, im = self.ev_encoders[k], self.im_encoders[k]
+        se, si = self.super_state_ev_encoder[k].encoder, self.super_state_im_encoders[k].encoder
+        h, Ce, Ci = ev.hidden, ev.conv_1.in_channels, im.conv_1.in_channels
+        ks, st, pd = ev.conv_1.kernel_size[0], ev.conv_1.stride[0], ev.conv_1.padding[0]
+        offs = (ctypes.c_int * 12)()
+        total = ctypes.c_int(0)
+        _lib.check(_lib.lib().rvo_stem_params_layout(Ce, Ci, ks, h, offs, ctypes.byref(total)),
+                   "rvo_stem_params_layout")
+        buf = torch.zeros(total.value, dtype=torch.float32)
+        rows = lambda w: torch.cat([w[0:h], w[2 * h:3 * h], w[3 * h:4 * h]], 0)   # gates i, g, o
+        parts = [ev.conv_1.weight, ev.conv_1.bias, im.conv_1.weight, im.conv_1.bias,
+                 rows(ev.convlstm.weight_ih_l0), rows(ev.convlstm.bias_ih_l0 + ev.convlstm.bias_hh_l0),
+                 rows(im.convlstm.weight_ih_l0), rows(im.convlstm.bias_ih_l0 + im.convlstm.bias_hh_l0),
+                 se.weight.reshape(h, 2 * h).t(), se.bias, si.weight.reshape(h, 2 * h).t(), si.bias]
+        for o, t in zip(offs, parts):
+            t = t.detach().float().cpu().contiguous().reshape(-1)
+            buf[o:o + t.numel()] = t
+        cache[k] = (buf.to(device), (Ce, Ci, ks, st, pd, h))
+        return cache[k]
+
+    def _forward_fast(self, events, images, use_image, reinit_hidden):
+        """One event stack + (optionally) one image: the fused stem kernel per scale, then the two
+        channels-last CNNs."""
+        ev = events[0, 0].float().contiguous()
+        im = images[0, 0].float().contiguous()
+        H, W = ev.shape[-2:]
+        L = _lib.lib()
+        st = _lib.stream_ptr(ev.device)
+        per_scale = []
+        for k in range(3):
+            if reinit_hidden:
+                self.super_states[k] = None
+            buf, (Ce, Ci, ks, sd, pd, h) = self._stem_params(k, ev.device)
+            Ho, Wo = (H + 2 * pd - ks) // sd + 1, (W + 2 * pd - ks) // sd + 1
+            prev = self.super_states[k]
+            if prev is not None and not (prev.dtype == torch.float16 and prev.is_contiguous(memory_format=CL)):
+                prev = prev.half().contiguous(memory_format=CL)
+            out = torch.empty(1, h, Ho, Wo, dtype=torch.float16, device=ev.device, memory_format=CL)
+            _lib.check(L.rvo_stem_forward(_lib.ptr(buf), Ce, Ci, ks, sd, pd, h, _lib.ptr(ev), _lib.ptr(im),
+                                          H, W, _lib.ptr(prev), int(use_image), _lib.ptr(out), st),
+                       "rvo_stem_forward")
+            self.super_states[k] = out
+            per_scale.append(out)
+        fmap = self.fmap_encoder(per_scale[0], per_scale[1], per_scale[2])
+        imap = self.imap_encoder(per_scale[0], per_scale[1], per_scale[2])
+        return fmap[None], imap[None]
+
     def forward(self, events, images, mask, reinit_hidden=False):
         """events [1,T,Ce,H,W], images [1,Ti,3,H,W], mask [T] bool (one image per True entry)
         -> fmap [1,n,128,H/4,W/4], imap [1,n,384,H/4,W/4] with n = number of images consumed
         (n = 1 with the states of the last event voxel when no image arrived, extractor.py:455)."""
+        mask = torch.as_tensor(mask).reshape(-1).tolist()
+        if (_fast(events) and events.shape[1] == 1 and len(mask) == 1 and not self.norm_superstate
+                and images.shape[1] >= 1):
+            return self._forward_fast(events, images, bool(mask[0]), reinit_hidden)
         ev = events[0].contiguous(memory_format=torch.channels_last)
         im = images[0].contiguous(memory_format=torch.channels_last)
-        mask = torch.as_tensor(mask).reshape(-1).tolist()
         per_scale = []
         for k in range(3):
             if reinit_hidden:

@@ -53,9 +53,12 @@ class GraphPlans:
     """Device-side bookkeeping shared by one update: the (kk, jj) plan gives `neighbors` and the
     agg_kk groups, the (ii*12345+jj) plan gives the agg_ij groups (net.py:77,84-85)."""
 
-    def __init__(self, ii, jj, kk, kmax=0, jmax=0):
+    def __init__(self, ii, jj, kk, kmax=0, jmax=0, max_patches=0, max_pairs=0):
         L = _lib.lib()
         self.E = E = ii.numel()
+        # upper bounds on the number of groups (0 = E); they size the per-group GEMM of SoftAgg.h
+        self.cap_k = min(E, max_patches) if max_patches else E
+        self.cap_ij = min(E, max_pairs) if max_pairs else E
         dev = ii.device
         nb = L.rvo_plan_bytes(E)
         self.plan_k = torch.empty(nb, dtype=torch.uint8, device=dev)
@@ -109,23 +112,129 @@ class Update(nn.Module):
         _lib.check(L.rvo_expand_add(_lib.ptr(hy), _lib.dtype_code(hy), _lib.ptr(plan), E, x.shape[1],
                                     _lib.ptr(x), st), "rvo_expand_add")
 
+    # ---- mixed-precision fused path -------------------------------------------------------
+    def _fused_weights(self):
+        """fp16 copies of the Linear weights (concatenated where two layers share an input) and
+        fp32 LayerNorm / head parameters, cached for inference."""
+        w = getattr(self, "_fw", None)
+        if w is not None:
+            return w
+        h = lambda t: t.detach().to(torch.float16).contiguous()
+        f = lambda t: t.detach().float().contiguous()
+        w = {}
+        for name, lin in (("corr0", self.corr[0]), ("corr2", self.corr[2]), ("corr5", self.corr[5]),
+                          ("c1a", self.c1[0]), ("c1b", self.c1[2]), ("c2a", self.c2[0]), ("c2b", self.c2[2]),
+                          ("kk_h", self.agg_kk.h), ("ij_h", self.agg_ij.h),
+                          ("g1_gate", self.gru[1].gate[0]), ("g1_a", self.gru[1].res[0]), ("g1_b", self.gru[1].res[2]),
+                          ("g3_gate", self.gru[3].gate[0]), ("g3_a", self.gru[3].res[0]), ("g3_b", self.gru[3].res[2])):
+            w[name] = (h(lin.weight), h(lin.bias))
+        for name, agg in (("kk_fg", self.agg_kk), ("ij_fg", self.agg_ij)):
+            w[name] = (h(torch.cat([agg.f.weight, agg.g.weight], 0)), h(torch.cat([agg.f.bias, agg.g.bias], 0)))
+        for name, ln in (("ln_corr", self.corr[3]), ("ln_norm", self.norm), ("ln_g0", self.gru[0]), ("ln_g2", self.gru[2])):
+            w[name] = (f(ln.weight), f(ln.bias))
+        w["corr0p"] = F.pad(w["corr0"][0], (0, 896 - w["corr0"][0].shape[1])).contiguous()   # K 882 -> 896
+        # heads run in fp16 under autocast: keep fp16-rounded values, stored fp32 for the kernel
+        w["d"] = (f(h(self.d[1].weight)), f(h(self.d[1].bias)))
+        w["w"] = (f(h(self.w[1].weight)), f(h(self.w[1].bias)))
+        self._fw = w
+        return w
+
+    def invalidate_cache(self):
+        self._fw = None
+
+    def _forward_fused(self, net, inp, corr, ii, jj, kk, plans):
+        """Same arithmetic and dtypes as the reference under autocast, 17 fp16 GEMMs + 13 fused
+        kernels instead of ~250 launches.  inp: [1,E,384] tensor or (imap_table [N,384] fp16, idx, mod)."""
+        L = _lib.lib()
+        W = self._fused_weights()
+        E = ii.numel()
+        dev = net.device
+        st = _lib.stream_ptr(dev)
+        P = _lib.ptr
+        lin = lambda x, k: F.linear(x, W[k][0], W[k][1])
+        lin_relu = lambda x, k: torch._addmm_activation(W[k][1], x, W[k][0].t())
+        f16 = lambda: torch.empty(E, DIM, dtype=torch.float16, device=dev)
+        f32 = lambda: torch.empty(E, DIM, dtype=torch.float32, device=dev)
+
+        K0 = corr.shape[-1]
+        if corr.dtype == torch.float16 and corr.stride(-1) == 1 and corr.stride(-2) == 896 and K0 == 882:
+            c = torch.as_strided(corr, (E, 896), (896, 1), corr.storage_offset())   # zero-padded rows
+            h = torch._addmm_activation(W["corr0"][1], c, W["corr0p"].t())
+        else:
+            c = corr.reshape(E, -1).to(torch.float16).contiguous()
+            h = lin_relu(c, "corr0")
+        h = lin(h, "corr2")
+        h3 = f16()
+        _lib.check(L.rvo_up_ln_relu(P(h), P(W["ln_corr"][0]), P(W["ln_corr"][1]), E, DIM, P(h3), st), "rvo_up_ln_relu")
+        h4 = lin(h3, "corr5")
+        if isinstance(inp, tuple):
+            table, idx, mod = inp
+            table = table.reshape(-1, DIM)
+        else:
+            table, idx, mod = inp.reshape(E, DIM).to(torch.float16).contiguous(), torch.arange(E, device=dev), 0
+        net_in = net.reshape(E, DIM).float().contiguous()
+        x = f32()
+        _lib.check(L.rvo_up_add3_ln(P(net_in), P(table), P(idx), mod, P(h4), P(W["ln_norm"][0]),
+                                    P(W["ln_norm"][1]), E, DIM, P(x), st), "rvo_up_add3_ln")
+        g = f16()
+        x16 = f16()
+        for ka, kb, nbr, last in (("c1a", "c1b", plans.ix, False), ("c2a", "c2b", plans.jx, True)):
+            _lib.check(L.rvo_gather_rows(P(x), P(nbr), E, DIM, P(g), _lib.RVO_F16, st), "rvo_gather_rows")
+            t = lin(lin_relu(g, ka), kb)
+            _lib.check(L.rvo_up_add_cast(P(x), P(t), E, DIM, P(x16) if last else None, st), "rvo_up_add_cast")
+        n32, n16 = f32(), f16()
+        for kfg, kh, plan, cap, with_ln in (("kk_fg", "kk_h", plans.plan_k, plans.cap_k, False),
+                                            ("ij_fg", "ij_h", plans.plan_ij, plans.cap_ij, True)):
+            fg = lin(x16, kfg)                                              # [E, 768] = [f | g]
+            y = torch.empty(cap, DIM, dtype=torch.float16, device=dev)
+            _lib.check(L.rvo_up_softagg_fg(P(fg), P(plan), E, DIM, cap, P(y), st), "rvo_up_softagg_fg")
+            hy = lin(y, kh)
+            if with_ln:
+                _lib.check(L.rvo_up_expand_add_ln(P(hy), P(plan), E, DIM, P(x), None, P(W["ln_g0"][0]),
+                                                  P(W["ln_g0"][1]), P(n32), P(n16), st), "rvo_up_expand_add_ln")
+            else:
+                _lib.check(L.rvo_up_expand_add_ln(P(hy), P(plan), E, DIM, P(x), P(x16), None, None, None,
+                                                  None, st), "rvo_up_expand_add_ln")
+        # gru: LN (done) -> GatedResidual -> LN -> GatedResidual -> heads
+        a = lin(n16, "g1_gate")
+        r = lin(lin_relu(n16, "g1_a"), "g1_b")
+        m32, m16 = f32(), f16()
+        _lib.check(L.rvo_up_gated_tail(P(n32), P(a), P(r), E, DIM, 0, P(W["ln_g2"][0]), P(W["ln_g2"][1]),
+                                       P(m32), P(m16), None, None, None, None, None, None, st), "rvo_up_gated_tail")
+        a = lin(m16, "g3_gate")
+        r = lin(lin_relu(m16, "g3_a"), "g3_b")
+        out = torch.empty(1, E, DIM, dtype=torch.float32, device=dev)
+        delta = torch.empty(1, E, 2, dtype=torch.float32, device=dev)
+        weight = torch.empty(1, E, 2, dtype=torch.float32, device=dev)
+        _lib.check(L.rvo_up_gated_tail(P(m32), P(a), P(r), E, DIM, 1, None, None, P(out), None,
+                                       P(W["d"][0]), P(W["d"][1]), P(W["w"][0]), P(W["w"][1]), P(delta),
+                                       P(weight), st), "rvo_up_gated_tail")
+        return out, (delta, weight, None)
+
     def forward(self, net, inp, corr, flow, ii, jj, kk, plans=None):
         """net [1,E,384], inp [1,E,384], corr [1,E,882], ii/jj/kk [E] ->
-        (net [1,E,384] fp32, (delta [1,E,2], weight [1,E,2], None)).  `plans` (extension): a
-        GraphPlans built once per graph; built here when omitted."""
-        _lib.require_cuda(net, inp, corr, ii, jj, kk)
+        (net [1,E,384] fp32, (delta [1,E,2], weight [1,E,2], None)).  Extensions: `plans`, a
+        GraphPlans built once per graph (built here when omitted); `inp` may be the tuple
+        (imap_table, index, modulo) so that the context gather is fused.  Under autocast the fused
+        mixed-precision path runs; otherwise the generic path in the tensors' own dtype."""
+        _lib.require_cuda(net, corr, ii, jj, kk)
         E = ii.numel()
         if plans is None:
             plans = GraphPlans(ii, jj, kk)
-        L = _lib.lib()
         dev = net.device
+        if torch.is_autocast_enabled() and E > 0:
+            with torch.cuda.device(dev), torch.autocast("cuda", enabled=False):
+                return self._forward_fused(net, inp, corr, ii, jj, kk, plans)
+        if isinstance(inp, tuple):
+            table, idx, mod = inp
+            inp = table.reshape(-1, DIM)[(idx % mod) if mod else idx][None]
+        L = _lib.lib()
         st = _lib.stream_ptr(dev)
         with torch.cuda.device(dev):
             net = net.float() + inp.float() + self.corr(corr).float()
             net = self.norm(net).float().contiguous()                     # [1,E,384] fp32
             x = net[0]
-            gdt = torch.float16 if torch.is_autocast_enabled() else torch.float32
-            g = torch.empty(E, DIM, dtype=gdt, device=dev)
+            g = torch.empty(E, DIM, dtype=torch.float32, device=dev)
             for mlp, idx in ((self.c1, plans.ix), (self.c2, plans.jx)):
                 _lib.check(L.rvo_gather_rows(_lib.ptr(x), _lib.ptr(idx), E, DIM, _lib.ptr(g),
                                              _lib.dtype_code(g), st), "rvo_gather_rows")
@@ -156,10 +265,11 @@ class Patchifier(nn.Module):
                 gradient_bias=False, gmap_out=None):
         events, images, mask = input_
         fmap, imap = self.encoder(events=events, images=images, mask=mask, reinit_hidden=reinit_hidden)
-        mask_t = torch.as_tensor(mask).reshape(-1)
-        if not bool(mask_t.any()):
+        mask_l = torch.as_tensor(mask).reshape(-1).tolist()       # host-side, like evaluate.py:163
+        if not any(mask_l):
             return None, None, None, None, None, None
-        events = events[:, mask_t.to(events.device)] if events.shape[1] == mask_t.numel() else events
+        if events.shape[1] == len(mask_l) and not all(mask_l):
+            events = events[:, [t for t, keep in enumerate(mask_l) if keep]]
         fmap = fmap / 4.0
         imap = imap / 4.0
         b, n, c, h, w = fmap.shape

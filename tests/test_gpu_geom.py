@@ -91,3 +91,30 @@ def test_empty_graph(prob):
     e = torch.zeros(0, dtype=torch.long, device="cuda")
     assert pops.transform(SE3(t["poses"]), t["patches"], t["intrinsics"], e, e, e).shape == (1, 0, 3, 3, 2)
     assert fastba.reproject(t["poses"], t["patches"], t["intrinsics"], e, e, e).shape == (1, 0, 2, 3, 3)
+
+
+def test_motion_model_and_pair_flow_kernels(prob):
+    """rvo_motion_model vs the tensor SE3 layer (Ramp_vo.py:356-363), rvo_pair_flow vs flow_mag means."""
+    from rampvo_b200 import _lib
+    t = problem_tensors(prob)
+    poses = t["poses"][0].clone()
+    n = 6
+    P1, P2 = SE3(poses[n - 1].double()), SE3(poses[n - 2].double())
+    exp = (SE3.exp(0.5 * (P1 * P2.inv()).log()) * P1).data.cpu().numpy()
+    _lib.check(_lib.lib().rvo_motion_model(_lib.ptr(poses), n, 0.5, _lib.stream_ptr()), "mm")
+    assert np.abs(poses[n].cpu().numpy() - exp).max() < 1e-5
+    # identical consecutive poses: Log = 0 (Taylor branches)
+    poses[3] = poses[2]
+    _lib.check(_lib.lib().rvo_motion_model(_lib.ptr(poses), 4, 0.5, _lib.stream_ptr()), "mm")
+    assert (poses[4] - poses[3]).abs().max().item() < 1e-6
+    i, j = 2, 5
+    out4 = torch.empty(4, device="cuda")
+    _lib.check(_lib.lib().rvo_pair_flow(_lib.ptr(t["poses"]), _lib.ptr(t["patches"]), _lib.ptr(t["intrinsics"]),
+                                        _lib.ptr(t["ii"]), _lib.ptr(t["jj"]), _lib.ptr(t["kk"]), prob["E"], 3,
+                                        i, j, 0.5, _lib.ptr(out4), _lib.stream_ptr()), "pf")
+    s1, c1, s2, c2 = out4.tolist()
+    for (a, b, s, c) in ((i, j, s1, c1), (j, i, s2, c2)):
+        k = (prob["ii"] == a) & (prob["jj"] == b)
+        ref = O.flow_mag(prob["poses"], prob["patches"], prob["intrinsics"], prob["ii"][k], prob["jj"][k],
+                         prob["kk"][k], beta=0.5)
+        assert c == ref.size and abs(s / c - ref.mean()) < 2e-3
