@@ -145,6 +145,9 @@ class Ramp_vo:
         self.fmap2_ = self._fmap2_store.permute(0, 3, 1, 2)[None]
         self.pyramid = (self.fmap1_, self.fmap2_)
 
+        # hidden state of the edges: two ping-pong buffers [1, capacity, DIM]; self.net is a view
+        self._net_bufs = [None, None]
+        self._net_cur = 0
         self.net = torch.zeros(1, 0, DIM, device=dev, dtype=torch.float)
         self.ii = torch.as_tensor([], dtype=torch.long, device=dev)
         self.jj = torch.as_tensor([], dtype=torch.long, device=dev)
@@ -241,22 +244,50 @@ class Ramp_vo:
         intrinsics = intrinsics if intrinsics is not None else self.intrinsics
         return pops.reproject_cf(SE3(poses), patches, intrinsics, ii, jj, kk)
 
+    def _net_reserve(self, E_new):
+        """make both hidden-state buffers hold at least E_new edges, keeping self.net's content"""
+        cur = self._net_bufs[self._net_cur]
+        if cur is not None and cur.shape[1] >= E_new:
+            return
+        cap = max(E_new * 5 // 4, 4096)
+        E0 = self.net.shape[1]
+        new = [torch.zeros(1, cap, self.DIM, device=self.device, dtype=torch.float) for _ in range(2)]
+        new[0][:, :E0] = self.net
+        self._net_bufs, self._net_cur = new, 0
+        self.net = new[0][:, :E0]
+
+    def _net_other(self, E):
+        """the [1,E,DIM] view of the buffer self.net does NOT live in (output of the next stage)"""
+        self._net_reserve(max(E, self.net.shape[1]))
+        return self._net_bufs[1 - self._net_cur][:, :E]
+
+    def _net_swap(self, E):
+        self._net_cur = 1 - self._net_cur
+        self.net = self._net_bufs[self._net_cur][:, :E]
+
     def append_factors(self, ii, jj):
-        """add factors to the graph (Ramp_vo.py:194-201)"""
+        """add factors to the graph (Ramp_vo.py:194-201); new edges start with a zero hidden state"""
         self.jj = torch.cat([self.jj, jj])
         self.kk = torch.cat([self.kk, ii])
         self.ii = torch.cat([self.ii, self.ix[ii]])
-        net = torch.zeros(1, len(ii), self.DIM, device=self.device, dtype=self.net.dtype)
-        self.net = torch.cat([self.net, net], dim=1)
+        E0, n = self.net.shape[1], len(ii)
+        self._net_reserve(E0 + n)
+        buf = self._net_bufs[self._net_cur]
+        buf[:, E0:E0 + n].zero_()
+        self.net = buf[:, :E0 + n]
         self._plans = None
 
     def remove_factors(self, m):
         """remove factors from the graph (Ramp_vo.py:203-208)"""
-        keep = ~m
+        keep = (~m).nonzero().view(-1)
+        if keep.numel() == m.numel():
+            return
         self.ii = self.ii[keep]
         self.jj = self.jj[keep]
         self.kk = self.kk[keep]
-        self.net = self.net[:, keep]
+        out = self._net_other(keep.numel())
+        torch.index_select(self.net, 1, keep, out=out)
+        self._net_swap(keep.numel())
         self._plans = None
 
     def _graph_plans(self):
@@ -337,8 +368,13 @@ class Ramp_vo:
         with torch.autocast("cuda", enabled=self.autocast):
             corr = self.corr(coords)
             ctx = (self.imap_, self.kk, self.M * self.mem)     # imap[:, kk % (M*mem)], gather fused
-            self.net, (delta, weight, _) = self.network.update(self.net, ctx, corr, None, self.ii,
-                                                               self.jj, self.kk, plans=plans)
+            E = self.ii.numel()
+            new_net, (delta, weight, _) = self.network.update(self.net, ctx, corr, None, self.ii, self.jj,
+                                                              self.kk, plans=plans,
+                                                              net_out=self._net_other(E))
+            if new_net.data_ptr() != self._net_bufs[1 - self._net_cur].data_ptr():
+                self._net_other(E).copy_(new_net)   # generic (non-fused) path returned its own tensor
+            self._net_swap(E)
         weight = weight.float()
         target = coords[..., self.P // 2, self.P // 2] + delta.float()
         weight = filter_features(confidences=weight, target=target,

@@ -163,6 +163,8 @@ struct StemParams {
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// tanh(x) = 1 - 2 / (1 + e^{2x}); saturates correctly for |x| large (e^{2x} -> inf or 0)
+__device__ __forceinline__ float tanhf_(float x) { return 1.0f - 2.0f / (1.0f + __expf(2.0f * x)); }
 
 template <int HID>
 __global__ void __launch_bounds__(kStemThreads)
@@ -181,35 +183,33 @@ stem_kernel(StemParams sp, const float* __restrict__ params, const float* __rest
   const int p0 = blockIdx.x * kStemPix;
   __syncthreads();
 
-  // phase 1: conv_1 of both modalities
-  {
-    const int px = tid & 63, grp = tid >> 6;
+  // phase 1: conv_1 of both modalities.  One (pixel, output channel) item per thread step; taps
+  // outside the image use a clamped address and a zero weight so that the loads stay independent
+  // (no early-outs) and many are in flight.
+  for (int item = tid; item < kStemPix * 8; item += kStemThreads) {
+    const int px = item & 63, ch = item >> 6;        // ch 0..4 events, 5..7 image
     const int p = p0 + px;
-    if (p < npix && grp < 3) {
-      const int oy = p / sp.Wo, ox = p - oy * sp.Wo;
-      const bool ev = grp < 2;
-      const int Cin = ev ? sp.Ce : sp.Ci;
-      const float* src = ev ? events : image;
-      const float* Wc = P + (ev ? sp.o_wce : sp.o_wci);
-      const float* bc = P + (ev ? sp.o_bce : sp.o_bci);
-      const int c_lo = ev ? (grp == 0 ? 0 : 3) : 0;
-      const int c_hi = ev ? (grp == 0 ? min(3, Cin) : Cin) : Cin;
-      float acc[3] = {0.f, 0.f, 0.f};
-      for (int ci = 0; ci < Cin; ci++)
-        for (int ky = 0; ky < sp.k; ky++) {
-          const int iy = oy * sp.stride - sp.pad + ky;
-          if (iy < 0 || iy >= sp.H) continue;
-          for (int kx = 0; kx < sp.k; kx++) {
-            const int ix = ox * sp.stride - sp.pad + kx;
-            if (ix < 0 || ix >= sp.W) continue;
-            const float v = src[((size_t)ci * sp.H + iy) * sp.W + ix];
-            for (int co = c_lo; co < c_hi; co++)
-              acc[co - c_lo] += v * Wc[((co * Cin + ci) * sp.k + ky) * sp.k + kx];
-          }
+    const bool ev = ch < 5;
+    const int Cin = ev ? sp.Ce : sp.Ci, co = ev ? ch : ch - 5;
+    if (p >= npix || co >= Cin) continue;
+    const int oy = p / sp.Wo, ox = p - oy * sp.Wo;
+    const float* src = ev ? events : image;
+    const float* Wc = P + (ev ? sp.o_wce : sp.o_wci) + co * Cin * sp.k * sp.k;
+    float acc = P[(ev ? sp.o_bce : sp.o_bci) + co];
+    for (int ci = 0; ci < Cin; ci++)
+      for (int ky = 0; ky < sp.k; ky++) {
+        const int iy = oy * sp.stride - sp.pad + ky;
+        const bool oky = (unsigned)iy < (unsigned)sp.H;
+        const float* row = src + ((size_t)ci * sp.H + (oky ? iy : 0)) * sp.W;
+#pragma unroll 5
+        for (int kx = 0; kx < sp.k; kx++) {
+          const int ix = ox * sp.stride - sp.pad + kx;
+          const bool ok = oky && (unsigned)ix < (unsigned)sp.W;
+          const float v = row[ok ? ix : 0];
+          acc += (ok ? Wc[(ci * sp.k + ky) * sp.k + kx] : 0.f) * v;
         }
-      for (int co = c_lo; co < c_hi; co++)
-        xin[((ev ? 0 : 5) + co) * kStemPix + px] = acc[co - c_lo] + bc[co];
-    }
+      }
+    xin[ch * kStemPix + px] = acc;
   }
   // previous super state -> inA[:, 0:h)
   for (int i = tid; i < kStemPix * HID; i += kStemThreads) {
@@ -237,7 +237,7 @@ stem_kernel(StemParams sp, const float* __restrict__ params, const float* __rest
       gg += v * Wg[(HID + j) * Cin + c];
       go += v * Wg[(2 * HID + j) * Cin + c];
     }
-    const float hval = sigmoidf_(go) * tanhf(sigmoidf_(gi) * tanhf(gg));
+    const float hval = sigmoidf_(go) * tanhf_(sigmoidf_(gi) * tanhf_(gg));
     (mod ? inB : inA)[px * LD + HID + j] = hval;
   }
   __syncthreads();

@@ -142,7 +142,7 @@ class Update(nn.Module):
     def invalidate_cache(self):
         self._fw = None
 
-    def _forward_fused(self, net, inp, corr, ii, jj, kk, plans):
+    def _forward_fused(self, net, inp, corr, ii, jj, kk, plans, net_out=None):
         """Same arithmetic and dtypes as the reference under autocast, 17 fp16 GEMMs + 13 fused
         kernels instead of ~250 launches.  inp: [1,E,384] tensor or (imap_table [N,384] fp16, idx, mod)."""
         L = _lib.lib()
@@ -203,7 +203,7 @@ class Update(nn.Module):
                                        P(m32), P(m16), None, None, None, None, None, None, st), "rvo_up_gated_tail")
         a = lin(m16, "g3_gate")
         r = lin(lin_relu(m16, "g3_a"), "g3_b")
-        out = torch.empty(1, E, DIM, dtype=torch.float32, device=dev)
+        out = net_out if net_out is not None else torch.empty(1, E, DIM, dtype=torch.float32, device=dev)
         delta = torch.empty(1, E, 2, dtype=torch.float32, device=dev)
         weight = torch.empty(1, E, 2, dtype=torch.float32, device=dev)
         _lib.check(L.rvo_up_gated_tail(P(m32), P(a), P(r), E, DIM, 1, None, None, P(out), None,
@@ -211,11 +211,12 @@ class Update(nn.Module):
                                        P(weight), st), "rvo_up_gated_tail")
         return out, (delta, weight, None)
 
-    def forward(self, net, inp, corr, flow, ii, jj, kk, plans=None):
+    def forward(self, net, inp, corr, flow, ii, jj, kk, plans=None, net_out=None):
         """net [1,E,384], inp [1,E,384], corr [1,E,882], ii/jj/kk [E] ->
         (net [1,E,384] fp32, (delta [1,E,2], weight [1,E,2], None)).  Extensions: `plans`, a
         GraphPlans built once per graph (built here when omitted); `inp` may be the tuple
-        (imap_table, index, modulo) so that the context gather is fused.  Under autocast the fused
+        (imap_table, index, modulo) so that the context gather is fused; `net_out`, a contiguous
+        fp32 [1,E,384] buffer for the new hidden state (fused path only).  Under autocast the fused
         mixed-precision path runs; otherwise the generic path in the tensors' own dtype."""
         _lib.require_cuda(net, corr, ii, jj, kk)
         E = ii.numel()
@@ -224,7 +225,7 @@ class Update(nn.Module):
         dev = net.device
         if torch.is_autocast_enabled() and E > 0:
             with torch.cuda.device(dev), torch.autocast("cuda", enabled=False):
-                return self._forward_fused(net, inp, corr, ii, jj, kk, plans)
+                return self._forward_fused(net, inp, corr, ii, jj, kk, plans, net_out)
         if isinstance(inp, tuple):
             table, idx, mod = inp
             inp = table.reshape(-1, DIM)[(idx % mod) if mod else idx][None]
