@@ -264,6 +264,11 @@ int rvo_ba_assemble(const float* poses, const float* patches, const float* intri
 int rvo_ba_solve(float* poses, float* patches, const float* Sy, int E, int64_t n_patches, int P,
                  int t0, int t1, void* ws, int64_t ws_bytes, void* stream);
 
+/* The replicated half of rvo_ba_solve alone (damping, Cholesky, pose retraction) for a rank that
+ * owns no edge of the current window; ws: rvo_ba_ws_bytes(1, 1, t1-t0) bytes or more. */
+int rvo_ba_solve_poses(float* poses, const float* Sy, int t0, int t1, void* ws, int64_t ws_bytes,
+                       void* stream);
+
 /* Host-buffer variant of rvo_ba_forward (all pointers HOST; poses/patches copied back). */
 int rvo_ba_forward_host(float* poses, float* patches, const float* intrinsics, const float* target,
                         const float* weight, const float* lmbda, const int64_t* ii,

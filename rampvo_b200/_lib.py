@@ -77,6 +77,7 @@ _SIGNATURES = {
     "rvo_up_expand_add_ln": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "rvo_up_gated_tail": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                   _P, _P]),
+    "rvo_ba_solve_poses": (c_int, [_P, _P, c_int, c_int, _P, _I64, _P]),
     "rvo_ba_forward_host": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, _I64, c_int,
                                     c_int, c_int, c_int, c_int, c_int, _P]),
 }

@@ -820,6 +820,24 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
   return RVO_OK;
 }
 
+extern "C" int rvo_ba_solve_poses(float* poses, const float* Sy, int t0, int t1, void* ws,
+                                  int64_t ws_bytes, void* stream) {
+  RVO_CHECK_ARG(poses && Sy && ws && t0 >= 0 && t1 >= t0, "rvo_ba_solve_poses: bad arguments");
+  const int N = t1 - t0, n6 = 6 * N;
+  if (N == 0) return RVO_OK;
+  BaWs w = ba_layout(ws, 1, 1, N);
+  RVO_CHECK_ARG((int64_t)w.total <= ws_bytes, "rvo_ba_solve_poses: workspace too small");
+  const bool in_smem = solve_smem_bytes(n6) <= kSmemMax;
+  const size_t smem = in_smem ? solve_smem_bytes(n6) : 2 * (size_t)n6 * sizeof(float);
+  RVO_CUDA(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)kSmemMax));
+  const dim3 threads(32, n6 <= 24 ? 8 : 32);
+  ba_solve_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(Sy, N, t0, poses, w.dX,
+                                                              in_smem ? nullptr : w.A);
+  RVO_LAUNCH_CHECK("ba_solve_kernel");
+  return RVO_OK;
+}
+
 extern "C" int rvo_ba_forward(float* poses, float* patches, const float* intrinsics,
                               const float* target, const float* weight, const float* lmbda,
                               const int64_t* ii, const int64_t* jj, const int64_t* kk, int E,
