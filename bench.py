@@ -114,13 +114,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    state = {}
+
     def timed(step_fn, first, profile=False):
         for t in range(first, first + W):
             step_fn(t)
         barrier()
         sampler = ClockSampler(local)
         sampler.start()
-        l0 = L.rvo_launch_count()
+        l0 = L.rvo_launch_count() + state["vo"].graph_kernel_launches
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if profile:
             torch.cuda.profiler.start()      # `ncu --profile-from-start off` captures only this region
@@ -133,7 +135,7 @@ def run_ours(args):
             torch.cuda.profiler.stop()
         sampler.stop_flag = True
         ms = a.elapsed_time(b)
-        launches = L.rvo_launch_count() - l0
+        launches = L.rvo_launch_count() + state["vo"].graph_kernel_launches - l0
         sampler.join(timeout=2)
         if world > 1:
             tt = torch.tensor([ms], device=dev)
@@ -143,6 +145,7 @@ def run_ours(args):
 
     with torch.no_grad():
         vo = build_vo(dev)
+        state["vo"] = vo
         for t in range(SETUP_FRAMES):
             vo(t, frames[t], intr)
 

@@ -246,6 +246,15 @@ int rvo_ba_forward_planned(float* poses, float* patches, const float* intrinsics
                            int64_t n_poses, int64_t n_patches, int P, int t0, int t1, int iterations,
                            void* ws, int64_t ws_bytes, void* stream);
 
+/* rvo_ba_forward_planned whose window start t0 lives in DEVICE memory (t0_dev[0]; the window is
+ * [t0, t0 + n_free)): every host-side scalar of the call is then constant from frame to frame, so a
+ * CUDA graph that contains the whole recurrent update can be replayed while the window slides. */
+int rvo_ba_forward_dyn(float* poses, float* patches, const float* intrinsics, const float* target,
+                       const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
+                       const void* plan, int E, int64_t n_poses, int64_t n_patches, int P, int n_free,
+                       const int32_t* t0_dev, int iterations, void* ws, int64_t ws_bytes,
+                       void* stream);
+
 /* One Gauss-Newton iteration in three steps, split where a patch graph sharded by source frame
  * needs its all-reduce:
  *   rvo_ba_plan      once per graph: sort / group the edges into `ws`;

@@ -62,10 +62,12 @@ class _PatchifyGraph:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         enc.super_states = list(self.state)
+        l0 = _lib.lib().rvo_launch_count()
         with torch.cuda.graph(self.graph):
             self._body(first=False)
             for buf, new in zip(self.state, enc.super_states):
                 buf.copy_(new)
+        self.n_kernels = _lib.lib().rvo_launch_count() - l0   # librampvo kernels inside the graph
         enc.super_states = saved
         for b in self.state:
             b.zero_()
@@ -97,7 +99,58 @@ class _PatchifyGraph:
         self.ev.copy_(events)
         self.im.copy_(images)
         self.graph.replay()
+        self.vo.graph_kernel_launches += self.n_kernels
         enc.super_states = list(self.state)
+
+
+class _UpdateGraph:
+    """CUDA graph of one recurrent update for a fixed edge count E and window length: static copies
+    of ii/jj/kk, the graph-plan sorts, reproject, corr, the update operator and both BA iterations.
+    The sliding window start t0 is a device scalar (rvo_ba_forward_dyn)."""
+
+    def __init__(self, vo, E, n_free):
+        self.vo = vo
+        dev = vo.device
+        self.ii = torch.zeros(E, dtype=torch.long, device=dev)
+        self.jj = torch.zeros(E, dtype=torch.long, device=dev)
+        self.kk = torch.zeros(E, dtype=torch.long, device=dev)
+        self.t0 = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.n_free = n_free
+        self.net_in = vo.net                     # view of the current ping-pong buffer
+        self.net_out = vo._net_other(E)
+        self._load(vo.n - n_free)
+        vo.corr(vo.reproject())                  # sizes the persistent corr buffer outside the capture
+        snap = (vo.poses_.clone(), vo.patches_.clone(), self.net_in.clone())
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):                   # warm-up (workspaces, cuBLAS handles) on a side stream
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        vo.poses_.copy_(snap[0]); vo.patches_.copy_(snap[1]); self.net_in.copy_(snap[2])
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = _lib.lib().rvo_launch_count()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        self.n_kernels = _lib.lib().rvo_launch_count() - l0   # librampvo kernels inside the graph
+        vo.poses_.copy_(snap[0]); vo.patches_.copy_(snap[1]); self.net_in.copy_(snap[2])
+
+    def _load(self, t0):
+        vo = self.vo
+        self.ii.copy_(vo.ii); self.jj.copy_(vo.jj); self.kk.copy_(vo.kk)
+        self.t0.fill_(t0)
+
+    def _body(self):
+        vo = self.vo
+        plans = vo._new_plans(self.ii, self.jj, self.kk)
+        _, self.weight = vo._update_body(self.ii, self.jj, self.kk, self.net_in, self.net_out, plans,
+                                         0, self.n_free, t0_dev=self.t0)
+
+    def run(self, t0):
+        self._load(t0)
+        self.graph.replay()
+        self.vo.graph_kernel_launches += self.n_kernels
 
 
 class Ramp_vo:
@@ -156,6 +209,9 @@ class Ramp_vo:
         self.use_graphs = use_graphs
         self._pgraph = None         # _PatchifyGraph, captured at the first frame
         self._corr_buf = None       # [1, capacity, 896] correlation rows (882 used)
+        self._ugraphs = {}          # (E, window, buffer parity) -> _UpdateGraph
+        self._ukey_prev, self._ukey_hist = None, []
+        self.graph_kernel_launches = 0   # librampvo kernels executed through CUDA-graph replays
 
         self.poses_[:, 6] = 1.0
         self.delta = {}
@@ -292,10 +348,7 @@ class Ramp_vo:
 
     def _graph_plans(self):
         if self._plans is None:
-            frames = self.cfg.REMOVAL_WINDOW + 2        # source frames that can still own edges
-            self._plans = GraphPlans(self.ii, self.jj, self.kk, kmax=self.N * self.M, jmax=self.N,
-                                     max_patches=frames * self.M,
-                                     max_pairs=frames * (2 * self.cfg.PATCH_LIFETIME + 1))
+            self._plans = self._new_plans(self.ii, self.jj, self.kk)
         return self._plans
 
     @torch.no_grad()
@@ -359,38 +412,72 @@ class Ramp_vo:
             self.m -= self.M
         self.remove_factors(self.ix[self.kk] < self.n - self.cfg.REMOVAL_WINDOW)
 
-    @torch.no_grad()
-    def update(self):
-        """one recurrent update: reproject -> corr -> update operator -> 2 BA iterations
-        (Ramp_vo.py:276-310)"""
-        coords = self.reproject()
-        plans = self._graph_plans()
+    def _update_body(self, ii, jj, kk, net_in, net_out, plans, t0, t1, t0_dev=None):
+        """reproject -> corr -> update operator -> 2 BA iterations on explicit buffers; every
+        host-side scalar is either constant across frames or read from device memory (t0_dev)"""
+        coords = self.reproject(indicies=(ii, jj, kk))
         with torch.autocast("cuda", enabled=self.autocast):
-            corr = self.corr(coords)
-            ctx = (self.imap_, self.kk, self.M * self.mem)     # imap[:, kk % (M*mem)], gather fused
-            E = self.ii.numel()
-            new_net, (delta, weight, _) = self.network.update(self.net, ctx, corr, None, self.ii, self.jj,
-                                                              self.kk, plans=plans,
-                                                              net_out=self._net_other(E))
-            if new_net.data_ptr() != self._net_bufs[1 - self._net_cur].data_ptr():
-                self._net_other(E).copy_(new_net)   # generic (non-fused) path returned its own tensor
-            self._net_swap(E)
+            corr = self.corr(coords, indicies=(kk, jj))
+            ctx = (self.imap_, kk, self.M * self.mem)     # imap[:, kk % (M*mem)], gather fused
+            new_net, (delta, weight, _) = self.network.update(net_in, ctx, corr, None, ii, jj, kk,
+                                                              plans=plans, net_out=net_out)
         weight = weight.float()
         target = coords[..., self.P // 2, self.P // 2] + delta.float()
         weight = filter_features(confidences=weight, target=target,
                                  data_shape=(self.ht // 4, self.wd // 4))
-        self.last_weight = weight
+        fastba.BA(self.poses, self.patches, self.intrinsics, target, weight, self.lmbda, ii, jj, kk,
+                  t0, t1, M=self.M, iterations=2, eff_impl=False, plan=plans.plan_k, t0_dev=t0_dev)
+        return new_net, weight
+
+    def _new_plans(self, ii, jj, kk):
+        frames = self.cfg.REMOVAL_WINDOW + 2        # source frames that can still own edges
+        return GraphPlans(ii, jj, kk, kmax=self.N * self.M, jmax=self.N, max_patches=frames * self.M,
+                          max_pairs=frames * (2 * self.cfg.PATCH_LIFETIME + 1))
+
+    @torch.no_grad()
+    def update(self):
+        """one recurrent update: reproject -> corr -> update operator -> 2 BA iterations
+        (Ramp_vo.py:276-310).  With use_graphs the whole body (incl. the graph-plan sorts) is a CUDA
+        graph keyed by (edge count, window length), replayed while the window slides."""
+        E = self.ii.numel()
         t0 = self.n - self.cfg.OPTIMIZATION_WINDOW if self.is_initialized else 1
         t0 = max(t0, 1)
-        try:
-            fastba.BA(self.poses, self.patches, self.intrinsics, target, weight, self.lmbda, self.ii,
-                      self.jj, self.kk, t0, self.n, M=self.M, iterations=2, eff_impl=False,
-                      plan=plans.plan_k)
-        except RuntimeError as e:   # BA failure is non-fatal, like the reference (:302-306)
-            print(f"WARNING: BA failed...{e}")
+        key = (E, self.n - t0, self._net_cur)
+        repeat = key == self._ukey_prev or key in self._ukey_hist   # capture only shapes that recur
+        self._ukey_hist = (self._ukey_hist + [self._ukey_prev])[-4:]
+        self._ukey_prev = key
+        if (self.use_graphs and self.autocast and E > 0 and self.network.update._fused_ready()
+                and (repeat or (key + (self._net_bufs[0].data_ptr(),)) in self._ugraphs)):
+            try:
+                self._update_graphed(E, t0, self.n)
+            except RuntimeError as e:   # BA failure is non-fatal, like the reference (:302-306)
+                print(f"WARNING: BA failed...{e}")
+        else:
+            plans = self._graph_plans()
+            other = self._net_other(E)
+            try:
+                new_net, weight = self._update_body(self.ii, self.jj, self.kk, self.net, other, plans,
+                                                    t0, self.n)
+                if new_net.data_ptr() != other.data_ptr():
+                    other.copy_(new_net)   # generic (non-fused) path returned its own tensor
+                self._net_swap(E)
+                self.last_weight = weight
+            except RuntimeError as e:
+                print(f"WARNING: BA failed...{e}")
         pts = pops.point_cloud_centers(SE3(self.poses), self.patches[:, :self.m], self.intrinsics,
                                        self.ix[:self.m])
         self.points_[:len(pts)] = pts
+
+    def _update_graphed(self, E, t0, t1):
+        key = (E, t1 - t0, self._net_cur, self._net_bufs[0].data_ptr())
+        g = self._ugraphs.get(key)
+        if g is None:
+            if len(self._ugraphs) >= 8:              # bounded cache: drop the oldest capture
+                self._ugraphs.pop(next(iter(self._ugraphs)))
+            g = self._ugraphs[key] = _UpdateGraph(self, E, t1 - t0)
+        g.run(t0)
+        self._net_swap(E)
+        self.last_weight = g.weight
 
     def _edges_forw(self):
         r = self.cfg.PATCH_LIFETIME

@@ -63,6 +63,8 @@ _SIGNATURES = {
                                c_int, c_int, c_int, c_int, _P, _I64, _P]),
     "rvo_ba_forward_planned": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, _I64, c_int,
                                        c_int, c_int, c_int, _P, _I64, _P]),
+    "rvo_ba_forward_dyn": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, _I64, c_int, c_int,
+                                   _P, c_int, _P, _I64, _P]),
     "rvo_ba_plan": (c_int, [_P, _P, c_int, _I64, _I64, c_int, _P, _I64, _P]),
     "rvo_ba_assemble": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, c_int, c_int, c_int,
                                 _P, _P, _I64, _P]),

@@ -230,10 +230,11 @@ ba_assemble_kernel(const int32_t* __restrict__ count, const int32_t* __restrict_
                    const float* __restrict__ poses, const float* __restrict__ patches,
                    const float* __restrict__ intr, const float* __restrict__ target,
                    const float* __restrict__ weight, const float* __restrict__ lmbda,
-                   const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, int P, int t0,
-                   int N, int cap, float* __restrict__ Sy_g, float* __restrict__ Qg,
-                   float* __restrict__ ug, float* __restrict__ Eg) {
+                   const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, int P, int t0_arg,
+                   const int32_t* __restrict__ t0_dev, int N, int cap, float* __restrict__ Sy_g,
+                   float* __restrict__ Qg, float* __restrict__ ug, float* __restrict__ Eg) {
   extern __shared__ float sm[];
+  const int t0 = t0_dev ? t0_dev[0] : t0_arg;   // device-side window start keeps CUDA graphs replayable
   const int n6 = 6 * N, ld = n6 + 1;
   float* S = SMEM_S ? sm : Sy_g;                       // [n6][ld] upper triangle + y column
   float* Ew = sm + (SMEM_S ? (size_t)n6 * ld : 0);     // [W][n6]  E_k rows of this round
@@ -494,9 +495,10 @@ __device__ __forceinline__ void retr_se3(const float* xi, float* t, float* q) {
 // trailing update); row n comes out as z = L^-1 y, then one warp solves L^T dX = z
 // (ba_cuda.cu:558-562) with warp-level synchronisation only.
 __global__ void __launch_bounds__(1024)
-ba_solve_kernel(const float* __restrict__ Sy, int N, int t0, float* __restrict__ poses,
-                float* __restrict__ dX_g, float* __restrict__ A_g) {
+ba_solve_kernel(const float* __restrict__ Sy, int N, int t0_arg, const int32_t* __restrict__ t0_dev,
+                float* __restrict__ poses, float* __restrict__ dX_g, float* __restrict__ A_g) {
   extern __shared__ float sm[];
+  const int t0 = t0_dev ? t0_dev[0] : t0_arg;
   const int n = 6 * N, ld = n + 1;
   const int la = (n + 1) | 1;                              // odd row stride: conflict-free columns
   float* A = A_g ? A_g : sm;                              // [(n+1)][la]
@@ -629,7 +631,8 @@ static inline int64_t patch_cap(int E, int64_t n_patches) {
 static int ba_assemble(const BaWs& w, const float* poses, const float* patches,
                        const float* intrinsics, const float* target, const float* weight,
                        const float* lmbda, const int64_t* ii, const int64_t* jj, int E, int64_t cap,
-                       int P, int t0, int t1, float* Sy_out, cudaStream_t st) {
+                       int P, int t0, int t1, float* Sy_out, cudaStream_t st,
+                       const int32_t* t0_dev = nullptr) {
   const int N = t1 - t0, n6 = 6 * N;
   if (n6 > 0) RVO_CUDA(cudaMemsetAsync(Sy_out, 0, (size_t)n6 * (n6 + 1) * sizeof(float), st));
   const bool smem_s = assemble_smem_bytes(n6, true) <= kSmemMax;
@@ -643,11 +646,11 @@ static int ba_assemble(const BaWs& w, const float* poses, const float* patches,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     ba_assemble_kernel<true><<<grid, kBaThreads, smem, st>>>(
         w.plan.count, w.plan.perm, w.plan.seg_start, w.plan.kx, poses, patches, intrinsics, target,
-        weight, lmbda, ii, jj, P, t0, N, (int)cap, Sy_out, w.Qg, w.ug, w.Eg);
+        weight, lmbda, ii, jj, P, t0, t0_dev, N, (int)cap, Sy_out, w.Qg, w.ug, w.Eg);
   } else {
     ba_assemble_kernel<false><<<grid, kBaThreads, smem, st>>>(
         w.plan.count, w.plan.perm, w.plan.seg_start, w.plan.kx, poses, patches, intrinsics, target,
-        weight, lmbda, ii, jj, P, t0, N, (int)cap, Sy_out, w.Qg, w.ug, w.Eg);
+        weight, lmbda, ii, jj, P, t0, t0_dev, N, (int)cap, Sy_out, w.Qg, w.ug, w.Eg);
   }
   RVO_LAUNCH_CHECK("ba_assemble_kernel");
   if (n6 > 0) {
@@ -659,7 +662,7 @@ static int ba_assemble(const BaWs& w, const float* poses, const float* patches,
 }
 
 static int ba_solve(const BaWs& w, float* poses, float* patches, const float* Sy, int64_t cap, int P,
-                    int t0, int t1, cudaStream_t st) {
+                    int t0, int t1, cudaStream_t st, const int32_t* t0_dev = nullptr) {
   const int N = t1 - t0, n6 = 6 * N;
   if (N > 0) {
     const bool in_smem = solve_smem_bytes(n6) <= kSmemMax;
@@ -667,7 +670,7 @@ static int ba_solve(const BaWs& w, float* poses, float* patches, const float* Sy
     RVO_CUDA(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)kSmemMax));
     const dim3 threads(32, n6 <= 24 ? 8 : 32);
-    ba_solve_kernel<<<1, threads, smem, st>>>(Sy, N, t0, poses, w.dX, in_smem ? nullptr : w.A);
+    ba_solve_kernel<<<1, threads, smem, st>>>(Sy, N, t0, t0_dev, poses, w.dX, in_smem ? nullptr : w.A);
     RVO_LAUNCH_CHECK("ba_solve_kernel");
   }
   int64_t warps = cap;
@@ -790,7 +793,7 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
                            const int64_t* ii, const int64_t* jj, const int64_t* kk, int E,
                            int64_t n_poses, int64_t n_patches, int P, int PPF, int t0, int t1,
                            int iterations, int eff_impl, const void* ext_plan, void* ws,
-                           int64_t ws_bytes, void* stream) {
+                           int64_t ws_bytes, void* stream, const int32_t* t0_dev = nullptr) {
   (void)PPF; (void)eff_impl;  // block-sparse E is the only implementation; results do not depend on it
   int rc = ba_check("rvo_ba_forward", poses, patches, intrinsics, E, P, t0, t1);
   if (rc != RVO_OK) return rc;
@@ -812,9 +815,9 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
   }
   for (int it = 0; it < iterations; it++) {
     rc = ba_assemble(w, poses, patches, intrinsics, target, weight, lmbda, ii, jj, E, cap, P, t0, t1,
-                     w.Sy, st);
+                     w.Sy, st, t0_dev);
     if (rc != RVO_OK) return rc;
-    rc = ba_solve(w, poses, patches, w.Sy, cap, P, t0, t1, st);
+    rc = ba_solve(w, poses, patches, w.Sy, cap, P, t0, t1, st, t0_dev);
     if (rc != RVO_OK) return rc;
   }
   return RVO_OK;
@@ -832,7 +835,7 @@ extern "C" int rvo_ba_solve_poses(float* poses, const float* Sy, int t0, int t1,
   RVO_CUDA(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)kSmemMax));
   const dim3 threads(32, n6 <= 24 ? 8 : 32);
-  ba_solve_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(Sy, N, t0, poses, w.dX,
+  ba_solve_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(Sy, N, t0, nullptr, poses, w.dX,
                                                               in_smem ? nullptr : w.A);
   RVO_LAUNCH_CHECK("ba_solve_kernel");
   return RVO_OK;
@@ -856,6 +859,18 @@ extern "C" int rvo_ba_forward_planned(float* poses, float* patches, const float*
   RVO_CHECK_ARG(plan || E == 0, "rvo_ba_forward_planned: null plan");
   return ba_forward_impl(poses, patches, intrinsics, target, weight, lmbda, ii, jj, nullptr, E, n_poses,
                          n_patches, P, 0, t0, t1, iterations, 0, plan, ws, ws_bytes, stream);
+}
+
+extern "C" int rvo_ba_forward_dyn(float* poses, float* patches, const float* intrinsics,
+                                  const float* target, const float* weight, const float* lmbda,
+                                  const int64_t* ii, const int64_t* jj, const void* plan, int E,
+                                  int64_t n_poses, int64_t n_patches, int P, int n_free,
+                                  const int32_t* t0_dev, int iterations, void* ws, int64_t ws_bytes,
+                                  void* stream) {
+  RVO_CHECK_ARG(plan || E == 0, "rvo_ba_forward_dyn: null plan");
+  RVO_CHECK_ARG(t0_dev && n_free >= 0, "rvo_ba_forward_dyn: needs the device-side window start");
+  return ba_forward_impl(poses, patches, intrinsics, target, weight, lmbda, ii, jj, nullptr, E, 0,
+                         n_patches, P, 0, 0, n_free, iterations, 0, plan, ws, ws_bytes, stream, t0_dev);
 }
 
 extern "C" int rvo_ba_forward_host(float* poses, float* patches, const float* intrinsics,

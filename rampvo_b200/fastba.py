@@ -37,11 +37,13 @@ def _flat(t, name, last):
 
 
 def BA(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, M, iterations,
-       eff_impl=False, plan=None):
+       eff_impl=False, plan=None, t0_dev=None):
     """ramp.fastba.BA (ba.py:7 -> cuda_ba.forward, ba_cuda.cu:433-582).  Mutates `poses`
     (rows t0..t1-1) and the inverse depths in `patches` IN PLACE and returns [] like the reference.
     `poses` may be a lietorch SE3 (its .data is used, ba.py:8).  `plan` (extension): the device
-    buffer of an rvo_graph_plan(kk, jj) built for the same edge list — skips the edge sort."""
+    buffer of an rvo_graph_plan(kk, jj) built for the same edge list — skips the edge sort;
+    `t0_dev` (extension, needs `plan`): int32 device scalar holding t0, read by the kernels instead of
+    the host value so that a captured CUDA graph stays valid while the window slides (t1 - t0 fixed)."""
     poses = getattr(poses, "data", poses)
     _lib.require_cuda(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk)
     P = patches.shape[-1]
@@ -59,6 +61,14 @@ def BA(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, M,
     n_poses, n_patches = pv.shape[0], qv.shape[0]
     nb = L.rvo_ba_ws_bytes(E, n_patches, max(t1 - t0, 0))
     ws = _lib.Workspace.get(pv.device, nb, "ba")
+    if plan is not None and t0_dev is not None:
+        with torch.cuda.device(pv.device):
+            _lib.check(L.rvo_ba_forward_dyn(_lib.ptr(pv), _lib.ptr(qv), _lib.ptr(kv), _lib.ptr(tv),
+                                            _lib.ptr(wv), _lib.ptr(lm), _lib.ptr(ii), _lib.ptr(jj),
+                                            _lib.ptr(plan), E, n_poses, n_patches, P, int(t1 - t0),
+                                            _lib.ptr(t0_dev), int(iterations), _lib.ptr(ws), ws.numel(),
+                                            _lib.stream_ptr()), "rvo_ba_forward_dyn")
+        return []
     if plan is not None:
         with torch.cuda.device(pv.device):
             _lib.check(L.rvo_ba_forward_planned(_lib.ptr(pv), _lib.ptr(qv), _lib.ptr(kv), _lib.ptr(tv),

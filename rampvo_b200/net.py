@@ -142,6 +142,10 @@ class Update(nn.Module):
     def invalidate_cache(self):
         self._fw = None
 
+    def _fused_ready(self):
+        """the fused mixed-precision path needs CUDA parameters (it has no other requirement)"""
+        return self.norm.weight.is_cuda
+
     def _forward_fused(self, net, inp, corr, ii, jj, kk, plans, net_out=None):
         """Same arithmetic and dtypes as the reference under autocast, 17 fp16 GEMMs + 13 fused
         kernels instead of ~250 launches.  inp: [1,E,384] tensor or (imap_table [N,384] fp16, idx, mod)."""
