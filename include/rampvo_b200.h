@@ -99,6 +99,21 @@ int rvo_corr_pyramid(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const float
                      int64_t pmod, int64_t fmod, int E, int radius, void* out, int64_t out_ld,
                      void* stream);
 
+/* The same lookup as rvo_corr_pyramid (radius 3, P = 3, C = 128, channels-last fp16) computed as
+ * tile GEMMs on the tcgen05 tensor cores with TMEM accumulators: rows (edge, patch pixel, level) are
+ * binned by the 16x16-position tile of the target frame that holds their 8x8 window, one CTA runs
+ * D[128 rows, 256 positions] = A * B^T per tile with tcgen05.mma and extracts / blends each row's
+ * window in the epilogue.  Output "tile layout":
+ *   out[e*out_ld + ((lvl*9 + pix)*7 + a)*8 + b]   a = y offset, b = x offset in 0..6; b = 7 is a
+ *   zero pad (one aligned 16-byte store per row); out_ld >= 504*nlevels, % 8 == 0.  (The reference layout of
+ *   ramp/Ramp_vo.py:182 is index ((b*7 + a)*9 + pix)*nlevels + lvl.)
+ * ws: rvo_corr_tiles_ws_bytes(pyr, nlevels, E) bytes of device scratch. */
+int64_t rvo_corr_tiles_ws_bytes(const rvo_fmap_t* pyr, int nlevels, int E);
+int rvo_corr_tiles(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const float* scale, int nlevels,
+                   const float* coords, const int64_t* kk, const int64_t* jj, int64_t pmod,
+                   int64_t fmod, int E, void* out, int64_t out_ld, void* ws, int64_t ws_bytes,
+                   void* stream);
+
 /* Host-buffer variant of rvo_corr_pyramid: every pointer (also inside the rvo_fmap_t views) is
  * HOST memory; copies in, launches, copies the [E,882] result back, synchronises. */
 int rvo_corr_pyramid_host(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const float* scale,

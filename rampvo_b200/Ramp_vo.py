@@ -119,7 +119,7 @@ class _UpdateGraph:
         self.net_in = vo.net                     # view of the current ping-pong buffer
         self.net_out = vo._net_other(E)
         self._load(vo.n - n_free)
-        vo.corr(vo.reproject())                  # sizes the persistent corr buffer outside the capture
+        vo.corr_tiles(vo.reproject())            # sizes the persistent corr buffer outside the capture
         snap = (vo.poses_.clone(), vo.patches_.clone(), self.net_in.clone())
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
@@ -209,6 +209,7 @@ class Ramp_vo:
         self.use_graphs = use_graphs
         self._pgraph = None         # _PatchifyGraph, captured at the first frame
         self._corr_buf = None       # [1, capacity, 896] correlation rows (882 used)
+        self._corrt_buf = None      # [1, capacity, 1008] correlation rows in the tile layout
         self._ugraphs = {}          # (E, window, buffer parity) -> _UpdateGraph
         self._ukey_prev, self._ukey_hist = None, []
         self.graph_kernel_launches = 0   # librampvo kernels executed through CUDA-graph replays
@@ -292,6 +293,18 @@ class Ramp_vo:
         return altcorr.corr_pyramid(self.gmap, self.pyramid, coords, ii, jj, self.M * self.mem,
                                     self.mem, 3, out=out)
 
+    def corr_tiles(self, coords, indicies=None):
+        """the same correlation volume in the tile layout of altcorr.corr_tiles ([1,E,1008]), computed
+        on the tcgen05 tensor cores; the update operator consumes it with permuted first-layer weights"""
+        ii, jj = indicies if indicies is not None else (self.kk, self.jj)
+        E = ii.numel()
+        buf = self._corrt_buf
+        if buf is None or buf.shape[1] < E:
+            buf = self._corrt_buf = torch.zeros(1, max(E, 1) * 5 // 4 + 256, 18 * altcorr.TILE_GROUP,
+                                                dtype=self.fdtype, device=self.device)
+        return altcorr.corr_tiles(self.gmap, self.pyramid, coords, ii, jj, self.M * self.mem, self.mem,
+                                  out=buf[:, :E])
+
     def reproject(self, indicies=None, poses=None, patches=None, intrinsics=None):
         """reproject patch k from i -> j: coords [1,E,2,P,P] (Ramp_vo.py:184-192)"""
         (ii, jj, kk) = indicies if indicies is not None else (self.ii, self.jj, self.kk)
@@ -360,7 +373,10 @@ class Ramp_vo:
         net = torch.zeros(1, len(ii), self.DIM, device=self.device)
         coords = self.reproject(indicies=(ii, jj, kk))
         with torch.autocast("cuda", enabled=self.autocast):
-            corr = self.corr(coords, indicies=(kk, jj))
+            if self.autocast and self.P == 3:
+                corr = self.corr_tiles(coords, indicies=(kk, jj))     # tcgen05 path, tile layout
+            else:
+                corr = self.corr(coords, indicies=(kk, jj))
             ctx = self.imap[:, kk % (self.M * self.mem)]
             net, (delta, weight, _) = self.network.update(net, ctx, corr, None, ii, jj, kk)
         return torch.quantile(delta.norm(dim=-1).float(), 0.5)
@@ -417,7 +433,10 @@ class Ramp_vo:
         host-side scalar is either constant across frames or read from device memory (t0_dev)"""
         coords = self.reproject(indicies=(ii, jj, kk))
         with torch.autocast("cuda", enabled=self.autocast):
-            corr = self.corr(coords, indicies=(kk, jj))
+            if self.autocast and self.P == 3:
+                corr = self.corr_tiles(coords, indicies=(kk, jj))     # tcgen05 path, tile layout
+            else:
+                corr = self.corr(coords, indicies=(kk, jj))
             ctx = (self.imap_, kk, self.M * self.mem)     # imap[:, kk % (M*mem)], gather fused
             new_net, (delta, weight, _) = self.network.update(net_in, ctx, corr, None, ii, jj, kk,
                                                               plans=plans, net_out=net_out)

@@ -134,3 +134,51 @@ def corr_pyramid(gmap, pyramid, coords, kk, jj, pmod=0, fmod=0, radius=3, scales
                                                _lib.ptr(out), ld, _lib.stream_ptr()),
                    "rvo_corr_pyramid")
     return out
+
+
+TILE_GROUP = 56      # halves per (level, pixel) group of the tile layout: 7 rows of 8 (7 used)
+
+
+def tile_layout_index(nlevels=2, P=3, radius=3):
+    """index map from the tile layout of corr_tiles to the reference layout of Ramp_vo.corr:
+    ref_index[t] for every used tile-layout column t, and the list of those columns."""
+    d = 2 * radius + 1
+    cols, ref = [], []
+    for lvl in range(nlevels):
+        for pix in range(P * P):
+            for a in range(d):
+                for b in range(d):
+                    cols.append((lvl * P * P + pix) * TILE_GROUP + a * 8 + b)
+                    ref.append(((b * d + a) * P * P + pix) * nlevels + lvl)
+    return torch.tensor(cols), torch.tensor(ref)
+
+
+def corr_tiles(gmap, pyramid, coords, kk, jj, pmod=0, fmod=0, scales=None, out=None):
+    """Ramp_vo.corr on the tcgen05 tensor cores (rvo_corr_tiles): same values as corr_pyramid in the
+    TILE layout [1, E, >= 450*levels] (see tile_layout_index); gmap / pyramid must be channels-last
+    fp16 with 128 channels, P = 3, radius 3."""
+    _lib.require_cuda(gmap, coords, kk, jj, *pyramid)
+    nl = len(pyramid)
+    if scales is None:
+        scales = [1.0, 0.25][:nl]
+    E = coords.shape[1]
+    coords = coords.to(torch.float32).contiguous()
+    kk = kk.to(torch.int64).contiguous()
+    jj = jj.to(torch.int64).contiguous()
+    row = 9 * nl * TILE_GROUP
+    if out is None:
+        out = torch.zeros(1, E, (row + 7) // 8 * 8, dtype=torch.float16, device=gmap.device)
+    ld = out.stride(-2) if out.numel() else row
+    v1 = _lib.fmap_view(gmap[0])
+    arr = (_lib.FMap * nl)(*[_lib.fmap_view(p[0]) for p in pyramid])
+    sc = (ctypes.c_float * nl)(*scales)
+    L = _lib.lib()
+    nb = L.rvo_corr_tiles_ws_bytes(arr, nl, E)
+    if nb < 0:
+        raise RuntimeError("altcorr.corr_tiles: %s" % L.rvo_last_error().decode())
+    ws = _lib.Workspace.get(gmap.device, nb, "corr_tiles")
+    with torch.cuda.device(gmap.device):
+        _lib.check(L.rvo_corr_tiles(ctypes.byref(v1), arr, sc, nl, _lib.ptr(coords), _lib.ptr(kk),
+                                    _lib.ptr(jj), pmod, fmod, E, _lib.ptr(out), ld, _lib.ptr(ws),
+                                    ws.numel(), _lib.stream_ptr()), "rvo_corr_tiles")
+    return out

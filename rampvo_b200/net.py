@@ -133,6 +133,11 @@ class Update(nn.Module):
         for name, ln in (("ln_corr", self.corr[3]), ("ln_norm", self.norm), ("ln_g0", self.gru[0]), ("ln_g2", self.gru[2])):
             w[name] = (f(ln.weight), f(ln.bias))
         w["corr0p"] = F.pad(w["corr0"][0], (0, 896 - w["corr0"][0].shape[1])).contiguous()   # K 882 -> 896
+        cols, ref = altcorr.tile_layout_index(2)
+        w0t = torch.zeros(w["corr0"][0].shape[0], 18 * altcorr.TILE_GROUP, dtype=torch.float16,
+                          device=w["corr0"][0].device)
+        w0t[:, cols.to(w0t.device)] = w["corr0"][0][:, ref.to(w0t.device)]
+        w["corr0t"] = w0t                                          # same layer, tile-layout input
         # heads run in fp16 under autocast: keep fp16-rounded values, stored fp32 for the kernel
         w["d"] = (f(h(self.d[1].weight)), f(h(self.d[1].bias)))
         w["w"] = (f(h(self.w[1].weight)), f(h(self.w[1].bias)))
@@ -161,7 +166,11 @@ class Update(nn.Module):
         f32 = lambda: torch.empty(E, DIM, dtype=torch.float32, device=dev)
 
         K0 = corr.shape[-1]
-        if corr.dtype == torch.float16 and corr.stride(-1) == 1 and corr.stride(-2) == 896 and K0 == 882:
+        if K0 == 18 * altcorr.TILE_GROUP and corr.dtype == torch.float16:
+            # tile layout of altcorr.corr_tiles: first-layer weight columns permuted to match
+            c = corr.reshape(E, K0)
+            h = torch._addmm_activation(W["corr0"][1], c, W["corr0t"].t())
+        elif corr.dtype == torch.float16 and corr.stride(-1) == 1 and corr.stride(-2) == 896 and K0 == 882:
             c = torch.as_strided(corr, (E, 896), (896, 1), corr.storage_offset())   # zero-padded rows
             h = torch._addmm_activation(W["corr0"][1], c, W["corr0p"].t())
         else:

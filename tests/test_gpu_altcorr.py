@@ -179,3 +179,53 @@ def test_corr_full_size_properties():
                          prob["kk"][sel], prob["jj"][sel], 96 * 32, 32, 3)
     got = out[0, torch.from_numpy(sel).cuda()].float().cpu().numpy()
     assert (np.abs(got - exp) <= 2.0 ** -10 * np.abs(exp) + 2e-4).all()
+
+
+@pytest.mark.parametrize("spread", [1.0, 2.2])
+def test_corr_tiles_tcgen05_matches_oracle(spread):
+    """The tcgen05 / TMEM tile-GEMM lookup (rvo_corr_tiles) against the float64 oracle, through the
+    tile-layout -> reference-layout index map; windows partly and entirely outside the maps included."""
+    rng = np.random.default_rng(14)
+    Np, Nf, C, H, W, P, E = 60, 5, 128, 30, 40, 3, 700
+    gmap, pyr = synth.make_features(Nf, Np, C, H, W, P, seed=14)
+    kk = rng.integers(0, 3 * Np, E)
+    jj = rng.integers(0, 3 * Nf, E)
+    _, _, coords = _corr_case(rng, E, Np, Nf, C, H, W, P, spread)
+    coords[:5] = 1e9          # far outside
+    coords[5:8] = -50.0
+    coords[8] = np.nan
+    g_t = torch.from_numpy(gmap).cuda().permute(0, 3, 1, 2)[None]
+    p_t = [torch.from_numpy(p).cuda().permute(0, 3, 1, 2)[None] for p in pyr]
+    c_t = torch.from_numpy(coords).cuda()[None]
+    k_t, j_t = torch.from_numpy(kk).cuda(), torch.from_numpy(jj).cuda()
+    out = altcorr.corr_tiles(g_t, p_t, c_t, k_t, j_t, Np, Nf)
+    assert out.shape == (1, E, 1008) and out.dtype == torch.float16
+    cols, ref = altcorr.tile_layout_index(2)
+    got = torch.empty(E, 882, dtype=torch.float16, device="cuda")
+    got[:, ref.cuda()] = out[0][:, cols.cuda()]
+    exp = O.corr_pyramid(gmap.transpose(0, 3, 1, 2), [p.transpose(0, 3, 1, 2) for p in pyr],
+                         np.nan_to_num(coords, nan=-1e9), kk, jj, Np, Nf, 3)
+    g = got.float().cpu().numpy().astype(np.float64)
+    assert np.isfinite(g).all()
+    assert (np.abs(g - exp) <= 2.0 ** -10 * np.abs(exp) + 2e-4).all()
+    # pad columns stay zero, and the per-edge kernel agrees
+    pad = torch.ones(1008, dtype=torch.bool)
+    pad[cols] = False
+    assert (out[0][:, pad.cuda()] == 0).all()
+    v1 = altcorr.corr_pyramid(g_t, p_t, torch.nan_to_num(c_t, nan=-1e9), k_t, j_t, Np, Nf, 3)
+    assert (v1[0].float() - got.float()).abs().max().item() < 2e-3
+
+
+def test_corr_tiles_full_size_agrees_with_per_edge_kernel():
+    prob = synth.make_problem("default", 40, seed=1)
+    gmap, pyr = synth.make_features(32, 96 * 32, seed=1)
+    c = O.reproject(prob["poses"], prob["patches"], prob["intrinsics"], prob["ii"], prob["jj"],
+                    prob["kk"]).astype(np.float32)
+    g_t = torch.from_numpy(gmap).cuda().permute(0, 3, 1, 2)[None]
+    p_t = [torch.from_numpy(p).cuda().permute(0, 3, 1, 2)[None] for p in pyr]
+    c_t = torch.from_numpy(c).cuda()[None]
+    k_t, j_t = torch.from_numpy(prob["kk"]).cuda(), torch.from_numpy(prob["jj"]).cuda()
+    a = altcorr.corr_pyramid(g_t, p_t, c_t, k_t, j_t, 96 * 32, 32, 3)
+    b = altcorr.corr_tiles(g_t, p_t, c_t, k_t, j_t, 96 * 32, 32)
+    cols, ref = altcorr.tile_layout_index(2)
+    assert (a[0][:, ref.cuda()].float() - b[0][:, cols.cuda()].float()).abs().max().item() < 2e-3

@@ -115,3 +115,20 @@ def test_ramp_vo_runs_online_and_keeps_reference_invariants():
             vo.update()
         poses, tstamps = vo.terminate()
         assert poses.shape == (14, 7) and len(tstamps) == 14 and np.isfinite(poses).all()
+
+
+def test_update_operator_accepts_tile_layout_corr():
+    """The tcgen05 corr output (tile layout) through the permuted first-layer weight gives the same
+    update as the reference-layout corr."""
+    from rampvo_b200 import altcorr
+    up = _my_update()
+    g = GI.update_inputs("cuda")
+    E = g["ii"].numel()
+    corr_ref = g["corr"].half()
+    cols, ref = altcorr.tile_layout_index(2)
+    tile = torch.zeros(1, E, 1008, dtype=torch.float16, device="cuda")
+    tile[0][:, cols.cuda()] = corr_ref[0][:, ref.cuda()]
+    with torch.no_grad(), torch.autocast("cuda", enabled=True):
+        n1, (d1, w1, _) = up(g["net"], g["inp"], corr_ref, None, g["ii"], g["jj"], g["kk"])
+        n2, (d2, w2, _) = up(g["net"], g["inp"], tile, None, g["ii"], g["jj"], g["kk"])
+    assert (n1 - n2).abs().max().item() < 2e-2 and (w1 - w2).abs().max().item() < 5e-3

@@ -63,6 +63,13 @@ def main():
     res["corr_us_min"] = mn
     res["corr_alg_MB"] = byt / 1e6
     res["corr_GBs"] = byt / med / 1e3
+    out_t = torch.zeros(1, E, 1008, dtype=torch.float16, device=dev)
+    try:
+        med, mn = timeit(lambda: altcorr.corr_tiles(g_t, p_t, coords, t["kk"], t["jj"], M * 32, 32, out=out_t), flush=flush)
+        res["corr_tiles_us"] = med
+        res["corr_tiles_GBs"] = byt / med / 1e3
+    except Exception as ex:  # noqa: BLE001
+        res["corr_tiles_error"] = str(ex)[:200]
     med, mn = timeit(lambda: fastba.neighbors(t["kk"], t["jj"], kmax=patches.shape[1], jmax=poses.shape[1]), flush=flush)
     res["neighbors_us"] = med
     tgt = (coords[0, :, :, 1, 1] + torch.from_numpy(prob["noise"]).to(dev))[None].contiguous()
