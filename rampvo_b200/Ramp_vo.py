@@ -53,6 +53,7 @@ class _PatchifyGraph:
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
         saved = list(enc.super_states)
+        torch.backends.cudnn.benchmark = True    # fixed shapes: let cuDNN pick its fastest conv kernels
         with torch.cuda.stream(s):
             for _ in range(3):
                 enc.super_states = [None, None, None]
@@ -206,6 +207,7 @@ class Ramp_vo:
         self.jj = torch.as_tensor([], dtype=torch.long, device=dev)
         self.kk = torch.as_tensor([], dtype=torch.long, device=dev)
         self._plans = None          # GraphPlans of the current edge list
+        self._pair_cnt = None       # host-side {(source frame, target frame): number of edges}
         self.use_graphs = use_graphs
         self._pgraph = None         # _PatchifyGraph, captured at the first frame
         self._corr_buf = None       # [1, capacity, 896] correlation rows (882 used)
@@ -334,11 +336,31 @@ class Ramp_vo:
         self._net_cur = 1 - self._net_cur
         self.net = self._net_bufs[self._net_cur][:, :E]
 
-    def append_factors(self, ii, jj):
-        """add factors to the graph (Ramp_vo.py:194-201); new edges start with a zero hidden state"""
+    # The edge lists live on the device (self.ii / jj / kk, public like the reference's).  The host
+    # keeps only the number of edges per (source frame, target frame) pair — enough to know how many
+    # edges a removal keeps, so that the compaction can use torch.nonzero_static instead of a boolean
+    # index that waits for the device.
+    def _pair_counts(self):
+        pc = self._pair_cnt
+        if pc is None or sum(pc.values()) != self.ii.numel():      # edited from outside: recount once
+            key = (self.ii * (self.N + 1) + self.jj).cpu().numpy()
+            u, c = np.unique(key, return_counts=True)
+            pc = self._pair_cnt = {(int(k) // (self.N + 1), int(k) % (self.N + 1)): int(v) for k, v in zip(u, c)}
+        return pc
+
+    def append_factors(self, ii, jj, pairs=None):
+        """add factors to the graph (Ramp_vo.py:194-201); new edges start with a zero hidden state.
+        pairs: {(i, j): count} of the new edges when the caller knows it (no device read needed)"""
+        pc = self._pair_counts()
+        if pairs is None:
+            key = (torch.div(ii, self.M, rounding_mode="floor") * (self.N + 1) + jj).cpu().numpy()
+            u, c = np.unique(key, return_counts=True)
+            pairs = {(int(k) // (self.N + 1), int(k) % (self.N + 1)): int(v) for k, v in zip(u, c)}
+        for k, v in pairs.items():
+            pc[k] = pc.get(k, 0) + v
         self.jj = torch.cat([self.jj, jj])
         self.kk = torch.cat([self.kk, ii])
-        self.ii = torch.cat([self.ii, self.ix[ii]])
+        self.ii = torch.cat([self.ii, torch.div(ii, self.M, rounding_mode="floor")])
         E0, n = self.net.shape[1], len(ii)
         self._net_reserve(E0 + n)
         buf = self._net_bufs[self._net_cur]
@@ -346,11 +368,22 @@ class Ramp_vo:
         self.net = buf[:, :E0 + n]
         self._plans = None
 
-    def remove_factors(self, m):
-        """remove factors from the graph (Ramp_vo.py:203-208)"""
-        keep = (~m).nonzero().view(-1)
-        if keep.numel() == m.numel():
+    def remove_factors(self, m, pair_pred=None):
+        """remove factors from the graph (Ramp_vo.py:203-208).  m: boolean device mask (reference
+        signature).  pair_pred(i, j) -> bool: the same predicate on (source, target) frame pairs; with
+        it the number of surviving edges is known on the host and the compaction does not synchronise"""
+        pc = self._pair_counts()
+        if pair_pred is None:
+            n_keep = int((~m).sum().item())
+            self._pair_cnt = None                                   # recount lazily
+        else:
+            gone = [k for k in pc if pair_pred(*k)]
+            for k in gone:
+                del pc[k]
+            n_keep = sum(pc.values())
+        if n_keep == m.numel():
             return
+        keep = torch.nonzero_static(~m, size=n_keep).view(-1)
         self.ii = self.ii[keep]
         self.jj = self.jj[keep]
         self.kk = self.kk[keep]
@@ -408,10 +441,13 @@ class Ramp_vo:
             t1 = self.tstamps_[k].item()
             dP = SE3(self.poses_[k]) * SE3(self.poses_[k - 1]).inv()
             self.delta[t1] = (t0, dP)
-            self.remove_factors((self.ii == k) | (self.jj == k))
-            self.kk[self.ii > k] -= self.M
-            self.ii[self.ii > k] -= 1
-            self.jj[self.jj > k] -= 1
+            self.remove_factors((self.ii == k) | (self.jj == k), lambda i, j: i == k or j == k)
+            # renumber without boolean indexing (no size-dependent sync): subtract masks
+            gi = self.ii > k
+            self.kk -= gi * self.M
+            self.ii -= gi.to(self.ii.dtype)
+            self.jj -= (self.jj > k).to(self.jj.dtype)
+            self._pair_cnt = {(i - (i > k), j - (j > k)): v for (i, j), v in self._pair_counts().items()}
             # shift every per-frame buffer one slot down (the reference loops frame by frame)
             n = self.n
             for buf in (self.tstamps_, self.colors_, self.poses_, self.patches_, self.intrinsics_):
@@ -426,7 +462,8 @@ class Ramp_vo:
                 self._fmap2_store[dst] = self._fmap2_store[src]
             self.n -= 1
             self.m -= self.M
-        self.remove_factors(self.ix[self.kk] < self.n - self.cfg.REMOVAL_WINDOW)
+        lim = self.n - self.cfg.REMOVAL_WINDOW
+        self.remove_factors(self.ii < lim, lambda i, j: i < lim)     # ix[kk] == ii (index_[f] == f)
 
     def _update_body(self, ii, jj, kk, net_in, net_out, plans, t0, t1, t0_dev=None):
         """reproject -> corr -> update operator -> 2 BA iterations on explicit buffers; every
@@ -499,18 +536,22 @@ class Ramp_vo:
         self.last_weight = g.weight
 
     def _edges_forw(self):
+        """patches of frames [n-r, n-1) -> frame n-1 (Ramp_vo.py:312-318): (kk, jj, pair counts)"""
         r = self.cfg.PATCH_LIFETIME
-        t0 = self.M * max((self.n - r), 0)
-        t1 = self.M * max((self.n - 1), 0)
-        return flatmeshgrid(torch.arange(t0, t1, device=self.device),
-                            torch.arange(self.n - 1, self.n, device=self.device), indexing='ij')
+        f0, f1 = max(self.n - r, 0), max(self.n - 1, 0)
+        kk = torch.arange(self.M * f0, self.M * f1, device=self.device)
+        return kk, torch.full_like(kk, self.n - 1), {(i, self.n - 1): self.M for i in range(f0, f1)}
 
     def _edges_back(self):
+        """patches of frame n-1 -> frames [n-r, n) (Ramp_vo.py:320-325), 'ij' meshgrid order"""
         r = self.cfg.PATCH_LIFETIME
         t0 = self.M * max((self.n - 1), 0)
         t1 = self.M * max((self.n - 0), 0)
-        return flatmeshgrid(torch.arange(t0, t1, device=self.device),
-                            torch.arange(max(self.n - r, 0), self.n, device=self.device), indexing='ij')
+        j0 = max(self.n - r, 0)
+        k = torch.arange(t0, t1, device=self.device)
+        j = torch.arange(j0, self.n, device=self.device)
+        pairs = {(self.n - 1, jf): t1 - t0 for jf in range(j0, self.n)} if t1 > t0 else {}
+        return k.repeat_interleave(self.n - j0), j.repeat(t1 - t0), pairs
 
     @torch.no_grad()
     def __call__(self, tstamp, input_tensor, intrinsics):

@@ -8,6 +8,8 @@
 //   in_apply   out = relu( [IN](res) + relu( [IN](t) ) )  — normalisation of the conv output, ReLU,
 //              the (optionally normalised) shortcut and the final ReLU in ONE pass, 16-byte vectors.
 // Bound: HBM/L2 (2 reads + 1 write of the activation per ResidualBlock half instead of ~8).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rvo {
@@ -293,6 +295,14 @@ stem_kernel(StemParams sp, const float* __restrict__ params, const float* __rest
 
 }  // namespace rvo
 
+namespace rvo {
+template <int HID>
+__global__ void stem_mma_kernel(StemParams sp, const float* __restrict__ params, const float* __restrict__ events,
+                                const float* __restrict__ image, const __half* __restrict__ ss_prev,
+                                int use_image, __half* __restrict__ ss_out);
+static size_t stem_mma_smem(const StemParams& sp, int h);
+}  // namespace rvo
+
 extern "C" int rvo_stem_forward(const float* params, int Ce, int Ci, int k, int stride, int pad, int h,
                                 const float* events, const float* image, int H, int W,
                                 const void* ss_prev16, int use_image, void* ss_out16, void* stream) {
@@ -315,9 +325,27 @@ extern "C" int rvo_stem_forward(const float* params, int Ce, int Ci, int k, int 
   o = (o + 3) & ~3;
   sp.o_wsi = o; o += 2 * h * h;        sp.o_bsi = o; o += h;
   sp.n_params = (o + 3) & ~3;
-  const size_t smem = ((size_t)sp.n_params + 8 * kStemPix + 2 * (size_t)kStemPix * (2 * h + 1)) * sizeof(float);
   const int grid = (sp.Ho * sp.Wo + kStemPix - 1) / kStemPix;
   cudaStream_t st = (cudaStream_t)stream;
+  static const int variant = getenv("RVO_STEM_VARIANT") ? atoi(getenv("RVO_STEM_VARIANT")) : 1;
+  if (variant == 1 && Ce <= 16 && Ci <= 16) {   // tensor-core variant
+    const size_t sm2 = stem_mma_smem(sp, h);
+#define RVO_STEM2(HID)                                                                             \
+  do {                                                                                             \
+    RVO_CUDA(cudaFuncSetAttribute(stem_mma_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)sm2));                                                      \
+    stem_mma_kernel<HID><<<grid, kStemThreads, sm2, st>>>(sp, params, events, image,               \
+                                                          (const __half*)ss_prev16, use_image,     \
+                                                          (__half*)ss_out16);                      \
+  } while (0)
+    if (h == 16) RVO_STEM2(16);
+    else if (h == 32) RVO_STEM2(32);
+    else RVO_STEM2(64);
+#undef RVO_STEM2
+    RVO_LAUNCH_CHECK("stem_mma_kernel");
+    return RVO_OK;
+  }
+  const size_t smem = ((size_t)sp.n_params + 8 * kStemPix + 2 * (size_t)kStemPix * (2 * h + 1)) * sizeof(float);
 #define RVO_STEM(HID)                                                                              \
   do {                                                                                             \
     RVO_CUDA(cudaFuncSetAttribute(stem_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
@@ -349,3 +377,183 @@ extern "C" int rvo_stem_params_layout(int Ce, int Ci, int k, int h, int* offsets
   *total = (o + 3) & ~3;
   return RVO_OK;
 }
+
+// ------------------------------------------------------------------ recurrent stem, tensor-core variant ----
+//
+// Same computation as stem_kernel, with the three dense pieces on mma.sync (fp16 operands, fp32
+// accumulate — the operand precision the reference has under autocast): the LSTM gate projection
+// [64 px x 16] x [16 x 3h] and the two super-state GEMMs [64 px x 2h] x [2h x h].  conv_1 (<= 625 MACs
+// per pixel on 3-5 channels) stays on the CUDA cores.  All operands live in shared memory with padded
+// rows (stride = width + 8 halves) so that every fragment load is conflict-free.
+namespace rvo {
+
+__device__ __forceinline__ void mma16816_f16(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                             uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t lds_u32(const __half* p) { return *reinterpret_cast<const uint32_t*>(p); }
+
+template <int HID>
+__global__ void __launch_bounds__(kStemThreads)
+stem_mma_kernel(StemParams sp, const float* __restrict__ params, const float* __restrict__ events,
+                const float* __restrict__ image, const __half* __restrict__ ss_prev, int use_image,
+                __half* __restrict__ ss_out) {
+  constexpr int LDA = 2 * HID + 8;      // halves per row of the state-GEMM operands
+  constexpr int LDX = 24;               // halves per row of the gate-GEMM operands (K = 16)
+  extern __shared__ __align__(16) uint8_t smraw[];
+  float* Pc = reinterpret_cast<float*>(smraw);                 // conv_1 weights / biases (fp32), gate+state biases
+  // fp32 region: [o_wce .. o_wge) conv params, then biases bge[3h], bgi[3h], bse[h], bsi[h]
+  const int n_conv = sp.o_wge;                                  // floats
+  float* bge = Pc + n_conv;
+  float* bgi = bge + 3 * HID;
+  float* bse = bgi + 3 * HID;
+  float* bsi = bse + HID;
+  __half* Wge = reinterpret_cast<__half*>(smraw + (((size_t)(n_conv + 8 * HID) * 4 + 15) / 16 * 16));   // [3h][LDX]
+  __half* Wgi = Wge + 3 * HID * LDX;                            // [3h][LDX]
+  __half* Wse = Wgi + 3 * HID * LDX;                            // [h][LDA]
+  __half* Wsi = Wse + HID * LDA;                                // [h][LDA]
+  __half* Xe = Wsi + HID * LDA;                                 // [64][LDX]
+  __half* Xi = Xe + kStemPix * LDX;                             // [64][LDX]
+  __half* inA = Xi + kStemPix * LDX;                            // [64][LDA] = [ss_prev | h_ev]
+  __half* inB = inA + kStemPix * LDA;                           // [64][LDA] = [ss_1    | h_im]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int npix = sp.Ho * sp.Wo;
+  const int p0 = blockIdx.x * kStemPix;
+  const __half hz = __float2half_rn(0.f);
+
+  // ---- stage parameters
+  for (int i = tid; i < n_conv; i += kStemThreads) Pc[i] = params[i];
+  for (int i = tid; i < 3 * HID; i += kStemThreads) { bge[i] = params[sp.o_bge + i]; bgi[i] = params[sp.o_bgi + i]; }
+  for (int i = tid; i < HID; i += kStemThreads) { bse[i] = params[sp.o_bse + i]; bsi[i] = params[sp.o_bsi + i]; }
+  for (int i = tid; i < 3 * HID * 16; i += kStemThreads) {
+    const int n = i >> 4, k = i & 15;
+    Wge[n * LDX + k] = k < sp.Ce ? __float2half_rn(params[sp.o_wge + n * sp.Ce + k]) : hz;
+    Wgi[n * LDX + k] = k < sp.Ci ? __float2half_rn(params[sp.o_wgi + n * sp.Ci + k]) : hz;
+  }
+  for (int i = tid; i < 2 * HID * HID; i += kStemThreads) {   // packed transposed [2h][h] -> [h][2h]
+    const int k = i / HID, n = i - k * HID;
+    Wse[n * LDA + k] = __float2half_rn(params[sp.o_wse + i]);
+    Wsi[n * LDA + k] = __float2half_rn(params[sp.o_wsi + i]);
+  }
+  for (int i = tid; i < kStemPix * 16; i += kStemThreads) {    // zero the K padding of the gate operands
+    Xe[(i >> 4) * LDX + (i & 15)] = hz;
+    Xi[(i >> 4) * LDX + (i & 15)] = hz;
+  }
+  __syncthreads();
+
+  // ---- phase 1: conv_1 of both modalities -> Xe / Xi (fp16)
+  for (int item = tid; item < kStemPix * 8; item += kStemThreads) {
+    const int px = item & 63, ch = item >> 6;
+    const int p = p0 + px;
+    const bool ev = ch < 5;
+    const int Cin = ev ? sp.Ce : sp.Ci, co = ev ? ch : ch - 5;
+    if (p >= npix || co >= Cin) continue;
+    const int oy = p / sp.Wo, ox = p - oy * sp.Wo;
+    const float* src = ev ? events : image;
+    const float* Wc = Pc + (ev ? sp.o_wce : sp.o_wci) + co * Cin * sp.k * sp.k;
+    float acc = Pc[(ev ? sp.o_bce : sp.o_bci) + co];
+    for (int ci = 0; ci < Cin; ci++)
+      for (int ky = 0; ky < sp.k; ky++) {
+        const int iy = oy * sp.stride - sp.pad + ky;
+        const bool oky = (unsigned)iy < (unsigned)sp.H;
+        const float* row = src + ((size_t)ci * sp.H + (oky ? iy : 0)) * sp.W;
+#pragma unroll 5
+        for (int kx = 0; kx < sp.k; kx++) {
+          const int ix = ox * sp.stride - sp.pad + kx;
+          const bool ok = oky && (unsigned)ix < (unsigned)sp.W;
+          acc += (ok ? Wc[(ci * sp.k + ky) * sp.k + kx] : 0.f) * row[ok ? ix : 0];
+        }
+      }
+    (ev ? Xe : Xi)[px * LDX + co] = __float2half_rn(acc);
+  }
+  // previous super state -> inA[:, 0:h)
+  for (int i = tid; i < kStemPix * HID / 2; i += kStemThreads) {
+    const int px = i / (HID / 2), c2 = i - px * (HID / 2);
+    const int p = p0 + px;
+    uint32_t v = 0u;
+    if (ss_prev && p < npix) v = reinterpret_cast<const uint32_t*>(ss_prev + (size_t)p * HID)[c2];
+    *reinterpret_cast<uint32_t*>(inA + px * LDA + 2 * c2) = v;
+  }
+  __syncthreads();
+
+  const int mt = warp & 3, half_id = warp >> 2;      // m-tile of this warp, which half of the n-tiles
+  const int r0 = 16 * mt + g, r1 = r0 + 8;
+
+  // ---- phase 2: gates (one k-step) + LSTM cell, one step from a zero state
+#pragma unroll 1
+  for (int mod = 0; mod < 2; mod++) {
+    const __half* X = mod ? Xi : Xe;
+    const __half* Wg = mod ? Wgi : Wge;
+    const float* bg = mod ? bgi : bge;
+    __half* dst = mod ? inB : inA;
+    const uint32_t a0 = lds_u32(X + r0 * LDX + 2 * t), a1 = lds_u32(X + r1 * LDX + 2 * t);
+    const uint32_t a2 = lds_u32(X + r0 * LDX + 2 * t + 8), a3 = lds_u32(X + r1 * LDX + 2 * t + 8);
+    for (int jt = half_id; jt < HID / 8; jt += 2) {
+      float acc[3][4];
+#pragma unroll
+      for (int gate = 0; gate < 3; gate++) {
+        const int n = gate * HID + 8 * jt;
+        const float bl = bg[n + 2 * t], bh = bg[n + 2 * t + 1];
+        acc[gate][0] = bl; acc[gate][1] = bh; acc[gate][2] = bl; acc[gate][3] = bh;
+        const __half* wrow = Wg + (n + g) * LDX + 2 * t;
+        mma16816_f16(acc[gate], a0, a1, a2, a3, lds_u32(wrow), lds_u32(wrow + 8));
+      }
+      float hv[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) hv[q] = sigmoidf_(acc[2][q]) * tanhf_(sigmoidf_(acc[0][q]) * tanhf_(acc[1][q]));
+      const int col = HID + 8 * jt + 2 * t;
+      *reinterpret_cast<__half2*>(dst + r0 * LDA + col) = __floats2half2_rn(hv[0], hv[1]);
+      *reinterpret_cast<__half2*>(dst + r1 * LDA + col) = __floats2half2_rn(hv[2], hv[3]);
+    }
+  }
+  __syncthreads();
+
+  // ---- phases 3 / 4: ss <- W [ss ; h] + b
+#pragma unroll 1
+  for (int stage = 0; stage < 2; stage++) {
+    if (stage == 1 && !use_image) break;
+    const __half* A = stage ? inB : inA;
+    const __half* Wm = stage ? Wsi : Wse;
+    const float* bs = stage ? bsi : bse;
+    const bool last = (stage == 1) || !use_image;
+    for (int nt = half_id; nt < HID / 8; nt += 2) {
+      float acc[4];
+      const float bl = bs[8 * nt + 2 * t], bh = bs[8 * nt + 2 * t + 1];
+      acc[0] = bl; acc[1] = bh; acc[2] = bl; acc[3] = bh;
+      const __half* wrow = Wm + (8 * nt + g) * LDA + 2 * t;
+#pragma unroll
+      for (int ks = 0; ks < 2 * HID / 16; ks++) {
+        const __half* ar0 = A + r0 * LDA + 16 * ks + 2 * t;
+        const __half* ar1 = A + r1 * LDA + 16 * ks + 2 * t;
+        mma16816_f16(acc, lds_u32(ar0), lds_u32(ar1), lds_u32(ar0 + 8), lds_u32(ar1 + 8),
+                     lds_u32(wrow + 16 * ks), lds_u32(wrow + 16 * ks + 8));
+      }
+      const __half2 lo = __floats2half2_rn(acc[0], acc[1]), hi = __floats2half2_rn(acc[2], acc[3]);
+      const int col = 8 * nt + 2 * t;
+      if (last) {
+        if (p0 + r0 < npix) *reinterpret_cast<__half2*>(ss_out + (size_t)(p0 + r0) * HID + col) = lo;
+        if (p0 + r1 < npix) *reinterpret_cast<__half2*>(ss_out + (size_t)(p0 + r1) * HID + col) = hi;
+      } else {
+        *reinterpret_cast<__half2*>(inB + r0 * LDA + col) = lo;
+        *reinterpret_cast<__half2*>(inB + r1 * LDA + col) = hi;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static size_t stem_mma_smem(const StemParams& sp, int h) {
+  const size_t f32 = (size_t)sp.o_wge + 3 * h * 2 + 2 * h;
+  const size_t f16 = (size_t)2 * 3 * h * 24 + 2 * (size_t)h * (2 * h + 8) + 2 * kStemPix * 24 +
+                     2 * (size_t)kStemPix * (2 * h + 8);
+  return ((f32 * 4 + 15) / 16 * 16) + f16 * 2 + 16;
+}
+
+}  // namespace rvo

@@ -26,12 +26,13 @@ def _fast(x):
     return x.is_cuda and torch.is_autocast_enabled() and not torch.is_grad_enabled()
 
 
-def _conv16(conv, x):
-    """cuDNN convolution on fp16 channels-last operands with cached fp16 weights."""
+def _conv16(conv, x, scale=1.0):
+    """cuDNN convolution on fp16 channels-last operands with cached fp16 weights.  `scale` (a power
+    of two) is folded into the cached weights and bias — exact in fp16 up to subnormals."""
     w = getattr(conv, "_w16", None)
-    if w is None:
-        w = conv._w16 = (conv.weight.detach().half().contiguous(memory_format=CL),
-                         conv.bias.detach().half())
+    if w is None or w[2] != scale:
+        w = conv._w16 = ((conv.weight.detach() * scale).half().contiguous(memory_format=CL),
+                         (conv.bias.detach() * scale).half(), scale)
     with torch.autocast("cuda", enabled=False):
         y = F.conv2d(x, w[0], w[1], stride=conv.stride, padding=conv.padding)
     return y if y.is_contiguous(memory_format=CL) else y.contiguous(memory_format=CL)
@@ -116,22 +117,24 @@ class MultiScaleBasicEncoder4(nn.Module):
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
 
-    def forward(self, x, x_down2, x_down4):
-        """x [1,16,H,W], x_down2 [1,32,H/2,W/2], x_down4 [1,64,H/4,W/4] -> [1,out,H/4,W/4]."""
+    def forward(self, x, x_down2, x_down4, out_scale=1.0):
+        """x [1,16,H,W], x_down2 [1,32,H/2,W/2], x_down4 [1,64,H/4,W/4] -> [1,out,H/4,W/4] (times
+        out_scale: the /4 of net.py:152-153 folded into the last 1x1 conv on the fast path)."""
         if _fast(x) and x.shape[0] == 1:
             h16 = lambda t: t.half().contiguous(memory_format=CL)
             t = _conv16(self.conv1, h16(x))
             x = _apply(t, _stats(t) if self.instance else None)
             x = self.layer1(x)
             x = self.layer3(torch.cat((x, h16(x_down2)), dim=1).contiguous(memory_format=CL))
-            return _conv16(self.conv3, torch.cat((x, h16(x_down4)), dim=1).contiguous(memory_format=CL))
+            return _conv16(self.conv3, torch.cat((x, h16(x_down4)), dim=1).contiguous(memory_format=CL),
+                           out_scale)
         x = self.conv1(x)
         if self.instance:
             x = F.instance_norm(x)
         x = F.relu(x)
         x = self.layer1(x)
         x = self.layer3(torch.cat((x, x_down2), dim=1))
-        return self.conv3(torch.cat((x, x_down4), dim=1))
+        return self.conv3(torch.cat((x, x_down4), dim=1)) * out_scale
 
 
 class LSTMEncoder(nn.Module):
@@ -230,7 +233,7 @@ class MultiScaleMergerDoubleNet(nn.Module):
         cache[k] = (buf.to(device), (Ce, Ci, ks, st, pd, h))
         return cache[k]
 
-    def _forward_fast(self, events, images, use_image, reinit_hidden):
+    def _forward_fast(self, events, images, use_image, reinit_hidden, out_scale=1.0):
         """One event stack + (optionally) one image: the fused stem kernel per scale, then the two
         channels-last CNNs."""
         ev = events[0, 0].float().contiguous()
@@ -253,18 +256,18 @@ class MultiScaleMergerDoubleNet(nn.Module):
                        "rvo_stem_forward")
             self.super_states[k] = out
             per_scale.append(out)
-        fmap = self.fmap_encoder(per_scale[0], per_scale[1], per_scale[2])
-        imap = self.imap_encoder(per_scale[0], per_scale[1], per_scale[2])
+        fmap = self.fmap_encoder(per_scale[0], per_scale[1], per_scale[2], out_scale)
+        imap = self.imap_encoder(per_scale[0], per_scale[1], per_scale[2], out_scale)
         return fmap[None], imap[None]
 
-    def forward(self, events, images, mask, reinit_hidden=False):
+    def forward(self, events, images, mask, reinit_hidden=False, out_scale=1.0):
         """events [1,T,Ce,H,W], images [1,Ti,3,H,W], mask [T] bool (one image per True entry)
         -> fmap [1,n,128,H/4,W/4], imap [1,n,384,H/4,W/4] with n = number of images consumed
         (n = 1 with the states of the last event voxel when no image arrived, extractor.py:455)."""
         mask = torch.as_tensor(mask).reshape(-1).tolist()
         if (_fast(events) and events.shape[1] == 1 and len(mask) == 1 and not self.norm_superstate
                 and images.shape[1] >= 1):
-            return self._forward_fast(events, images, bool(mask[0]), reinit_hidden)
+            return self._forward_fast(events, images, bool(mask[0]), reinit_hidden, out_scale)
         ev = events[0].contiguous(memory_format=torch.channels_last)
         im = images[0].contiguous(memory_format=torch.channels_last)
         per_scale = []
@@ -288,6 +291,6 @@ class MultiScaleMergerDoubleNet(nn.Module):
             # (extractor.py:440-441,560): with one image per call that is the last state
             self.super_states[k] = allss[-1:] if allss.shape[0] > 1 else allss
             per_scale.append(allss)
-        fmap = self.fmap_encoder(per_scale[0], per_scale[1], per_scale[2])
-        imap = self.imap_encoder(per_scale[0], per_scale[1], per_scale[2])
+        fmap = self.fmap_encoder(per_scale[0], per_scale[1], per_scale[2], out_scale)
+        imap = self.imap_encoder(per_scale[0], per_scale[1], per_scale[2], out_scale)
         return fmap[None], imap[None]

@@ -278,14 +278,14 @@ class Patchifier(nn.Module):
     def forward(self, input_, patches_per_image=80, reinit_hidden=False, disps=None, event_bias=False,
                 gradient_bias=False, gmap_out=None):
         events, images, mask = input_
-        fmap, imap = self.encoder(events=events, images=images, mask=mask, reinit_hidden=reinit_hidden)
+        # fmap / 4, imap / 4 (net.py:152-153) are folded into the encoders' last 1x1 convolutions
+        fmap, imap = self.encoder(events=events, images=images, mask=mask, reinit_hidden=reinit_hidden,
+                                  out_scale=0.25)
         mask_l = torch.as_tensor(mask).reshape(-1).tolist()       # host-side, like evaluate.py:163
         if not any(mask_l):
             return None, None, None, None, None, None
         if events.shape[1] == len(mask_l) and not all(mask_l):
             events = events[:, [t for t, keep in enumerate(mask_l) if keep]]
-        fmap = fmap / 4.0
-        imap = imap / 4.0
         b, n, c, h, w = fmap.shape
         dev = fmap.device
         if event_bias:

@@ -1,0 +1,54 @@
+"""Host-side wall time per section of Ramp_vo.__call__ at steady state (no device syncs added except
+at the frame end).  Usage: python tools/host_profile.py"""
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from rampvo_b200 import synth  # noqa: E402
+from rampvo_b200.Ramp_vo import Ramp_vo  # noqa: E402
+
+T = {}
+
+
+def wrap(cls, name):
+    f = getattr(cls, name)
+
+    def g(self, *a, **k):
+        t = time.perf_counter()
+        r = f(self, *a, **k)
+        T[name] = T.get(name, 0.0) + time.perf_counter() - t
+        return r
+    setattr(cls, name, g)
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    seq = synth.SyntheticSequence(seed=0, device=dev)
+    n = 30
+    frames = [seq.frame(t) for t in range(bench.SETUP_FRAMES + n + 3)]
+    vo = bench.build_vo(dev)
+    for t in range(bench.SETUP_FRAMES + 3):
+        vo(t, frames[t], seq.intrinsics)
+    for name in ("update", "keyframe", "append_factors", "remove_factors", "_update_graphed", "_edges_forw", "_edges_back"):
+        wrap(Ramp_vo, name)
+    from rampvo_b200 import Ramp_vo as mod
+    wrap(mod._PatchifyGraph, "run")
+    wrap(mod._UpdateGraph, "run")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for t in range(bench.SETUP_FRAMES + 3, bench.SETUP_FRAMES + 3 + n):
+        vo(t, frames[t], seq.intrinsics)
+    torch.cuda.synchronize()
+    tot = time.perf_counter() - t0
+    print("frame wall %.3f ms" % (tot / n * 1e3))
+    for k, v in sorted(T.items(), key=lambda x: -x[1]):
+        print("  %-18s %.3f ms/frame" % (k, v / n * 1e3))
+
+
+if __name__ == "__main__":
+    main()
