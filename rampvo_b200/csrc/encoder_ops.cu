@@ -296,7 +296,7 @@ stem_kernel(StemParams sp, const float* __restrict__ params, const float* __rest
 }  // namespace rvo
 
 namespace rvo {
-template <int HID>
+template <int HID, int K>
 __global__ void stem_mma_kernel(StemParams sp, const float* __restrict__ params, const float* __restrict__ events,
                                 const float* __restrict__ image, const __half* __restrict__ ss_prev,
                                 int use_image, __half* __restrict__ ss_out);
@@ -328,19 +328,28 @@ extern "C" int rvo_stem_forward(const float* params, int Ce, int Ci, int k, int 
   const int grid = (sp.Ho * sp.Wo + kStemPix - 1) / kStemPix;
   cudaStream_t st = (cudaStream_t)stream;
   static const int variant = getenv("RVO_STEM_VARIANT") ? atoi(getenv("RVO_STEM_VARIANT")) : 1;
-  if (variant == 1 && Ce <= 16 && Ci <= 16) {   // tensor-core variant
+  const bool std_geom = (k == 1 && stride == 1 && pad == 0) || ((k == 3 || k == 5) && stride == k - 1 && pad == 1);
+  if (variant == 1 && Ce <= 5 && Ci <= 3 && std_geom) {   // tensor-core variant
     const size_t sm2 = stem_mma_smem(sp, h);
-#define RVO_STEM2(HID)                                                                             \
+    int per_sm = (int)((220 * 1024) / (sm2 + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+    const int grid2 = grid < kNumSMs * per_sm ? grid : kNumSMs * per_sm;
+#define RVO_STEM2(HID, KK)                                                                         \
   do {                                                                                             \
-    RVO_CUDA(cudaFuncSetAttribute(stem_mma_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    RVO_CUDA(cudaFuncSetAttribute(stem_mma_kernel<HID, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)sm2));                                                      \
-    stem_mma_kernel<HID><<<grid, kStemThreads, sm2, st>>>(sp, params, events, image,               \
-                                                          (const __half*)ss_prev16, use_image,     \
-                                                          (__half*)ss_out16);                      \
+    stem_mma_kernel<HID, KK><<<grid2, kStemThreads, sm2, st>>>(sp, params, events, image,          \
+                                                               (const __half*)ss_prev16, use_image, \
+                                                               (__half*)ss_out16);                 \
   } while (0)
-    if (h == 16) RVO_STEM2(16);
-    else if (h == 32) RVO_STEM2(32);
-    else RVO_STEM2(64);
+#define RVO_STEM2K(HID)                                                                            \
+  do {                                                                                             \
+    if (k == 1) RVO_STEM2(HID, 1); else if (k == 3) RVO_STEM2(HID, 3); else RVO_STEM2(HID, 5);     \
+  } while (0)
+    if (h == 16) RVO_STEM2K(16);
+    else if (h == 32) RVO_STEM2K(32);
+    else RVO_STEM2K(64);
+#undef RVO_STEM2K
 #undef RVO_STEM2
     RVO_LAUNCH_CHECK("stem_mma_kernel");
     return RVO_OK;
@@ -398,7 +407,7 @@ __device__ __forceinline__ void mma16816_f16(float* c, uint32_t a0, uint32_t a1,
 
 __device__ __forceinline__ uint32_t lds_u32(const __half* p) { return *reinterpret_cast<const uint32_t*>(p); }
 
-template <int HID>
+template <int HID, int K>
 __global__ void __launch_bounds__(kStemThreads)
 stem_mma_kernel(StemParams sp, const float* __restrict__ params, const float* __restrict__ events,
                 const float* __restrict__ image, const __half* __restrict__ ss_prev, int use_image,
@@ -425,10 +434,10 @@ stem_mma_kernel(StemParams sp, const float* __restrict__ params, const float* __
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int npix = sp.Ho * sp.Wo;
-  const int p0 = blockIdx.x * kStemPix;
+  const int ntiles = (npix + kStemPix - 1) / kStemPix;
   const __half hz = __float2half_rn(0.f);
 
-  // ---- stage parameters
+  // ---- stage parameters (once per CTA; the CTA then walks over pixel tiles)
   for (int i = tid; i < n_conv; i += kStemThreads) Pc[i] = params[i];
   for (int i = tid; i < 3 * HID; i += kStemThreads) { bge[i] = params[sp.o_bge + i]; bgi[i] = params[sp.o_bgi + i]; }
   for (int i = tid; i < HID; i += kStemThreads) { bse[i] = params[sp.o_bse + i]; bsi[i] = params[sp.o_bsi + i]; }
@@ -448,30 +457,51 @@ stem_mma_kernel(StemParams sp, const float* __restrict__ params, const float* __
   }
   __syncthreads();
 
-  // ---- phase 1: conv_1 of both modalities -> Xe / Xi (fp16)
-  for (int item = tid; item < kStemPix * 8; item += kStemThreads) {
-    const int px = item & 63, ch = item >> 6;
-    const int p = p0 + px;
-    const bool ev = ch < 5;
-    const int Cin = ev ? sp.Ce : sp.Ci, co = ev ? ch : ch - 5;
-    if (p >= npix || co >= Cin) continue;
-    const int oy = p / sp.Wo, ox = p - oy * sp.Wo;
-    const float* src = ev ? events : image;
-    const float* Wc = Pc + (ev ? sp.o_wce : sp.o_wci) + co * Cin * sp.k * sp.k;
-    float acc = Pc[(ev ? sp.o_bce : sp.o_bci) + co];
-    for (int ci = 0; ci < Cin; ci++)
-      for (int ky = 0; ky < sp.k; ky++) {
-        const int iy = oy * sp.stride - sp.pad + ky;
-        const bool oky = (unsigned)iy < (unsigned)sp.H;
-        const float* row = src + ((size_t)ci * sp.H + (oky ? iy : 0)) * sp.W;
-#pragma unroll 5
-        for (int kx = 0; kx < sp.k; kx++) {
-          const int ix = ox * sp.stride - sp.pad + kx;
-          const bool ok = oky && (unsigned)ix < (unsigned)sp.W;
-          acc += (ok ? Wc[(ci * sp.k + ky) * sp.k + kx] : 0.f) * row[ok ? ix : 0];
+  const int mt = warp & 3, half_id = warp >> 2;      // m-tile of this warp, which half of the n-tiles
+  const int r0 = 16 * mt + g, r1 = r0 + 8;
+
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const int p0 = tile * kStemPix;
+  // ---- phase 1: conv_1 of both modalities -> Xe / Xi (fp16).  K (kernel size) is a template
+  // parameter: stride = max(K-1, 1), pad = (K > 1); taps are unrolled, the valid tap range is
+  // computed once per item instead of a bounds check (and index arithmetic) per tap.
+  {
+    constexpr int STRIDE = K > 1 ? K - 1 : 1, PAD = K > 1 ? 1 : 0;
+    for (int item = tid; item < kStemPix * 8; item += kStemThreads) {
+      const int px = item & 63, ch = item >> 6;
+      const int p = p0 + px;
+      const bool ev = ch < 5;
+      const int Cin = ev ? sp.Ce : sp.Ci, co = ev ? ch : ch - 5;
+      if (p >= npix || co >= Cin) continue;
+      const int oy = p / sp.Wo, ox = p - oy * sp.Wo;
+      const int iy0 = oy * STRIDE - PAD, ix0 = ox * STRIDE - PAD;
+      const float* src = (ev ? events : image) + (size_t)iy0 * sp.W + ix0;
+      const float* Wc = Pc + (ev ? sp.o_wce : sp.o_wci) + co * Cin * K * K;
+      float acc = Pc[(ev ? sp.o_bce : sp.o_bci) + co];
+      const bool interior = iy0 >= 0 && ix0 >= 0 && iy0 + K <= sp.H && ix0 + K <= sp.W;
+      if (interior) {
+        for (int ci = 0; ci < Cin; ci++) {
+          const float* sc = src + (size_t)ci * sp.H * sp.W;
+#pragma unroll
+          for (int ky = 0; ky < K; ky++)
+#pragma unroll
+            for (int kx = 0; kx < K; kx++) acc += Wc[(ci * K + ky) * K + kx] * sc[ky * sp.W + kx];
+        }
+      } else {
+        for (int ci = 0; ci < Cin; ci++) {
+          const float* sc = src + (size_t)ci * sp.H * sp.W;
+#pragma unroll
+          for (int ky = 0; ky < K; ky++)
+#pragma unroll
+            for (int kx = 0; kx < K; kx++) {
+              const bool ok = (unsigned)(iy0 + ky) < (unsigned)sp.H && (unsigned)(ix0 + kx) < (unsigned)sp.W;
+              if (ok) acc += Wc[(ci * K + ky) * K + kx] * sc[ky * sp.W + kx];
+            }
         }
       }
-    (ev ? Xe : Xi)[px * LDX + co] = __float2half_rn(acc);
+      (ev ? Xe : Xi)[px * LDX + co] = __float2half_rn(acc);
+    }
   }
   // previous super state -> inA[:, 0:h)
   for (int i = tid; i < kStemPix * HID / 2; i += kStemThreads) {
@@ -482,9 +512,6 @@ stem_mma_kernel(StemParams sp, const float* __restrict__ params, const float* __
     *reinterpret_cast<uint32_t*>(inA + px * LDA + 2 * c2) = v;
   }
   __syncthreads();
-
-  const int mt = warp & 3, half_id = warp >> 2;      // m-tile of this warp, which half of the n-tiles
-  const int r0 = 16 * mt + g, r1 = r0 + 8;
 
   // ---- phase 2: gates (one k-step) + LSTM cell, one step from a zero state
 #pragma unroll 1
@@ -547,6 +574,7 @@ stem_mma_kernel(StemParams sp, const float* __restrict__ params, const float* __
     }
     __syncthreads();
   }
+  }  // tile loop
 }
 
 static size_t stem_mma_smem(const StemParams& sp, int h) {
