@@ -45,19 +45,25 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.armed = index, [], False, False
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        # one long-running nvidia-smi in loop mode (a fresh process per sample takes ~80 ms)
+        try:
+            proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                     "--format=csv,noheader,nounits", "-lms", "20"],
+                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        try:
+            while not self.stop_flag:
+                line = proc.stdout.readline()
+                if not line:
+                    break
+                if self.armed:
+                    self.rows.append([x.strip() for x in line.split(",")])
+        finally:
+            proc.kill()
 
     def summary(self):
         import statistics
@@ -119,9 +125,11 @@ def run_ours(args):
     def timed(step_fn, first, profile=False):
         for t in range(first, first + W):
             step_fn(t)
-        barrier()
         sampler = ClockSampler(local)
         sampler.start()
+        time.sleep(0.3)                      # let nvidia-smi start streaming before the timed region
+        barrier()
+        sampler.armed = True
         l0 = L.rvo_launch_count() + state["vo"].graph_kernel_launches
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if profile:
@@ -133,6 +141,7 @@ def run_ours(args):
         barrier()
         if profile:
             torch.cuda.profiler.stop()
+        sampler.armed = False
         sampler.stop_flag = True
         ms = a.elapsed_time(b)
         launches = L.rvo_launch_count() + state["vo"].graph_kernel_launches - l0
@@ -294,7 +303,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

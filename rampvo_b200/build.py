@@ -20,6 +20,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
+    "-ftemplate-depth=4096",
 ]
 
 

@@ -669,6 +669,8 @@ static int ba_solve(const BaWs& w, float* poses, float* patches, const float* Sy
     const size_t smem = in_smem ? solve_smem_bytes(n6) : 2 * (size_t)n6 * sizeof(float);
     RVO_CUDA(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)kSmemMax));
+    // (a fully unrolled single-warp register Cholesky was tried for 6N <= 64: 60 us vs 45 us here —
+    // its ~160 KB of straight-line code runs once per launch and is bound by instruction fetch)
     const dim3 threads(32, n6 <= 24 ? 8 : 32);
     ba_solve_kernel<<<1, threads, smem, st>>>(Sy, N, t0, t0_dev, poses, w.dX, in_smem ? nullptr : w.A);
     RVO_LAUNCH_CHECK("ba_solve_kernel");
