@@ -20,6 +20,7 @@
 //   every (row, a) is one aligned 16-byte store.  rvo_corr_pyramid keeps the reference's [E, 882] layout.
 #include <stdlib.h>
 
+#include <cuda.h>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -120,7 +121,7 @@ tc_bin_count_kernel(TcGeom G, const float* __restrict__ coords, const int64_t* _
 }
 
 struct __align__(16) TcHdr {
-  int nrows, rbase, lvl, f, X0, Y0, pad0, pad1;
+  int nrows, rbase, lvl, f, X0, Y0, flags, pad1;   // flags: bit 0 = same tile as the previous block, bit 1 = as the next
 };
 
 // one CTA: exclusive scans of the per-bin row counts and block counts (counts staged in shared
@@ -172,11 +173,12 @@ tc_block_hdr_kernel(TcGeom G, const int32_t* __restrict__ cnt, const int32_t* __
   TcHdr h;
   h.lvl = lvl; h.f = t / TY;
   h.X0 = tx * kTcStep - kTcWin; h.Y0 = ty * kTcStep - kTcWin;
-  h.pad0 = h.pad1 = 0;
+  h.pad1 = 0;
   const int rs = rowstart[b], bs = blkstart[b];
   for (int i = 0; i * kTcRows < c; i++) {
     h.nrows = min(kTcRows, c - i * kTcRows);
     h.rbase = rs + i * kTcRows;
+    h.flags = (i > 0 ? 1 : 0) | ((i + 1) * kTcRows < c ? 2 : 0);
     hdr[bs + i] = h;
   }
 }
@@ -337,7 +339,7 @@ __device__ __forceinline__ TcHdr ld_hdr(const TcHdr* __restrict__ hdr, int b) {
   const uint4 a = p[0], c = p[1];
   TcHdr h;
   h.nrows = (int)a.x; h.rbase = (int)a.y; h.lvl = (int)a.z; h.f = (int)a.w;
-  h.X0 = (int)c.x; h.Y0 = (int)c.y; h.pad0 = 0; h.pad1 = 0;
+  h.X0 = (int)c.x; h.Y0 = (int)c.y; h.flags = (int)c.z; h.pad1 = 0;
   return h;
 }
 
@@ -549,6 +551,264 @@ corr_tile_pipe_kernel(TcGeom G, const __half* __restrict__ gmap, const TcHdr* __
   }
 }
 
+// ------------------------------------------------------------------ TMA variant ----
+//
+// corr_tile_tma_kernel: the same block list, restructured around the memory system —
+//   B tiles   one thread issues two cp.async.bulk.tensor (TMA) box loads per tile: the 4-D tensor map
+//             over the channels-last frame ring {C, W, H, N} with box {64, 16, 16, 1} and
+//             SWIZZLE_128B lands exactly in the UMMA canonical layout, and out-of-map positions
+//             (negative coordinates included) are zero-filled by the hardware.  A tile is loaded
+//             ONCE for all consecutive row blocks that share it (level 2 has ~5 blocks per tile);
+//   chunks    a CTA takes chunks of kChunk consecutive blocks (so tile sharing survives the
+//             persistent schedule) strided by the grid;
+//   A rows    4 producer warps gather the 128 patch-pixel vectors with cp.async, two blocks in
+//             flight (completion of block b is published after block b+1 has been issued);
+//   MMA       as before, 8 x tcgen05.mma M128 N256 K16 per block into one of two TMEM accumulators;
+//   epilogue  2 x 4 warps; warps whose 32 rows are all past nrows skip the drain, the window-row
+//             staging uses 16-byte shared-memory stores.
+constexpr int kChunkLog2 = 3;
+constexpr int kChunk = 1 << kChunkLog2;
+constexpr int kTmaThreads = 640;              // warps 0-7 A producers, 8 TMA, 9 MMA, 12-19 epilogue
+constexpr int kTmaTmaWarp = 8;
+constexpr int kTmaMmaWarp = 9;
+constexpr int kTmaEpiWarp0 = 12;
+constexpr int kTmaOffB = 0;                   // 2 x 64 KB
+constexpr int kTmaOffA = 2 * kTcSmemB;        // 2 x 32 KB
+constexpr int kTmaOffS = kTmaOffA + 2 * kTcSmemA;
+constexpr int kStageV = 20;                   // floats per thread of the window-row stage (16 + pad, 16-B aligned)
+constexpr int kTmaSmemBytes = kTmaOffS + 256 * kStageV * 4 + 1024;
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2];\n" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+struct __align__(64) TcTmap {
+  unsigned char bytes[128];                   // CUtensorMap
+};
+
+// block index of the i-th block of this CTA's schedule
+__device__ __forceinline__ int tma_block(int i) {
+  return ((int)blockIdx.x + (i >> kChunkLog2) * (int)gridDim.x) * kChunk + (i & (kChunk - 1));
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 1)
+corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__ TcTmap tm1,
+                     const __half* __restrict__ gmap, const TcHdr* __restrict__ hdr,
+                     const TcRow* __restrict__ rows, const int32_t* __restrict__ total_blocks,
+                     __half* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bfull[2], bempty[2], afull[2], aempty[2], tfull[2], tempty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ long long rowsrc[2][kTcRows];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nblk = total_blocks[0];
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; s++) {
+      mbar_init(&bfull[s], 1);
+      mbar_init(&bempty[s], 1);
+      mbar_init(&afull[s], 128);
+      mbar_init(&aempty[s], 1);
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == kTmaMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(
+                     smem_u32(&tmem_base_s))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 8) {
+    // ===== A producers: group pg (4 warps) fills stage pg for blocks i == pg (mod 2); the two groups
+    // run concurrently so one block's gather is in flight while the other is published.  Thread owns
+    // 16-byte chunk `ch` of rows q0 + 8 j =====
+    const int pg = warp >> 2, ptid = tid & 127;
+    const int ch = ptid & 15, q0 = ptid >> 4;
+    const uint32_t swz = (uint32_t)(((ch & 7) ^ q0) << 4);
+    const uint32_t kboff_a = (ch >> 3) * (kTcRows * 128);
+    const __half* gsrc = gmap + ch * 8;
+    const uint32_t dst0 = smem_u32(smem + kTmaOffA + pg * kTcSmemA) + kboff_a + swz + q0 * 128;
+    TcHdr Hn;
+    if (tma_block(pg) < nblk) Hn = ld_hdr(hdr, tma_block(pg));
+    for (int i = pg;; i += 2) {
+      const int b = tma_block(i);
+      if (b >= nblk) break;
+      const TcHdr B = Hn;
+      if (tma_block(i + 2) < nblk) Hn = ld_hdr(hdr, tma_block(i + 2));
+      const long long my_src = (ptid < B.nrows) ? rows[B.rbase + ptid].src : -1;
+      mbar_wait(&aempty[pg], ((i >> 1) & 1) ^ 1);
+      rowsrc[pg][ptid] = my_src;
+      if (pg == 0) asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      else asm volatile("bar.sync 2, 128;\n" ::: "memory");
+      uint32_t dst = dst0;
+      const long long* rs = rowsrc[pg] + q0;
+#pragma unroll 4
+      for (int j = 0; j < 16; j++, dst += 8 * 128) {
+        const long long off = rs[8 * j];
+        const bool ok = off >= 0;
+        cp_async16(dst, gsrc + (ok ? off : 0), ok ? 16u : 0u);
+      }
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> async proxy
+      mbar_arrive(&afull[pg]);
+    }
+  } else if (warp == kTmaTmaWarp) {
+    // ===== TMA producer: one thread, one tile load per run of blocks that share the tile =====
+    if (lane == 0) {
+      int ib = 0;
+      TcHdr Hn;
+      if (tma_block(0) < nblk) Hn = ld_hdr(hdr, tma_block(0));
+      for (int i = 0;; i++) {
+        const int b = tma_block(i);
+        if (b >= nblk) break;
+        const TcHdr B = Hn;
+        if (tma_block(i + 1) < nblk) Hn = ld_hdr(hdr, tma_block(i + 1));
+        const bool newB = (i & (kChunk - 1)) == 0 || !(B.flags & 1);
+        if (!newB) continue;
+        const int s = ib & 1;
+        mbar_wait(&bempty[s], ((ib >> 1) & 1) ^ 1);
+        const void* tm = B.lvl ? (const void*)&tm1 : (const void*)&tm0;
+        const uint32_t Bs_u = smem_u32(smem + kTmaOffB + s * kTcSmemB);
+        mbar_expect_tx(&bfull[s], (uint32_t)kTcSmemB);
+        tma_load_4d(Bs_u, tm, 0, B.X0, B.Y0, B.f, &bfull[s]);
+        tma_load_4d(Bs_u + 256 * 128, tm, 64, B.X0, B.Y0, B.f, &bfull[s]);
+        ib++;
+      }
+    }
+  } else if (warp == kTmaMmaWarp) {
+    // ===== MMA issuer =====
+    int ib = -1;
+    TcHdr Hn;
+    if (tma_block(0) < nblk) Hn = ld_hdr(hdr, tma_block(0));
+    for (int i = 0;; i++) {
+      const int b = tma_block(i);
+      if (b >= nblk) break;
+      const TcHdr B = Hn;
+      if (tma_block(i + 1) < nblk) Hn = ld_hdr(hdr, tma_block(i + 1));
+      const bool newB = (i & (kChunk - 1)) == 0 || !(B.flags & 1);
+      const bool lastB = (i & (kChunk - 1)) == kChunk - 1 || !(B.flags & 2);
+      if (newB) {
+        ib++;
+        mbar_wait(&bfull[ib & 1], (ib >> 1) & 1);
+      }
+      const int s = i & 1, sb = ib & 1;
+      mbar_wait(&afull[s], (i >> 1) & 1);
+      mbar_wait(&tempty[s], ((i >> 1) & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      if (lane == 0) {
+        const uint32_t As_u = smem_u32(smem + kTmaOffA + s * kTcSmemA);
+        const uint32_t Bs_u = smem_u32(smem + kTmaOffB + sb * kTcSmemB);
+#pragma unroll
+        for (int kb = 0; kb < 2; kb++)
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            umma_f16(tmem_base + s * 256, umma_desc(As_u + kb * (kTcRows * 128) + k * 32),
+                     umma_desc(Bs_u + kb * (256 * 128) + k * 32), (kb | k) ? 1u : 0u);
+        umma_commit(&aempty[s]);
+        umma_commit(&tfull[s]);
+        if (lastB) umma_commit(&bempty[sb]);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= kTmaEpiWarp0) {
+    // ===== epilogue: group g (4 warps) drains TMEM accumulator g, i.e. blocks i == g (mod 2) =====
+    const int g = (warp - kTmaEpiWarp0) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    float* S1 = reinterpret_cast<float*>(smem + kTmaOffS) + (g * 128 + row) * kStageV;
+    const uint32_t tlane = tmem_base + g * 256 + ((uint32_t)(q * 32) << 16);
+    TcHdr Hn;
+    if (tma_block(g) < nblk) Hn = ld_hdr(hdr, tma_block(g));
+    for (int i = g;; i += 2) {
+      const int b = tma_block(i);
+      if (b >= nblk) break;
+      const TcHdr B = Hn;
+      if (tma_block(i + 2) < nblk) Hn = ld_hdr(hdr, tma_block(i + 2));
+      int ox = 0, oy = 1 << 20;
+      float dx = 0.f, dy = 0.f;
+      __half* orow = out;
+      if (row < B.nrows) {
+        const uint4* rp = reinterpret_cast<const uint4*>(rows + B.rbase + row);
+        const uint4 r0 = rp[0], r1 = rp[1];
+        orow = out + (((long long)r0.w << 32) | (long long)r0.z);
+        dx = __uint_as_float(r1.x);
+        dy = __uint_as_float(r1.y);
+        ox = (int)r1.z;
+        oy = (int)r1.w;
+      }
+      mbar_wait(&tfull[g], (i >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      if (q * 32 < B.nrows) {                               // warp-uniform: this warp owns live rows
+        float hprev[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) hprev[k] = 0.f;
+#pragma unroll 1
+        for (int wy2 = 0; wy2 < kTcTile; wy2 += 2) {
+          float v[32];
+          tmem_ld32(tlane + wy2 * kTcTile, v);
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++) {
+            const int a = wy2 + hh - oy;
+            if (a >= 0 && a <= 7) {
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+                *reinterpret_cast<float4*>(S1 + 4 * k) =
+                    make_float4(v[hh * 16 + 4 * k], v[hh * 16 + 4 * k + 1], v[hh * 16 + 4 * k + 2],
+                                v[hh * 16 + 4 * k + 3]);
+              float c[8], h[7];
+#pragma unroll
+              for (int k = 0; k < 8; k++) c[k] = S1[ox + k];
+#pragma unroll
+              for (int k = 0; k < 7; k++) h[k] = c[k] + dx * (c[k + 1] - c[k]);
+              if (a >= 1) {
+                float o[7];
+#pragma unroll
+                for (int k = 0; k < 7; k++) o[k] = hprev[k] + dy * (h[k] - hprev[k]);
+                const __half2 p0 = __floats2half2_rn(o[0], o[1]), p1 = __floats2half2_rn(o[2], o[3]);
+                const __half2 p2 = __floats2half2_rn(o[4], o[5]), p3 = __floats2half2_rn(o[6], 0.f);
+                uint4 u;
+                u.x = *reinterpret_cast<const uint32_t*>(&p0);
+                u.y = *reinterpret_cast<const uint32_t*>(&p1);
+                u.z = *reinterpret_cast<const uint32_t*>(&p2);
+                u.w = *reinterpret_cast<const uint32_t*>(&p3);
+                *reinterpret_cast<uint4*>(orow + (a - 1) * 8) = u;
+              }
+#pragma unroll
+              for (int k = 0; k < 7; k++) hprev[k] = h[k];
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      mbar_arrive(&tempty[g]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == kTmaMmaWarp) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ host ----
 
 struct TcWs {
@@ -607,6 +867,47 @@ static int tc_geom(const rvo_fmap_t* pyr, const float* scale, int nlevels, TcGeo
 
 }  // namespace rvo
 
+
+namespace rvo {
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 4-D map over a channels-last level {C = 128, W, H, N}; box = one K block of a tile: {64, 16, 16, 1}
+static int tc_make_tmap(const TcLevel& L, TcTmap* out) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  RVO_CHECK_ARG(enc != nullptr, "rvo_corr_tiles: cuTensorMapEncodeTiled is not available in this driver");
+  static_assert(sizeof(CUtensorMap) == sizeof(TcTmap), "CUtensorMap size");
+  const cuuint64_t dims[4] = {(cuuint64_t)kTcC, (cuuint64_t)L.W, (cuuint64_t)L.H, (cuuint64_t)L.N};
+  const cuuint64_t strides[3] = {(cuuint64_t)L.sW * 2, (cuuint64_t)L.sH * 2, (cuuint64_t)L.sN * 2};
+  const cuuint32_t box[4] = {64, (cuuint32_t)kTcTile, (cuuint32_t)kTcTile, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                   const_cast<__half*>(L.data), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RVO_CHECK_ARG(r == CUDA_SUCCESS, "rvo_corr_tiles: cuTensorMapEncodeTiled failed (%d) for a level of %d x %d x %d",
+                (int)r, L.N, L.H, L.W);
+  return RVO_OK;
+}
+
+}  // namespace rvo
+
 using namespace rvo;
 
 extern "C" int64_t rvo_corr_tiles_ws_bytes(const rvo_fmap_t* pyr, int nlevels, int E) {
@@ -653,9 +954,22 @@ extern "C" int rvo_corr_tiles(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, co
   tc_bin_scatter_kernel<<<grid, 256, 0, st>>>(G, coords, kk, pmod, fmap1->sN, fmap1->sH, fmap1->sW, out_ld, R,
                                               w.rowbin, w.rowrank, w.rowstart, w.rows);
   RVO_LAUNCH_CHECK("tc_bin_scatter_kernel");
-  RVO_CUDA(cudaFuncSetAttribute(corr_tile_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmemBytes));
-  corr_tile_pipe_kernel<<<kNumSMs, kPipeThreads, kPipeSmemBytes, st>>>(G, (const __half*)fmap1->data, w.hdr,
-                                                                       w.rows, w.total, (__half*)out);
-  RVO_LAUNCH_CHECK("corr_tile_pipe_kernel");
+  static const bool legacy = getenv("RVO_CORR_LEGACY") != nullptr;   // debugging aid: the cp.async-only kernel
+  if (legacy) {
+    RVO_CUDA(cudaFuncSetAttribute(corr_tile_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmemBytes));
+    corr_tile_pipe_kernel<<<kNumSMs, kPipeThreads, kPipeSmemBytes, st>>>(G, (const __half*)fmap1->data, w.hdr,
+                                                                         w.rows, w.total, (__half*)out);
+    RVO_LAUNCH_CHECK("corr_tile_pipe_kernel");
+    return RVO_OK;
+  }
+  TcTmap tm[kTcMaxLevels];
+  for (int l = 0; l < kTcMaxLevels; l++) {
+    rc = tc_make_tmap(G.lv[l], &tm[l]);
+    if (rc != RVO_OK) return rc;
+  }
+  RVO_CUDA(cudaFuncSetAttribute(corr_tile_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
+  corr_tile_tma_kernel<<<kNumSMs, kTmaThreads, kTmaSmemBytes, st>>>(tm[0], tm[1], (const __half*)fmap1->data,
+                                                                    w.hdr, w.rows, w.total, (__half*)out);
+  RVO_LAUNCH_CHECK("corr_tile_tma_kernel");
   return RVO_OK;
 }
