@@ -221,8 +221,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": 28},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "altcorr lookup, both pyramid levels: corr_tile_pipe_kernel (tcgen05/TMEM) "
-                               "incl. its 4 binning passes", "bound": "hbm",
+        "roofline": {"kernel": "altcorr lookup, both pyramid levels: corr_tile_tma_kernel (tcgen05/TMEM, TMA "
+                               "tile loads) incl. its 3 binning passes", "bound": "hbm",
                      "achieved": alg / corr_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": alg / corr_s / 1e9 / peaks["hbm_gbs"], "traffic": traffic,
                      "peak_source": which, "algorithmic_bytes": alg, "launch_us": corr_s * 1e6},

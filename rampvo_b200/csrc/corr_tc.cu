@@ -6,14 +6,16 @@
 //
 //   bin      every (edge, patch pixel, level) row is assigned to the 16x16-position tile of its target
 //            frame that contains its 8x8 window (tiles step by 9 so every window fits in exactly one
-//            tile): histogram + scan + scatter on the device, no host sync;
-//   GEMM     one CTA per (tile, <=128 rows): A = the rows' 128-channel patch vectors gathered into
-//            shared memory, B = the tile's 256 feature vectors (zero-filled outside the map), both in
-//            the canonical K-major SWIZZLE_128B layout; ONE elected thread issues 8 tcgen05.mma
-//            (M=128, N=256, K=16) into a 128x256 fp32 accumulator in TMEM;
-//   epilogue thread r owns TMEM lane r: tcgen05.ld brings one tile row (16 columns) at a time, the
-//            thread picks its own 8-wide window, does the separable bilinear blend and stages its
-//            7x7 outputs in shared memory; rows are then written with coalesced 100-byte stores.
+//            tile) and, inside the tile, ordered by the tile row its window starts in: warp-aggregated
+//            histogram + single-CTA scan + scatter on the device, no host sync;
+//   GEMM     persistent CTAs walk the (tile, <=128 rows) blocks: A = the rows' 128-channel patch vectors
+//            gathered with cp.async, B = the tile's 256 feature vectors brought by TMA (zero-filled
+//            outside the map), both in the canonical K-major SWIZZLE_128B layout; ONE elected thread
+//            issues 8 tcgen05.mma (M=128, N=256, K=16) into a 128x256 fp32 accumulator in TMEM;
+//   epilogue thread r owns TMEM lane r: tcgen05.ld brings two tile rows at a time, the thread picks its
+//            own 8-wide window in registers, does the separable bilinear blend and writes each of its
+//            7 output rows as one aligned 16-byte store.
+//   (corr_tile_tma_kernel below documents the pipeline and what was measured to bound it.)
 //
 // Output layout ("tile layout", consumed by the update operator with a permuted first-layer weight):
 //   out[e, ((lvl*9 + pix)*7 + a)*8 + b], a = y offset, b = x offset (0..6); b = 7 is a zero pad so that
@@ -34,8 +36,8 @@ constexpr int kTcStep = 9;         // tile step = tile - window + 1
 constexpr int kTcRows = 128;       // rows (edge, pixel, level) per CTA = MMA M
 constexpr int kTcC = 128;          // channels = MMA K total
 constexpr int kTcGroup = 56;       // output halves per (level, pixel) group: 7 rows of 8 (7 used)
-constexpr int kTcThreads = 128;
 constexpr int kTcMaxLevels = 2;
+constexpr int kTcSub = 12;         // counters per tile: one per window-origin row oy = 0..8 (12 keeps int4 alignment)
 
 struct TcLevel {
   const __half* data;
@@ -59,56 +61,83 @@ __device__ __forceinline__ int tc_floor(float v) {
 
 // ------------------------------------------------------------------ binning ----
 
-// one thread per (edge, level): the 9 patch pixels of an edge almost always share one tile, so their
-// histogram updates are aggregated into one atomicAdd per distinct bin (ranks stay unique per bin)
+// index % mod for ring-buffer indices: 32-bit arithmetic whenever the operands allow it (a 64-bit
+// modulo is ~100 instructions)
+__device__ __forceinline__ int64_t tc_mod(int64_t v, int64_t mod) {
+  if (mod <= 0) return v;
+  if ((uint64_t)v < 0x80000000ull && mod < 0x80000000ll) return (int64_t)((uint32_t)v % (uint32_t)mod);
+  return v % mod;
+}
+
+// one thread per (edge, level): the 9 patch pixels of an edge almost always share a tile and fall into
+// ~3 window-origin rows, so the histogram updates are aggregated in registers — one atomicAdd per
+// distinct sub-bin (its return value ranks the rows, ranks stay unique per sub-bin) and one
+// fire-and-forget add per distinct tile for the per-tile totals
 __global__ void __launch_bounds__(256)
 tc_bin_count_kernel(TcGeom G, const float* __restrict__ coords, const int64_t* __restrict__ kk,
                     const int64_t* __restrict__ jj, int64_t pmod, int64_t fmod, int64_t gN, int E,
-                    int32_t* __restrict__ cnt, int32_t* __restrict__ rowbin,
+                    int32_t* __restrict__ cnt, int32_t* __restrict__ tot, int32_t* __restrict__ rowbin,
                     int32_t* __restrict__ rowrank, __half* __restrict__ out, int64_t out_ld) {
   const int NL = G.nlevels;
-  const int64_t T = (int64_t)E * NL;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < T;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    const int lvl = (int)(t % NL);
-    const int e = (int)(t / NL);
+  const int T = E * NL;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    const int e = t / NL;
+    const int lvl = t - e * NL;
     const bool l1 = lvl != 0;
     const float scale = l1 ? G.lv[1].scale : G.lv[0].scale;
     const int LW = l1 ? G.lv[1].W : G.lv[0].W, LH = l1 ? G.lv[1].H : G.lv[0].H;
     const int LN = l1 ? G.lv[1].N : G.lv[0].N, TX = l1 ? G.lv[1].TX : G.lv[0].TX;
     const int TY = l1 ? G.lv[1].TY : G.lv[0].TY, base = l1 ? G.lv[1].binbase : G.lv[0].binbase;
-    int64_t ip = kk[e], jf = jj[e];
-    if (pmod > 0) ip %= pmod;
-    if (fmod > 0) jf %= fmod;
+    const int64_t ip = tc_mod(kk[e], pmod), jf = tc_mod(jj[e], fmod);
     const bool idx_ok = ip >= 0 && ip < gN && jf >= 0 && jf < LN;
-    int bins[9];
+    const float* cp = coords + (int64_t)e * 18;
+    int subs[9];
 #pragma unroll
     for (int pix = 0; pix < 9; pix++) {
-      const float x = coords[(int64_t)e * 18 + pix] * scale;
-      const float y = coords[(int64_t)e * 18 + 9 + pix] * scale;
-      const int x0 = tc_floor(x) - kTcR, y0 = tc_floor(y) - kTcR;
+      const int x0 = tc_floor(cp[pix] * scale) - kTcR, y0 = tc_floor(cp[9 + pix] * scale) - kTcR;
       const bool ok = idx_ok && x0 > -kTcWin && x0 < LW && y0 > -kTcWin && y0 < LH;
-      bins[pix] = ok ? base + ((int)jf * TY + (y0 + kTcWin) / kTcStep) * TX + (x0 + kTcWin) / kTcStep : -1;
+      // sub-bin = (tile, oy): rows of a tile end up sorted by the tile row their window starts in, so a
+      // warp of the tile kernel's epilogue reads few more than 8 accumulator rows
+      subs[pix] = ok ? (base + ((int)jf * TY + (y0 + kTcWin) / kTcStep) * TX + (x0 + kTcWin) / kTcStep) * kTcSub +
+                           (y0 + kTcWin) % kTcStep
+                     : -1;
     }
     int ranks[9];
-#pragma unroll
-    for (int pix = 0; pix < 9; pix++) ranks[pix] = -1;
+    unsigned done = 0, tdone = 0;
 #pragma unroll
     for (int pix = 0; pix < 9; pix++) {
-      if (bins[pix] < 0 || ranks[pix] >= 0) continue;
+      ranks[pix] = -1;
+      if (subs[pix] < 0 || ((done >> pix) & 1u)) continue;
       int n = 0;
 #pragma unroll
-      for (int q = 0; q < 9; q++) n += (q >= pix && bins[q] == bins[pix]) ? 1 : 0;
-      int r0 = atomicAdd(&cnt[bins[pix]], n);
+      for (int q = 0; q < 9; q++)
+        if (q >= pix && subs[q] == subs[pix]) n++;
+      int r0 = atomicAdd(&cnt[subs[pix]], n);
 #pragma unroll
       for (int q = 0; q < 9; q++)
-        if (q >= pix && bins[q] == bins[pix]) ranks[q] = r0++;
+        if (q >= pix && subs[q] == subs[pix]) {
+          ranks[q] = r0++;
+          done |= 1u << q;
+        }
     }
 #pragma unroll
     for (int pix = 0; pix < 9; pix++) {
-      const int64_t r = ((int64_t)e * 9 + pix) * NL + lvl;
-      rowbin[r] = bins[pix];
-      if (bins[pix] >= 0) {
+      if (subs[pix] < 0 || ((tdone >> pix) & 1u)) continue;
+      const int tile = subs[pix] / kTcSub;
+      int n = 0;
+#pragma unroll
+      for (int q = 0; q < 9; q++)
+        if (q >= pix && subs[q] >= 0 && subs[q] / kTcSub == tile) {
+          n++;
+          tdone |= 1u << q;
+        }
+      atomicAdd(&tot[tile], n);
+    }
+#pragma unroll
+    for (int pix = 0; pix < 9; pix++) {
+      const int r = (e * 9 + pix) * NL + lvl;
+      rowbin[r] = subs[pix];
+      if (subs[pix] >= 0) {
         rowrank[r] = ranks[pix];
       } else {
         // window entirely outside the map (or invalid index): the 7x7 outputs are zero
@@ -124,62 +153,51 @@ struct __align__(16) TcHdr {
   int nrows, rbase, lvl, f, X0, Y0, flags, pad1;   // flags: bit 0 = same tile as the previous block, bit 1 = as the next
 };
 
-// one CTA: exclusive scans of the per-bin row counts and block counts (counts staged in shared
-// memory with coalesced loads)
-constexpr int kScanMaxBins = 49152;        // 192 KB of dynamic shared memory
+// one CTA: exclusive scans of the per-tile row totals and 128-row block counts -> first row and first
+// block of every tile.  Kept tiny on purpose — it runs on ONE SM: coalesced loads / stores staged
+// through shared memory (a single SM keeps few scattered sectors in flight), everything heavier (the
+// block headers) is done by the row-parallel scatter pass.
+constexpr int kScanMaxBins = 24576;          // 6 B x bins + 4 KB of dynamic shared memory
 __global__ void __launch_bounds__(1024)
-tc_bin_scan_kernel(const int32_t* __restrict__ cnt, int nbins, int32_t* __restrict__ rowstart,
+tc_bin_scan_kernel(const int32_t* __restrict__ tot, int nbins, int32_t* __restrict__ rowstart,
                    int32_t* __restrict__ blkstart, int32_t* __restrict__ total_blocks) {
-  typedef cub::BlockScan<int, 1024> Scan;
-  __shared__ typename Scan::TempStorage tmp;
-  extern __shared__ int32_t c_s[];            // [nbins]
-  for (int b = threadIdx.x; b < nbins; b += 1024) c_s[b] = cnt[b];
+  typedef cub::BlockScan<int, 1024, cub::BLOCK_SCAN_WARP_SCANS> Scan;
+  __shared__ typename Scan::TempStorage tmp_r, tmp_b;
+  extern __shared__ int32_t scan_sm[];
+  int32_t* bfirst_s = scan_sm;                               // [1024]
+  int32_t* r_s = scan_sm + 1024;                             // [nbins]
+  uint16_t* b_s = reinterpret_cast<uint16_t*>(r_s + nbins);  // [nbins]
+  for (int b = threadIdx.x; b < nbins; b += 1024) r_s[b] = tot[b];
   __syncthreads();
+  // thread t owns tiles t*per .. t*per + per - 1
   const int per = (nbins + 1023) / 1024;
-  const int b0 = threadIdx.x * per, b1 = min(nbins, b0 + per);
+  const int b0 = threadIdx.x * per;
   int rows = 0, blks = 0;
-  for (int b = b0; b < b1; b++) {
-    rows += c_s[b];
-    blks += (c_s[b] + kTcRows - 1) / kTcRows;
+  for (int i = 0; i < per; i++) {
+    const int c = (b0 + i < nbins) ? r_s[b0 + i] : 0;
+    rows += c;
+    blks += (c + kTcRows - 1) / kTcRows;
   }
   int rpre, bpre, btot;
-  Scan(tmp).ExclusiveSum(rows, rpre);
-  __syncthreads();
-  Scan(tmp).ExclusiveSum(blks, bpre, btot);
-  for (int b = b0; b < b1; b++) {
-    const int c = c_s[b];
-    rowstart[b] = rpre;
-    blkstart[b] = bpre;
-    rpre += c;
-    bpre += (c + kTcRows - 1) / kTcRows;
-  }
+  Scan(tmp_r).ExclusiveSum(rows, rpre);
+  Scan(tmp_b).ExclusiveSum(blks, bpre, btot);
   if (threadIdx.x == 0) total_blocks[0] = btot;
-}
-
-// one thread per tile: the headers of its blocks
-__global__ void __launch_bounds__(256)
-tc_block_hdr_kernel(TcGeom G, const int32_t* __restrict__ cnt, const int32_t* __restrict__ rowstart,
-                    const int32_t* __restrict__ blkstart, TcHdr* __restrict__ hdr) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= G.nbins) return;
-  const int c = cnt[b];
-  if (c == 0) return;
-  const int lvl = (G.nlevels > 1 && b >= G.lv[1].binbase) ? 1 : 0;
-  const bool l1 = lvl != 0;
-  const int TX = l1 ? G.lv[1].TX : G.lv[0].TX, TY = l1 ? G.lv[1].TY : G.lv[0].TY;
-  int t = b - (l1 ? G.lv[1].binbase : G.lv[0].binbase);
-  const int tx = t % TX; t /= TX;
-  const int ty = t % TY;
-  TcHdr h;
-  h.lvl = lvl; h.f = t / TY;
-  h.X0 = tx * kTcStep - kTcWin; h.Y0 = ty * kTcStep - kTcWin;
-  h.pad1 = 0;
-  const int rs = rowstart[b], bs = blkstart[b];
-  for (int i = 0; i * kTcRows < c; i++) {
-    h.nrows = min(kTcRows, c - i * kTcRows);
-    h.rbase = rs + i * kTcRows;
-    h.flags = (i > 0 ? 1 : 0) | ((i + 1) * kTcRows < c ? 2 : 0);
-    hdr[bs + i] = h;
+  // in place: counts -> exclusive row offsets; block offsets relative to the thread's first block fit 16 bits
+  const int bfirst = bpre;
+  for (int i = 0; i < per; i++) {
+    if (b0 + i < nbins) {
+      const int c = r_s[b0 + i];
+      r_s[b0 + i] = rpre;
+      b_s[b0 + i] = (uint16_t)(bpre - bfirst);
+      rpre += c;
+      bpre += (c + kTcRows - 1) / kTcRows;
+    }
+  }
+  bfirst_s[threadIdx.x] = bfirst;
+  __syncthreads();
+  for (int b = threadIdx.x; b < nbins; b += 1024) {
+    rowstart[b] = r_s[b];
+    blkstart[b] = bfirst_s[b / per] + b_s[b];
   }
 }
 
@@ -194,21 +212,22 @@ struct __align__(16) TcRow {
 
 __global__ void __launch_bounds__(256)
 tc_bin_scatter_kernel(TcGeom G, const float* __restrict__ coords, const int64_t* __restrict__ kk,
-                      int64_t pmod, int64_t g_sN, int64_t g_sH, int64_t g_sW, int64_t out_ld, int64_t R,
-                      const int32_t* __restrict__ rowbin, const int32_t* __restrict__ rowrank,
-                      const int32_t* __restrict__ rowstart, TcRow* __restrict__ rows) {
+                      const int64_t* __restrict__ jj, int64_t pmod, int64_t fmod, int64_t g_sN, int64_t g_sH,
+                      int64_t g_sW, int64_t out_ld, int64_t R, const int32_t* __restrict__ rowbin,
+                      const int32_t* __restrict__ rowrank, const int32_t* __restrict__ rowstart,
+                      const int32_t* __restrict__ blkstart, const int32_t* __restrict__ cnt,
+                      const int32_t* __restrict__ tot, TcRow* __restrict__ rows, TcHdr* __restrict__ hdr) {
   const int NL = G.nlevels;
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < R;
-       r += (int64_t)gridDim.x * blockDim.x) {
+  const int Ri = (int)R;                                     // < 2^31 (checked on the host)
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < Ri; r += gridDim.x * blockDim.x) {
     const int bin = rowbin[r];
     if (bin < 0) continue;
-    const int lvl = (int)(r % NL);
-    const int64_t ep = r / NL;
-    const int pix = (int)(ep % 9);
-    const int e = (int)(ep / 9);
+    const int ep = r / NL;
+    const int lvl = r - ep * NL;
+    const int e = ep / 9;
+    const int pix = ep - e * 9;
     const TcLevel& L = G.lv[lvl];
-    int64_t ip = kk[e];
-    if (pmod > 0) ip %= pmod;
+    const int64_t ip = tc_mod(kk[e], pmod);
     const float x = coords[(int64_t)e * 18 + pix] * L.scale;
     const float y = coords[(int64_t)e * 18 + 9 + pix] * L.scale;
     const float fxf = floorf(x), fyf = floorf(y);
@@ -219,7 +238,31 @@ tc_bin_scatter_kernel(TcGeom G, const float* __restrict__ coords, const int64_t*
     rec.dy = y - fyf;
     rec.ox = ((int)fxf - kTcR + kTcWin) % kTcStep;
     rec.oy = ((int)fyf - kTcR + kTcWin) % kTcStep;
-    rows[rowstart[bin] + rowrank[r]] = rec;
+    // rows of a tile are ordered by oy: first row of the tile + rows of the lower sub-bins + rank
+    const int tile = bin / kTcSub, oy = bin - tile * kTcSub;
+    const int4* c4 = reinterpret_cast<const int4*>(cnt) + tile * 3;
+    const int4 v0 = c4[0], v1 = c4[1];
+    const int rs = rowstart[tile];
+    int pos = rs + rowrank[r];
+    pos += (oy > 0 ? v0.x : 0) + (oy > 1 ? v0.y : 0) + (oy > 2 ? v0.z : 0) + (oy > 3 ? v0.w : 0);
+    pos += (oy > 4 ? v1.x : 0) + (oy > 5 ? v1.y : 0) + (oy > 6 ? v1.z : 0) + (oy > 7 ? v1.w : 0);
+    rows[pos] = rec;
+    // the row that opens a 128-row block of its tile also writes the block's header
+    const int k = pos - rs;
+    if ((k & (kTcRows - 1)) == 0) {
+      const int total = tot[tile];
+      const int64_t jf = tc_mod(jj[e], fmod);
+      TcHdr h;
+      h.nrows = min(kTcRows, total - k);
+      h.rbase = pos;
+      h.lvl = lvl;
+      h.f = (int)jf;
+      h.X0 = ((int)fxf - kTcR + kTcWin) / kTcStep * kTcStep - kTcWin;
+      h.Y0 = ((int)fyf - kTcR + kTcWin) / kTcStep * kTcStep - kTcWin;
+      h.flags = (k > 0 ? 1 : 0) | (k + kTcRows < total ? 2 : 0);
+      h.pad1 = 0;
+      hdr[blkstart[tile] + k / kTcRows] = h;
+    }
   }
 }
 
@@ -273,27 +316,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 
 constexpr int kTcSmemA = 2 * kTcRows * 128;            // two K blocks of [128 rows x 128 B] = 32 KB
 constexpr int kTcSmemB = 2 * 256 * 128;                // two K blocks of [256 rows x 128 B] = 64 KB
-constexpr int kStage1 = 17;                            // floats per lane of the window-row stage
 
-// ------------------------------------------------------------------ pipelined persistent variant ----
-//
-// Same math, canonical Blackwell structure: one persistent CTA per SM, warp-specialised, three
-// pipelines through mbarriers —
-//   producers (2 x 4 warps)  group s fills shared-memory stage s (cp.async A rows + B tile) for the
-//                            blocks it == s (mod 2); the two groups run concurrently so one group's
-//                            L2 latency hides behind the other's issue;
-//   MMA issuer (1 warp)      one thread, 8 tcgen05.mma per block into one of two 256-column TMEM
-//                            accumulators; tcgen05.commit releases the smem stage and publishes the
-//                            accumulator;
-//   epilogue (2 x 4 warps)   group s drains TMEM stage s: TMEM lane quadrant per warp, window
-//                            extraction + blend + 16-byte stores while the next block is multiplied.
-constexpr int kPipeThreads = 640;
-constexpr int kPipeProducers = 128;                                      // per stage: warps 0-3 even blocks, 4-7 odd
-constexpr int kPipeMmaWarp = 8;
-constexpr int kPipeEpiWarp0 = 12;                                        // warps 12-15: even blocks, 16-19: odd
-constexpr int kPipeStageBytes = kTcSmemA + kTcSmemB;                     // 96 KB
-constexpr int kPipeEpiBytes = 2 * 128 * kStage1 * 4;                     // 17 408
-constexpr int kPipeSmemBytes = 2 * kPipeStageBytes + kPipeEpiBytes + 1024;
+// ------------------------------------------------------------------ mbarrier / TMEM helpers ----
 
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
@@ -301,32 +325,37 @@ __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
 }
-// Waiting warps share issue slots with the producers: poll, then back off with nanosleep so that
-// a spinning epilogue / MMA warp does not starve the warps that are doing the work.
+// Waiting warps share issue slots with the warps that do the work: try_wait suspends the thread in
+// hardware until the phase completes or the time hint (ns) expires, so a long wait costs a handful of
+// instructions instead of a polling loop (ncu: the nanosleep loop was 25 % of all issued instructions).
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   const uint32_t addr = smem_u32(b);
-  uint32_t done;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}\n"
-      : "=r"(done)
-      : "r"(addr), "r"(parity)
+      "MBW_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra MBW_DONE;\n\t"
+      "bra MBW_LOOP;\n\t"
+      "MBW_DONE:\n\t"
+      "}\n" ::"r"(addr),
+      "r"(parity), "r"(20000u)
       : "memory");
-  while (!done) {
-    __nanosleep(64);
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  }
+}
+// latency-critical single-warp wait (the MMA issuer): try_wait suspends in hardware, no extra sleep
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* b, uint32_t parity) {
+  const uint32_t addr = smem_u32(b);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* b) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
@@ -360,200 +389,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
-__global__ void __launch_bounds__(kPipeThreads, 1)
-corr_tile_pipe_kernel(TcGeom G, const __half* __restrict__ gmap, const TcHdr* __restrict__ hdr,
-                      const TcRow* __restrict__ rows, const int32_t* __restrict__ total_blocks,
-                      __half* __restrict__ out) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[2], empty_bar[2], tfull_bar[2], tempty_bar[2];
-  __shared__ uint32_t tmem_base_s;
-  __shared__ long long rowsrc[2][2][kTcRows];   // [producer group][iteration parity][row]
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nblk = total_blocks[0];
-
-  if (tid == 0) {
-    for (int s = 0; s < 2; s++) {
-      mbar_init(&full_bar[s], kPipeProducers);
-      mbar_init(&empty_bar[s], 1);
-      mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  if (warp == kPipeMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(
-                     smem_u32(&tmem_base_s))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const uint32_t tmem_base = tmem_base_s;
-
-  if (warp < 2 * kPipeProducers / 32) {
-    // ===== producers: group pg fills stage pg; thread owns 16-byte chunk `ch` of rows / positions q0 + 8 j =====
-    const int pg = warp >> 2, ptid = tid & (kPipeProducers - 1);
-    const int ch = ptid & 15, q0 = ptid >> 4;                    // q0 in 0..7
-    // swizzled chunk offset inside a 128-byte row: row & 7 == q0 for every row this thread touches
-    const uint32_t swz = (uint32_t)(((ch & 7) ^ q0) << 4);
-    const uint32_t kboff_a = (ch >> 3) * (kTcRows * 128), kboff_b = (ch >> 3) * (256 * 128);
-    const int s = pg;
-    TcHdr Hn;
-    if ((int)blockIdx.x + pg * (int)gridDim.x < nblk) Hn = ld_hdr(hdr, blockIdx.x + pg * gridDim.x);
-    for (int it = pg; blockIdx.x + it * (int)gridDim.x < nblk; it += 2) {
-      const int b = blockIdx.x + it * gridDim.x;
-      const TcHdr B = Hn;
-      if (b + 2 * (int)gridDim.x < nblk) Hn = ld_hdr(hdr, b + 2 * gridDim.x);   // next header in flight
-      const long long my_src = (ptid < B.nrows) ? rows[B.rbase + ptid].src : -1;
-      mbar_wait(&empty_bar[s], ((it >> 1) & 1) ^ 1);        // first use of a stage passes immediately
-      // level parameters into registers (a dynamically indexed struct would be re-read from the
-      // constant bank on every use)
-      const bool l1 = B.lvl != 0;
-      const __half* ldata = l1 ? G.lv[1].data : G.lv[0].data;
-      const int LH = l1 ? G.lv[1].H : G.lv[0].H, LW = l1 ? G.lv[1].W : G.lv[0].W;
-      const int sH = (int)(l1 ? G.lv[1].sH : G.lv[0].sH), sW = (int)(l1 ? G.lv[1].sW : G.lv[0].sW);
-      const int64_t sN = l1 ? G.lv[1].sN : G.lv[0].sN;
-      const uint32_t As_u = smem_u32(smem + s * kPipeStageBytes);
-      const uint32_t Bs_u = As_u + kTcSmemA;
-      long long* rsrc = rowsrc[pg][(it >> 1) & 1];
-      rsrc[ptid] = my_src;
-      // B: positions p = q0 + 8 j (j < 32): py = j >> 1, px = q0 + 8 (j & 1).  Two fixed columns per
-      // thread, sixteen rows; in-frame offsets are 32-bit (checked on the host).
-      {
-        const __half* fbase = ldata + (int64_t)B.f * sN + ch * 8;
-        const int xa = B.X0 + q0, xb = xa + 8;
-        const bool oka = (unsigned)xa < (unsigned)LW, okb = (unsigned)xb < (unsigned)LW;
-        const int offa = oka ? xa * sW : 0, offb = okb ? xb * sW : 0;
-        uint32_t dst = Bs_u + kboff_b + swz + q0 * 128;
-        int y = B.Y0;
-#pragma unroll 4
-        for (int jy = 0; jy < 16; jy++, y++, dst += 2 * (8 * 128)) {
-          const bool oky = (unsigned)y < (unsigned)LH;
-          const int rowoff = oky ? y * sH : 0;
-          cp_async16(dst, fbase + rowoff + offa, (oky && oka) ? 16u : 0u);
-          cp_async16(dst + 8 * 128, fbase + rowoff + offb, (oky && okb) ? 16u : 0u);
-        }
-      }
-      if (pg == 0) asm volatile("bar.sync 1, 128;\n" ::: "memory");
-      else asm volatile("bar.sync 2, 128;\n" ::: "memory");
-      // A: rows r = q0 + 8 j (j < 16)
-      {
-        uint32_t dst = As_u + kboff_a + swz + q0 * 128;
-        const __half* gsrc = gmap + ch * 8;
-        const long long* rs = rsrc + q0;
-#pragma unroll 4
-        for (int j = 0; j < 16; j++, dst += 8 * 128) {
-          const long long off = rs[8 * j];
-          const bool ok = off >= 0;
-          cp_async16(dst, gsrc + (ok ? off : 0), ok ? 16u : 0u);
-        }
-      }
-      asm volatile("cp.async.commit_group;\n" ::: "memory");
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> async proxy
-      mbar_arrive(&full_bar[s]);
-    }
-  } else if (warp == kPipeMmaWarp) {
-    // ===== MMA issuer =====
-    int it = 0;
-    for (int b = blockIdx.x; b < nblk; b += gridDim.x, it++) {
-      const int s = it & 1;
-      mbar_wait(&full_bar[s], (it >> 1) & 1);
-      mbar_wait(&tempty_bar[s], ((it >> 1) & 1) ^ 1);
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      if (lane == 0) {
-        const uint32_t As_u = smem_u32(smem + s * kPipeStageBytes);
-        const uint32_t Bs_u = As_u + kTcSmemA;
-#pragma unroll
-        for (int kb = 0; kb < 2; kb++)
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            umma_f16(tmem_base + s * 256, umma_desc(As_u + kb * (kTcRows * 128) + k * 32),
-                     umma_desc(Bs_u + kb * (256 * 128) + k * 32), (kb | k) ? 1u : 0u);
-        umma_commit(&empty_bar[s]);     // smem stage may be refilled once these MMAs have read it
-        umma_commit(&tfull_bar[s]);     // accumulator ready for the epilogue
-      }
-      __syncwarp();
-    }
-  } else if (warp >= kPipeEpiWarp0) {
-    // ===== epilogue: group g (4 warps) drains TMEM stage g, i.e. blocks it == g (mod 2) =====
-    const int g = (warp - kPipeEpiWarp0) >> 2;
-    const int q = warp & 3;                               // TMEM lane quadrant of this warp
-    const int row = q * 32 + lane;                        // accumulator row == TMEM lane
-    float* S1 = reinterpret_cast<float*>(smem + 2 * kPipeStageBytes) + (g * 128 + row) * kStage1;
-    const uint32_t tlane = tmem_base + g * 256 + ((uint32_t)(q * 32) << 16);
-    TcHdr Hn;
-    if ((int)blockIdx.x + g * (int)gridDim.x < nblk) Hn = ld_hdr(hdr, blockIdx.x + g * gridDim.x);
-    for (int it = g; blockIdx.x + it * (int)gridDim.x < nblk; it += 2) {
-      const int b = blockIdx.x + it * gridDim.x;
-      const TcHdr B = Hn;
-      if (b + 2 * (int)gridDim.x < nblk) Hn = ld_hdr(hdr, b + 2 * gridDim.x);
-      int ox = 0, oy = 1 << 20;                           // inactive rows never match a window row
-      float dx = 0.f, dy = 0.f;
-      __half* orow = out;
-      if (row < B.nrows) {
-        const uint4* rp = reinterpret_cast<const uint4*>(rows + B.rbase + row);
-        const uint4 r0 = rp[0], r1 = rp[1];
-        orow = out + (((long long)r0.w << 32) | (long long)r0.z);
-        dx = __uint_as_float(r1.x);
-        dy = __uint_as_float(r1.y);
-        ox = (int)r1.z;
-        oy = (int)r1.w;
-      }
-      mbar_wait(&tfull_bar[g], (it >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      float hprev[7];
-#pragma unroll
-      for (int i = 0; i < 7; i++) hprev[i] = 0.f;
-#pragma unroll 1
-      for (int wy2 = 0; wy2 < kTcTile; wy2 += 2) {
-        float v[32];
-        tmem_ld32(tlane + wy2 * kTcTile, v);              // two tile rows per TMEM load
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-          const int a = wy2 + hh - oy;
-          if (a >= 0 && a <= 7) {
-#pragma unroll
-            for (int i = 0; i < 16; i++) S1[i] = v[hh * 16 + i];
-            float c[8], h[7];
-#pragma unroll
-            for (int i = 0; i < 8; i++) c[i] = S1[ox + i];
-#pragma unroll
-            for (int i = 0; i < 7; i++) h[i] = c[i] + dx * (c[i + 1] - c[i]);
-            if (a >= 1) {
-              float o[7];
-#pragma unroll
-              for (int i = 0; i < 7; i++) o[i] = hprev[i] + dy * (h[i] - hprev[i]);
-              const __half2 p0 = __floats2half2_rn(o[0], o[1]), p1 = __floats2half2_rn(o[2], o[3]);
-              const __half2 p2 = __floats2half2_rn(o[4], o[5]), p3 = __floats2half2_rn(o[6], 0.f);
-              uint4 u;
-              u.x = *reinterpret_cast<const uint32_t*>(&p0);
-              u.y = *reinterpret_cast<const uint32_t*>(&p1);
-              u.z = *reinterpret_cast<const uint32_t*>(&p2);
-              u.w = *reinterpret_cast<const uint32_t*>(&p3);
-              *reinterpret_cast<uint4*>(orow + (a - 1) * 8) = u;  // one aligned 16-byte store per (row, a)
-            }
-#pragma unroll
-            for (int i = 0; i < 7; i++) hprev[i] = h[i];
-          }
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-      mbar_arrive(&tempty_bar[g]);
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-  __syncthreads();
-  if (warp == kPipeMmaWarp) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
-  }
-}
-
 // ------------------------------------------------------------------ TMA variant ----
 //
-// corr_tile_tma_kernel: the same block list, restructured around the memory system —
+// corr_tile_tma_kernel: the same block list, restructured around what bounds it.  Measured on B200:
+// a tcgen05.mma M128 N256 K16 with both operands in shared memory takes ~200 cycles (operand fetch,
+// ~60 B/clk), so a block costs ~1600 tensor cycles and its 64 KB tile ~40 B/clk/SM of L2 bandwidth;
+// everything else has to hide behind those two.
 //   B tiles   one thread issues two cp.async.bulk.tensor (TMA) box loads per tile: the 4-D tensor map
 //             over the channels-last frame ring {C, W, H, N} with box {64, 16, 16, 1} and
 //             SWIZZLE_128B lands exactly in the UMMA canonical layout, and out-of-map positions
@@ -561,22 +402,28 @@ corr_tile_pipe_kernel(TcGeom G, const __half* __restrict__ gmap, const TcHdr* __
 //             ONCE for all consecutive row blocks that share it (level 2 has ~5 blocks per tile);
 //   chunks    a CTA takes chunks of kChunk consecutive blocks (so tile sharing survives the
 //             persistent schedule) strided by the grid;
-//   A rows    4 producer warps gather the 128 patch-pixel vectors with cp.async, two blocks in
-//             flight (completion of block b is published after block b+1 has been issued);
-//   MMA       as before, 8 x tcgen05.mma M128 N256 K16 per block into one of two TMEM accumulators;
-//   epilogue  2 x 4 warps; warps whose 32 rows are all past nrows skip the drain, the window-row
-//             staging uses 16-byte shared-memory stores.
+//   A rows    two producer groups (4 warps each, alternate blocks) gather the 128 patch-pixel
+//             vectors with cp.async into a 3-stage ring: the gather of block i starts when the MMAs
+//             of block i - 3 have retired;
+//   rows      row r of a block sits in TMEM lane r; odd blocks are rotated by 64 lanes so that the
+//             half-empty level-1 blocks keep all four schedulers busy;
+//   MMA       8 x tcgen05.mma M128 N256 K16 per block into one of two TMEM accumulators;
+//   epilogue  2 accumulators x 4 lane quadrants = 8 warps.  Rows of a tile are sorted by window-origin
+//             row, so a warp reads only the accumulator rows its windows cover, two rows per tcgen05.ld.
+//             The body is one branch-free basic block (only the 16-byte stores are predicated): the
+//             per-thread x offset is applied by 19 selects for its high bits and a 5-tap blend for the
+//             low bits — the half-rate ALU pipe (FSEL) is what bounds the epilogue, so work is moved to
+//             the FMA pipe — followed by the vertical blend and the fp16 pack.
 constexpr int kChunkLog2 = 3;
 constexpr int kChunk = 1 << kChunkLog2;
 constexpr int kTmaThreads = 640;              // warps 0-7 A producers, 8 TMA, 9 MMA, 12-19 epilogue
 constexpr int kTmaTmaWarp = 8;
 constexpr int kTmaMmaWarp = 9;
 constexpr int kTmaEpiWarp0 = 12;
+constexpr int kTmaAStages = 3;
 constexpr int kTmaOffB = 0;                   // 2 x 64 KB
-constexpr int kTmaOffA = 2 * kTcSmemB;        // 2 x 32 KB
-constexpr int kTmaOffS = kTmaOffA + 2 * kTcSmemA;
-constexpr int kStageV = 20;                   // floats per thread of the window-row stage (16 + pad, 16-B aligned)
-constexpr int kTmaSmemBytes = kTmaOffS + 256 * kStageV * 4 + 1024;
+constexpr int kTmaOffA = 2 * kTcSmemB;        // 3 x 32 KB
+constexpr int kTmaSmemBytes = kTmaOffA + kTmaAStages * kTcSmemA + 1024;
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes)
@@ -601,15 +448,66 @@ __device__ __forceinline__ int tma_block(int i) {
   return ((int)blockIdx.x + (i >> kChunkLog2) * (int)gridDim.x) * kChunk + (i & (kChunk - 1));
 }
 
+// row of a block that lives in TMEM lane (quadrant q, lane l): row r sits in lane r (fewest partially
+// filled warps — the epilogue is instruction-bound); odd blocks of a CTA's schedule (rot = 1) are rotated
+// by 64 lanes, so that the half-empty level-1 blocks load the four schedulers evenly (lane quadrant ==
+// scheduler: even blocks fill quadrants 0,1 first, odd blocks 2,3).
+__device__ __forceinline__ int tma_row_of(int q, int l, int nrows, int rot) {
+  const int r = (q * 32 + l + 64 * rot) & 127;
+  return r < nrows ? r : -1;
+}
+
+// h[k] = lerp_x(v[ox + k], v[ox + k + 1]), k = 0..6, for a per-thread window offset ox = 0..8.
+// The epilogue is bound by the half-rate ALU pipe (FSEL), so only bits 8 and 4 of ox go through
+// selects (19 FSEL); the low two bits are folded into the horizontal blend as a 5-tap filter with
+// per-thread weights w[j] = (j == s)(1 - dx) + (j == s + 1) dx, s = ox & 3 — 35 FMUL/FFMA on the FMA pipe
+// instead of 17 FSEL + 14 FADD/FFMA.  Zero taps contribute exact zeros.
+__device__ __forceinline__ void epi_hrow(const float* v, bool p8, bool p4, const float (&w)[5], float (&h)[7]) {
+  float t0[15], t1[11];
+#pragma unroll
+  for (int k = 0; k < 8; k++) t0[k] = p8 ? v[k + 8] : v[k];
+#pragma unroll
+  for (int k = 8; k < 15; k++) t0[k] = v[k];
+#pragma unroll
+  for (int k = 0; k < 11; k++) t1[k] = p4 ? t0[k + 4] : t0[k];
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    float acc = w[0] * t1[k];
+    acc = fmaf(w[1], t1[k + 1], acc);
+    acc = fmaf(w[2], t1[k + 2], acc);
+    acc = fmaf(w[3], t1[k + 3], acc);
+    h[k] = fmaf(w[4], t1[k + 4], acc);
+  }
+}
+
+// o = lerp_y(h0, h1) rounded to fp16: 7 values + zero pad = one aligned 16-byte vector
+__device__ __forceinline__ uint4 epi_pack(const float (&h0)[7], const float (&h1)[7], float dy) {
+  float o[7];
+#pragma unroll
+  for (int k = 0; k < 7; k++) o[k] = h0[k] + dy * (h1[k] - h0[k]);
+  const __half2 q0 = __floats2half2_rn(o[0], o[1]), q1 = __floats2half2_rn(o[2], o[3]);
+  const __half2 q2 = __floats2half2_rn(o[4], o[5]), q3 = __floats2half2_rn(o[6], 0.f);
+  uint4 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&q0);
+  u.y = *reinterpret_cast<const uint32_t*>(&q1);
+  u.z = *reinterpret_cast<const uint32_t*>(&q2);
+  u.w = *reinterpret_cast<const uint32_t*>(&q3);
+  return u;
+}
+
+// debugging aid (RVO_CORR_DBG & 16): per-block clock64 stamps of CTA 0, read back with rvo_corr_trace
+__device__ long long g_tc_trace[8 * 256];
+#define TC_TRACE(slot, i) do { if ((dbg & 16) && blockIdx.x == 0 && (i) < 256) g_tc_trace[(slot) * 256 + (i)] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(kTmaThreads, 1)
 corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__ TcTmap tm1,
                      const __half* __restrict__ gmap, const TcHdr* __restrict__ hdr,
                      const TcRow* __restrict__ rows, const int32_t* __restrict__ total_blocks,
-                     __half* __restrict__ out) {
+                     __half* __restrict__ out, int dbg) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bfull[2], bempty[2], afull[2], aempty[2], tfull[2], tempty[2];
+  __shared__ uint64_t bfull[2], bempty[2], afull[kTmaAStages], aempty[kTmaAStages], tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ long long rowsrc[2][kTcRows];
+  __shared__ int rowsrc[2][kTcRows];            // per producer group: gmap element offsets (< 2^31, host-checked)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nblk = total_blocks[0];
@@ -618,10 +516,12 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
     for (int s = 0; s < 2; s++) {
       mbar_init(&bfull[s], 1);
       mbar_init(&bempty[s], 1);
-      mbar_init(&afull[s], 128);
-      mbar_init(&aempty[s], 1);
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], 128);
+    }
+    for (int s = 0; s < kTmaAStages; s++) {
+      mbar_init(&afull[s], 128);
+      mbar_init(&aempty[s], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -637,39 +537,58 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp < 8) {
-    // ===== A producers: group pg (4 warps) fills stage pg for blocks i == pg (mod 2); the two groups
-    // run concurrently so one block's gather is in flight while the other is published.  Thread owns
-    // 16-byte chunk `ch` of rows q0 + 8 j =====
+    // ===== A producers: group pg takes blocks i == pg (mod 2), stage i % 3.  Thread owns 16-byte chunk
+    // `ch` of the M slots q0 + 8 j; headers run two own-blocks ahead and the row sources one ahead of
+    // the gather, so neither L2 round trip sits on the per-block critical path =====
     const int pg = warp >> 2, ptid = tid & 127;
     const int ch = ptid & 15, q0 = ptid >> 4;
     const uint32_t swz = (uint32_t)(((ch & 7) ^ q0) << 4);
     const uint32_t kboff_a = (ch >> 3) * (kTcRows * 128);
     const __half* gsrc = gmap + ch * 8;
-    const uint32_t dst0 = smem_u32(smem + kTmaOffA + pg * kTcSmemA) + kboff_a + swz + q0 * 128;
-    TcHdr Hn;
-    if (tma_block(pg) < nblk) Hn = ld_hdr(hdr, tma_block(pg));
+    const uint32_t dst0 = smem_u32(smem + kTmaOffA) + kboff_a + swz + q0 * 128;
+    const int my_q = ptid >> 5, my_l = ptid & 31;             // the M slot whose source this thread fetches
+    TcHdr H1, H2;
+    int src_n = -1;
+    if (tma_block(pg) < nblk) {
+      H1 = ld_hdr(hdr, tma_block(pg));
+      const int r = tma_row_of(my_q, my_l, H1.nrows, pg);
+      if (r >= 0) src_n = (int)rows[H1.rbase + r].src;
+    }
+    if (tma_block(pg + 2) < nblk) H1 = ld_hdr(hdr, tma_block(pg + 2));
     for (int i = pg;; i += 2) {
       const int b = tma_block(i);
       if (b >= nblk) break;
-      const TcHdr B = Hn;
-      if (tma_block(i + 2) < nblk) Hn = ld_hdr(hdr, tma_block(i + 2));
-      const long long my_src = (ptid < B.nrows) ? rows[B.rbase + ptid].src : -1;
-      mbar_wait(&aempty[pg], ((i >> 1) & 1) ^ 1);
+      const int my_src = src_n;
+      src_n = -1;
+      if (tma_block(i + 4) < nblk) H2 = ld_hdr(hdr, tma_block(i + 4));
+      if (tma_block(i + 2) < nblk) {
+        const int r = tma_row_of(my_q, my_l, H1.nrows, pg);
+        if (r >= 0) src_n = (int)rows[H1.rbase + r].src;
+      }
+      H1 = H2;
+      const int s = i % kTmaAStages, ph = (i / kTmaAStages) & 1;
+      mbar_wait(&aempty[s], ph ^ 1);
+      if (ptid == 0) TC_TRACE(0, i);
       rowsrc[pg][ptid] = my_src;
       if (pg == 0) asm volatile("bar.sync 1, 128;\n" ::: "memory");
       else asm volatile("bar.sync 2, 128;\n" ::: "memory");
-      uint32_t dst = dst0;
-      const long long* rs = rowsrc[pg] + q0;
+      uint32_t dst = dst0 + s * kTcSmemA;
+      const int* rs = rowsrc[pg] + q0;
 #pragma unroll 4
       for (int j = 0; j < 16; j++, dst += 8 * 128) {
-        const long long off = rs[8 * j];
+        const int off = rs[8 * j];
         const bool ok = off >= 0;
-        cp_async16(dst, gsrc + (ok ? off : 0), ok ? 16u : 0u);
+        if (!(dbg & 4)) cp_async16(dst, gsrc + (ok ? off : 0), ok ? 16u : 0u);
       }
       asm volatile("cp.async.commit_group;\n" ::: "memory");
       asm volatile("cp.async.wait_group 0;\n" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> async proxy
-      mbar_arrive(&afull[pg]);
+      mbar_arrive(&afull[s]);
+      if (ptid == 0) TC_TRACE(1, i);
+      // the group's next write of rowsrc[pg] comes after its next bar.sync partner has read this one:
+      // every thread passes the loop above before any thread can pass the next iteration's barrier
+      if (pg == 0) asm volatile("bar.sync 3, 128;\n" ::: "memory");
+      else asm volatile("bar.sync 4, 128;\n" ::: "memory");
     }
   } else if (warp == kTmaTmaWarp) {
     // ===== TMA producer: one thread, one tile load per run of blocks that share the tile =====
@@ -688,9 +607,13 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
         mbar_wait(&bempty[s], ((ib >> 1) & 1) ^ 1);
         const void* tm = B.lvl ? (const void*)&tm1 : (const void*)&tm0;
         const uint32_t Bs_u = smem_u32(smem + kTmaOffB + s * kTcSmemB);
-        mbar_expect_tx(&bfull[s], (uint32_t)kTcSmemB);
-        tma_load_4d(Bs_u, tm, 0, B.X0, B.Y0, B.f, &bfull[s]);
-        tma_load_4d(Bs_u + 256 * 128, tm, 64, B.X0, B.Y0, B.f, &bfull[s]);
+        if (dbg & 8) {
+          mbar_arrive(&bfull[s]);
+        } else {
+          mbar_expect_tx(&bfull[s], (uint32_t)kTcSmemB);
+          tma_load_4d(Bs_u, tm, 0, B.X0, B.Y0, B.f, &bfull[s]);
+          tma_load_4d(Bs_u + 256 * 128, tm, 64, B.X0, B.Y0, B.f, &bfull[s]);
+        }
         ib++;
       }
     }
@@ -699,6 +622,7 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
     int ib = -1;
     TcHdr Hn;
     if (tma_block(0) < nblk) Hn = ld_hdr(hdr, tma_block(0));
+    int sa = 0, pa = 0;
     for (int i = 0;; i++) {
       const int b = tma_block(i);
       if (b >= nblk) break;
@@ -706,100 +630,112 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
       if (tma_block(i + 1) < nblk) Hn = ld_hdr(hdr, tma_block(i + 1));
       const bool newB = (i & (kChunk - 1)) == 0 || !(B.flags & 1);
       const bool lastB = (i & (kChunk - 1)) == kChunk - 1 || !(B.flags & 2);
+      if (lane == 0) TC_TRACE(2, i);
       if (newB) {
         ib++;
-        mbar_wait(&bfull[ib & 1], (ib >> 1) & 1);
+        mbar_wait_spin(&bfull[ib & 1], (ib >> 1) & 1);
       }
-      const int s = i & 1, sb = ib & 1;
-      mbar_wait(&afull[s], (i >> 1) & 1);
-      mbar_wait(&tempty[s], ((i >> 1) & 1) ^ 1);
+      const int st = i & 1, sb = ib & 1;
+      mbar_wait_spin(&afull[sa], pa);
+      mbar_wait_spin(&tempty[st], ((i >> 1) & 1) ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      if (lane == 0) TC_TRACE(3, i);
       if (lane == 0) {
-        const uint32_t As_u = smem_u32(smem + kTmaOffA + s * kTcSmemA);
+        const uint32_t As_u = smem_u32(smem + kTmaOffA + sa * kTcSmemA);
         const uint32_t Bs_u = smem_u32(smem + kTmaOffB + sb * kTcSmemB);
+        // one descriptor per stage, advanced by constants (the address field counts 16-byte units and
+        // cannot carry out of its 14 bits below 256 KB): the issuing thread is the critical path
+        const uint64_t da0 = umma_desc(As_u), db0 = umma_desc(Bs_u);
 #pragma unroll
         for (int kb = 0; kb < 2; kb++)
 #pragma unroll
           for (int k = 0; k < 4; k++)
-            umma_f16(tmem_base + s * 256, umma_desc(As_u + kb * (kTcRows * 128) + k * 32),
-                     umma_desc(Bs_u + kb * (256 * 128) + k * 32), (kb | k) ? 1u : 0u);
-        umma_commit(&aempty[s]);
-        umma_commit(&tfull[s]);
+            umma_f16(tmem_base + st * 256, da0 + (uint64_t)((kb * (kTcRows * 128) + k * 32) >> 4),
+                     db0 + (uint64_t)((kb * (256 * 128) + k * 32) >> 4), (kb | k) ? 1u : 0u);
+        umma_commit(&aempty[sa]);
+        umma_commit(&tfull[st]);
         if (lastB) umma_commit(&bempty[sb]);
+        TC_TRACE(4, i);
       }
       __syncwarp();
+      if (++sa == kTmaAStages) { sa = 0; pa ^= 1; }
     }
   } else if (warp >= kTmaEpiWarp0) {
-    // ===== epilogue: group g (4 warps) drains TMEM accumulator g, i.e. blocks i == g (mod 2) =====
-    const int g = (warp - kTmaEpiWarp0) >> 2;
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    float* S1 = reinterpret_cast<float*>(smem + kTmaOffS) + (g * 128 + row) * kStageV;
+    // ===== epilogue: accumulator g, TMEM lane quadrant q; this group's blocks are i = g, g + 2, ... =====
+    const int ew = warp - kTmaEpiWarp0;
+    const int g = ew >> 2, q = warp & 3;
+    // window rows a_first .. a_last of every live row are this warp's: it stores output rows a_first .. a_last - 1
+    // (measured: splitting them over two warps per quadrant does not pay, both land on the same scheduler)
+    constexpr int a_first = 0, a_last = 7;
     const uint32_t tlane = tmem_base + g * 256 + ((uint32_t)(q * 32) << 16);
-    TcHdr Hn;
-    if (tma_block(g) < nblk) Hn = ld_hdr(hdr, tma_block(g));
+    TcHdr B, H1, H2;                                          // headers of blocks i, i + 2, i + 4
+    uint4 r0n = make_uint4(0, 0, 0, 0), r1n = make_uint4(0, 0, 0, 0);
+    if (tma_block(g) < nblk) {
+      B = ld_hdr(hdr, tma_block(g));
+      const int r = tma_row_of(q, lane, B.nrows, g);
+      if (r >= 0) {
+        const uint4* rp = reinterpret_cast<const uint4*>(rows + B.rbase + r);
+        r0n = rp[0]; r1n = rp[1];
+      }
+    }
+    if (tma_block(g + 2) < nblk) H1 = ld_hdr(hdr, tma_block(g + 2));
     for (int i = g;; i += 2) {
       const int b = tma_block(i);
       if (b >= nblk) break;
-      const TcHdr B = Hn;
-      if (tma_block(i + 2) < nblk) Hn = ld_hdr(hdr, tma_block(i + 2));
-      int ox = 0, oy = 1 << 20;
-      float dx = 0.f, dy = 0.f;
-      __half* orow = out;
-      if (row < B.nrows) {
-        const uint4* rp = reinterpret_cast<const uint4*>(rows + B.rbase + row);
-        const uint4 r0 = rp[0], r1 = rp[1];
-        orow = out + (((long long)r0.w << 32) | (long long)r0.z);
-        dx = __uint_as_float(r1.x);
-        dy = __uint_as_float(r1.y);
-        ox = (int)r1.z;
-        oy = (int)r1.w;
+      const uint4 r0 = r0n, r1 = r1n;
+      if (tma_block(i + 4) < nblk) H2 = ld_hdr(hdr, tma_block(i + 4));
+      if (tma_block(i + 2) < nblk) {                         // next own block's row record in flight
+        const int r = tma_row_of(q, lane, H1.nrows, g);
+        if (r >= 0) {
+          const uint4* rp = reinterpret_cast<const uint4*>(rows + H1.rbase + r);
+          r0n = rp[0]; r1n = rp[1];
+        }
       }
+      const bool live = tma_row_of(q, lane, B.nrows, g) >= 0;
+      __half* orow = out + (((long long)r0.w << 32) | (long long)r0.z);
+      const float dx = __uint_as_float(r1.x), dy = __uint_as_float(r1.y);
+      const int ox = (int)r1.z;
+      const int oy = live ? (int)r1.w : (1 << 20);           // dead rows never match an accumulator row
+      const bool p8 = (ox & 8) != 0, p4 = (ox & 4) != 0;
+      float w[5];
+      {
+        const int sx = ox & 3;
+#pragma unroll
+        for (int j = 0; j < 5; j++) w[j] = (j == sx ? 1.0f - dx : 0.0f) + (j == sx + 1 ? dx : 0.0f);
+      }
+      // warp-uniform range of accumulator rows (tcgen05.ld is warp-collective)
+      const int lo = __reduce_min_sync(0xffffffffu, live ? oy : 64);
+      const int hi = __reduce_max_sync(0xffffffffu, live ? oy : -1);
       mbar_wait(&tfull[g], (i >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      if (q * 32 < B.nrows) {                               // warp-uniform: this warp owns live rows
+      if (q == 0 && lane == 0) TC_TRACE(5, i);
+      if (hi >= 0 && !(dbg & 2)) {
         float hprev[7];
 #pragma unroll
         for (int k = 0; k < 7; k++) hprev[k] = 0.f;
 #pragma unroll 1
-        for (int wy2 = 0; wy2 < kTcTile; wy2 += 2) {
+        for (int wy = (lo + a_first) & ~1; wy <= hi + a_last; wy += 2) {   // accumulator rows wy, wy + 1
           float v[32];
-          tmem_ld32(tlane + wy2 * kTcTile, v);
+          tmem_ld32(tlane + wy * kTcTile, v);
+          if (dbg & 1) continue;
+          // one basic block for both rows (values are computed unconditionally, only the stores are
+          // predicated), so the selects (ALU), blends (FMA) and conversions of independent rows interleave
+          float hA[7], hB[7];
+          epi_hrow(v, p8, p4, w, hA);
+          epi_hrow(v + 16, p8, p4, w, hB);
+          const uint4 uA = epi_pack(hprev, hA, dy), uB = epi_pack(hA, hB, dy);
+          const int a = wy - oy;                             // window row of accumulator row wy
+          if (a > a_first && a <= a_last) *reinterpret_cast<uint4*>(orow + (a - 1) * 8) = uA;
+          if (a >= a_first && a < a_last) *reinterpret_cast<uint4*>(orow + a * 8) = uB;
 #pragma unroll
-          for (int hh = 0; hh < 2; hh++) {
-            const int a = wy2 + hh - oy;
-            if (a >= 0 && a <= 7) {
-#pragma unroll
-              for (int k = 0; k < 4; k++)
-                *reinterpret_cast<float4*>(S1 + 4 * k) =
-                    make_float4(v[hh * 16 + 4 * k], v[hh * 16 + 4 * k + 1], v[hh * 16 + 4 * k + 2],
-                                v[hh * 16 + 4 * k + 3]);
-              float c[8], h[7];
-#pragma unroll
-              for (int k = 0; k < 8; k++) c[k] = S1[ox + k];
-#pragma unroll
-              for (int k = 0; k < 7; k++) h[k] = c[k] + dx * (c[k + 1] - c[k]);
-              if (a >= 1) {
-                float o[7];
-#pragma unroll
-                for (int k = 0; k < 7; k++) o[k] = hprev[k] + dy * (h[k] - hprev[k]);
-                const __half2 p0 = __floats2half2_rn(o[0], o[1]), p1 = __floats2half2_rn(o[2], o[3]);
-                const __half2 p2 = __floats2half2_rn(o[4], o[5]), p3 = __floats2half2_rn(o[6], 0.f);
-                uint4 u;
-                u.x = *reinterpret_cast<const uint32_t*>(&p0);
-                u.y = *reinterpret_cast<const uint32_t*>(&p1);
-                u.z = *reinterpret_cast<const uint32_t*>(&p2);
-                u.w = *reinterpret_cast<const uint32_t*>(&p3);
-                *reinterpret_cast<uint4*>(orow + (a - 1) * 8) = u;
-              }
-#pragma unroll
-              for (int k = 0; k < 7; k++) hprev[k] = h[k];
-            }
-          }
+          for (int k = 0; k < 7; k++) hprev[k] = hB[k];
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      if (q == 0 && lane == 0) TC_TRACE(6, i);
       mbar_arrive(&tempty[g]);
+      B = H1;
+      H1 = H2;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -812,7 +748,7 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
 // ------------------------------------------------------------------ host ----
 
 struct TcWs {
-  int32_t *cnt, *rowstart, *blkstart, *total, *rowbin, *rowrank;
+  int32_t *cnt, *tot, *rowstart, *blkstart, *total, *rowbin, *rowrank;
   TcRow* rows;
   TcHdr* hdr;
   size_t total_bytes;
@@ -827,7 +763,8 @@ static TcWs tc_layout(void* base, int64_t R, int nbins) {
   size_t off = 0;
   auto take = [&](size_t bytes) { char* r = c + off; off += al256(bytes ? bytes : 4); return r; };
   w.maxblocks = R / kTcRows + nbins + 1;
-  w.cnt = (int32_t*)take((size_t)nbins * 4);
+  w.cnt = (int32_t*)take((size_t)nbins * kTcSub * 4);   // cnt and tot are adjacent: one memset
+  w.tot = (int32_t*)take((size_t)nbins * 4);
   w.rowstart = (int32_t*)take((size_t)(nbins + 1) * 4);
   w.blkstart = (int32_t*)take((size_t)(nbins + 1) * 4);
   w.total = (int32_t*)take(16);
@@ -910,6 +847,12 @@ static int tc_make_tmap(const TcLevel& L, TcTmap* out) {
 
 using namespace rvo;
 
+extern "C" int rvo_corr_trace(long long* host_out) {
+  RVO_CUDA(cudaDeviceSynchronize());
+  RVO_CUDA(cudaMemcpyFromSymbol(host_out, g_tc_trace, sizeof(long long) * 8 * 256));
+  return RVO_OK;
+}
+
 extern "C" int64_t rvo_corr_tiles_ws_bytes(const rvo_fmap_t* pyr, int nlevels, int E) {
   TcGeom G;
   if (E < 0 || tc_geom(pyr, nullptr, nlevels, &G, "rvo_corr_tiles_ws_bytes") != RVO_OK) return -1;
@@ -938,30 +881,25 @@ extern "C" int rvo_corr_tiles(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, co
   RVO_CHECK_ARG((int64_t)w.total_bytes <= ws_bytes, "rvo_corr_tiles: workspace %lld < %lld bytes",
                 (long long)ws_bytes, (long long)w.total_bytes);
   cudaStream_t st = (cudaStream_t)stream;
-  RVO_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)G.nbins * 4, st));
+  RVO_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)((char*)w.tot - (char*)w.cnt) + (size_t)G.nbins * 4, st));   // cnt + tot
   RVO_CHECK_ARG(G.nbins <= kScanMaxBins, "rvo_corr_tiles: %d tiles exceed the scan capacity", G.nbins);
   int grid = (int)((R + 255) / 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
-  tc_bin_count_kernel<<<(int)(((int64_t)E * nlevels + 255) / 256), 256, 0, st>>>(G, coords, kk, jj, pmod, fmod, fmap1->N, E, w.cnt, w.rowbin,
-                                            w.rowrank, (__half*)out, out_ld);
+  tc_bin_count_kernel<<<(int)(((int64_t)E * nlevels + 255) / 256), 256, 0, st>>>(G, coords, kk, jj, pmod, fmod, fmap1->N, E,
+                                                                                  w.cnt, w.tot, w.rowbin, w.rowrank,
+                                                                                  (__half*)out, out_ld);
   RVO_LAUNCH_CHECK("tc_bin_count_kernel");
   RVO_CUDA(cudaFuncSetAttribute(tc_bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                kScanMaxBins * 4));
-  tc_bin_scan_kernel<<<1, 1024, (size_t)G.nbins * 4, st>>>(w.cnt, G.nbins, w.rowstart, w.blkstart, w.total);
+                                kScanMaxBins * 6 + 4096));
+  tc_bin_scan_kernel<<<1, 1024, (size_t)G.nbins * 6 + 4096, st>>>(w.tot, G.nbins, w.rowstart, w.blkstart, w.total);
   RVO_LAUNCH_CHECK("tc_bin_scan_kernel");
-  tc_block_hdr_kernel<<<(G.nbins + 255) / 256, 256, 0, st>>>(G, w.cnt, w.rowstart, w.blkstart, w.hdr);
-  RVO_LAUNCH_CHECK("tc_block_hdr_kernel");
-  tc_bin_scatter_kernel<<<grid, 256, 0, st>>>(G, coords, kk, pmod, fmap1->sN, fmap1->sH, fmap1->sW, out_ld, R,
-                                              w.rowbin, w.rowrank, w.rowstart, w.rows);
+  tc_bin_scatter_kernel<<<grid, 256, 0, st>>>(G, coords, kk, jj, pmod, fmod, fmap1->sN, fmap1->sH, fmap1->sW,
+                                              out_ld, R, w.rowbin, w.rowrank, w.rowstart, w.blkstart, w.cnt, w.tot, w.rows,
+                                              w.hdr);
   RVO_LAUNCH_CHECK("tc_bin_scatter_kernel");
-  static const bool legacy = getenv("RVO_CORR_LEGACY") != nullptr;   // debugging aid: the cp.async-only kernel
-  if (legacy) {
-    RVO_CUDA(cudaFuncSetAttribute(corr_tile_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmemBytes));
-    corr_tile_pipe_kernel<<<kNumSMs, kPipeThreads, kPipeSmemBytes, st>>>(G, (const __half*)fmap1->data, w.hdr,
-                                                                         w.rows, w.total, (__half*)out);
-    RVO_LAUNCH_CHECK("corr_tile_pipe_kernel");
-    return RVO_OK;
-  }
+  const char* dbg_s = getenv("RVO_CORR_DBG");      // debugging aid: see the kernel's dbg bits
+  const int dbg = dbg_s ? atoi(dbg_s) : 0;
+  RVO_CHECK_ARG((int64_t)fmap1->N * fmap1->sN < 0x7fffffff, "rvo_corr_tiles: fmap1 too large for 32-bit offsets");
   TcTmap tm[kTcMaxLevels];
   for (int l = 0; l < kTcMaxLevels; l++) {
     rc = tc_make_tmap(G.lv[l], &tm[l]);
@@ -969,7 +907,7 @@ extern "C" int rvo_corr_tiles(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, co
   }
   RVO_CUDA(cudaFuncSetAttribute(corr_tile_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
   corr_tile_tma_kernel<<<kNumSMs, kTmaThreads, kTmaSmemBytes, st>>>(tm[0], tm[1], (const __half*)fmap1->data,
-                                                                    w.hdr, w.rows, w.total, (__half*)out);
+                                                                    w.hdr, w.rows, w.total, (__half*)out, dbg);
   RVO_LAUNCH_CHECK("corr_tile_tma_kernel");
   return RVO_OK;
 }
