@@ -320,6 +320,15 @@ int rvo_expand_add(const void* hy, int dtype, const void* plan, int E, int C, fl
 int rvo_gather_rows(const float* src, const int64_t* idx, int E, int C, void* out, int out_dtype,
                     void* stream);
 
+/* nn.Linear (+ nn.ReLU) of the update operator (ramp/net.py:36-67: c1, c2, corr[2], corr[5], gru gates /
+ * residual MLPs; ramp/blocks.py:36-38: SoftAgg f, g, h) as ONE hand-written tcgen05 GEMM:
+ *   y16[M, N] = act(x16[M, K] * w16[N, K]^T + bias16[N]),  fp16 operands, fp32 accumulation (TMEM), fp16 out
+ * (torch.nn.functional.linear under autocast).  K must be 384 (the update operator's width: the weight slice
+ * stays resident in shared memory), N a multiple of 192 (384 or 768 on the hot path); ldx / ldy = row pitches
+ * in elements (multiples of 8, 16-byte aligned bases); bias16 may be NULL; relu != 0 applies max(., 0). */
+int rvo_up_linear(const void* x16, int64_t ldx, const void* w16, const void* bias16, int M, int K, int N,
+                  int relu, void* y16, int64_t ldy, void* stream);
+
 /* Fused row kernels of the mixed-precision update operator (C = 384; fp16 GEMM operands, fp32
  * hidden state and LayerNorm, eps 1e-3 — the dtypes Update.forward has under autocast,
  * ramp/Ramp_vo.py:280, SURVEY.md appendix "dtype drift").  Each replaces 3-8 elementwise / cast /

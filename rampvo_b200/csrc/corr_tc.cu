@@ -26,6 +26,7 @@
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace rvo {
 
@@ -103,10 +104,11 @@ tc_bin_count_kernel(TcGeom G, const float* __restrict__ coords, const int64_t* _
                      : -1;
     }
     int ranks[9];
+#pragma unroll
+    for (int pix = 0; pix < 9; pix++) ranks[pix] = -1;
     unsigned done = 0, tdone = 0;
 #pragma unroll
     for (int pix = 0; pix < 9; pix++) {
-      ranks[pix] = -1;
       if (subs[pix] < 0 || ((done >> pix) & 1u)) continue;
       int n = 0;
 #pragma unroll
@@ -268,100 +270,10 @@ tc_bin_scatter_kernel(TcGeom G, const float* __restrict__ coords, const int64_t*
 
 // ------------------------------------------------------------------ tcgen05 helpers ----
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-  uint64_t d = (uint64_t)((smem_addr >> 4) & 0x3FFFu);   // start address, 16-byte units
-  d |= (uint64_t)(1024u >> 4) << 32;                      // stride byte offset (8 rows)
-  d |= (uint64_t)1 << 46;                                 // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                                 // SWIZZLE_128B
-  return d;
-}
-
-// kind::f16, A/B = fp16 K-major, D = fp32, M = 128, N = 256
-constexpr uint32_t kIdesc = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
-      : "memory");
-}
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes)
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-        "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
-}
-
 constexpr int kTcSmemA = 2 * kTcRows * 128;            // two K blocks of [128 rows x 128 B] = 32 KB
 constexpr int kTcSmemB = 2 * 256 * 128;                // two K blocks of [256 rows x 128 B] = 64 KB
 
 // ------------------------------------------------------------------ mbarrier / TMEM helpers ----
-
-__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
-}
-// Waiting warps share issue slots with the warps that do the work: try_wait suspends the thread in
-// hardware until the phase completes or the time hint (ns) expires, so a long wait costs a handful of
-// instructions instead of a polling loop (ncu: the nanosleep loop was 25 % of all issued instructions).
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-  const uint32_t addr = smem_u32(b);
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "MBW_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra MBW_DONE;\n\t"
-      "bra MBW_LOOP;\n\t"
-      "MBW_DONE:\n\t"
-      "}\n" ::"r"(addr),
-      "r"(parity), "r"(20000u)
-      : "memory");
-}
-// latency-critical single-warp wait (the MMA issuer): try_wait suspends in hardware, no extra sleep
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* b, uint32_t parity) {
-  const uint32_t addr = smem_u32(b);
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}\n" ::"r"(addr),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* b) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
-                   smem_u32(b))
-               : "memory");
-}
 
 __device__ __forceinline__ TcHdr ld_hdr(const TcHdr* __restrict__ hdr, int b) {
   const uint4* p = reinterpret_cast<const uint4*>(hdr + b);
@@ -370,23 +282,6 @@ __device__ __forceinline__ TcHdr ld_hdr(const TcHdr* __restrict__ hdr, int b) {
   h.nrows = (int)a.x; h.rbase = (int)a.y; h.lvl = (int)a.z; h.f = (int)a.w;
   h.X0 = (int)c.x; h.Y0 = (int)c.y; h.flags = (int)c.z; h.pad1 = 0;
   return h;
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
 // ------------------------------------------------------------------ TMA variant ----
@@ -424,24 +319,6 @@ constexpr int kTmaAStages = 3;
 constexpr int kTmaOffB = 0;                   // 2 x 64 KB
 constexpr int kTmaOffA = 2 * kTcSmemB;        // 3 x 32 KB
 constexpr int kTmaSmemBytes = kTmaOffA + kTmaAStages * kTcSmemA + 1024;
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes)
-               : "memory");
-}
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
-      "%5, %6}], [%2];\n" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-
-struct __align__(64) TcTmap {
-  unsigned char bytes[128];                   // CUtensorMap
-};
 
 // block index of the i-th block of this CTA's schedule
 __device__ __forceinline__ int tma_block(int i) {
@@ -651,7 +528,7 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < 4; k++)
             umma_f16(tmem_base + st * 256, da0 + (uint64_t)((kb * (kTcRows * 128) + k * 32) >> 4),
-                     db0 + (uint64_t)((kb * (256 * 128) + k * 32) >> 4), (kb | k) ? 1u : 0u);
+                     db0 + (uint64_t)((kb * (256 * 128) + k * 32) >> 4), umma_idesc_f16(128, 256), (kb | k) ? 1u : 0u);
         umma_commit(&aempty[sa]);
         umma_commit(&tfull[st]);
         if (lastB) umma_commit(&bempty[sb]);
@@ -806,24 +683,6 @@ static int tc_geom(const rvo_fmap_t* pyr, const float* scale, int nlevels, TcGeo
 
 
 namespace rvo {
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
 
 // 4-D map over a channels-last level {C = 128, W, H, N}; box = one K block of a tile: {64, 16, 16, 1}
 static int tc_make_tmap(const TcLevel& L, TcTmap* out) {

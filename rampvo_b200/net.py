@@ -10,7 +10,8 @@ restructured around the B200 kernels of librampvo_b200.so:
                     (LayerNorm returns fp32, SURVEY.md appendix "dtype drift").
   Patchifier        patch selection + the four altcorr.patchify gathers with the bilinear blend
                     fused; gmap is written straight into the caller's channels-last ring slot.
-The dense Linear layers currently run on cuBLAS (library GEMMs).
+The 384-input Linear layers run on the hand-written tcgen05 GEMM (rvo_up_linear); only the first
+correlation layer (K = 1008) still calls cuBLAS.
 """
 import ctypes
 
@@ -160,8 +161,16 @@ class Update(nn.Module):
         dev = net.device
         st = _lib.stream_ptr(dev)
         P = _lib.ptr
-        lin = lambda x, k: F.linear(x, W[k][0], W[k][1])
-        lin_relu = lambda x, k: torch._addmm_activation(W[k][1], x, W[k][0].t())
+        def linear(x, k, relu):
+            # nn.Linear (+ ReLU) on the tcgen05 GEMM of librampvo (rvo_up_linear, csrc/up_gemm.cu): weights
+            # resident in shared memory, activations streamed by TMA, bias / ReLU / fp16 pack in the epilogue
+            w, b = W[k]
+            y = torch.empty(x.shape[0], w.shape[0], dtype=torch.float16, device=dev)
+            _lib.check(L.rvo_up_linear(P(x), x.stride(0), P(w), P(b), x.shape[0], w.shape[1], w.shape[0],
+                                       int(relu), P(y), y.stride(0), st), "rvo_up_linear")
+            return y
+        lin = lambda x, k: linear(x, k, False)
+        lin_relu = lambda x, k: linear(x, k, True)
         f16 = lambda: torch.empty(E, DIM, dtype=torch.float16, device=dev)
         f32 = lambda: torch.empty(E, DIM, dtype=torch.float32, device=dev)
 
@@ -175,7 +184,7 @@ class Update(nn.Module):
             h = torch._addmm_activation(W["corr0"][1], c, W["corr0p"].t())
         else:
             c = corr.reshape(E, -1).to(torch.float16).contiguous()
-            h = lin_relu(c, "corr0")
+            h = torch._addmm_activation(W["corr0"][1], c, W["corr0"][0].t())
         h = lin(h, "corr2")
         h3 = f16()
         _lib.check(L.rvo_up_ln_relu(P(h), P(W["ln_corr"][0]), P(W["ln_corr"][1]), E, DIM, P(h3), st), "rvo_up_ln_relu")
