@@ -13,8 +13,8 @@
 //   * one elected thread issues 4 x tcgen05.mma (M128 N192 K16) per K block into one of two 192-column
 //     TMEM accumulators; tcgen05.commit hands the smem stage back to the TMA producer and, after the 6th
 //     K block, the accumulator to the epilogue;
-//   * epilogue: 2 x 4 warps (TMEM lane quadrant per warp, thread = output row): tcgen05.ld 32 columns at a
-//     time, + bias (fp32, from shared memory), optional ReLU, fp16 pack, 16-byte stores — while the tensor
+//   * epilogue: 2 accumulators x 4 TMEM lane quadrants x 2 warps (alternate 32-column chunks), thread = output
+//     row: tcgen05.ld 32 columns at a time, + bias (fp32, from shared memory), optional ReLU, fp16 pack, 16-byte stores — while the tensor
 //     core already works on the next M tile in the other accumulator.
 // Grid: 148 CTAs = (N / 192) column slices x 148 / (N / 192) row walkers.
 #include <stdlib.h>
@@ -32,15 +32,16 @@ constexpr int kUgStages = 5;
 constexpr int kUgWBytes = kUgKB * kUgN * 128;            // 147 456
 constexpr int kUgXStage = kUgM * 128;                    // 16 384
 constexpr int kUgSmemBytes = kUgWBytes + kUgStages * kUgXStage + 1024;
-constexpr int kUgThreads = 512;              // warp 0 TMA (W), warp 1 MMA, warps 4-11 epilogue, 12-15 X producers
+constexpr int kUgThreads = 768;              // warp 0 TMA (W), warp 1 MMA, warps 4-19 epilogue, 20-23 X producers
 
 // debugging aid (RVO_UP_TRACE=1): clock64 stamps of CTA 0, read back with rvo_up_trace
 __device__ long long g_ug_trace[8 * 64];
 #define UG_TRACE(slot, i) do { if (trace && blockIdx.x == 0 && (i) < 64) g_ug_trace[(slot) * 64 + (i)] = clock64(); } while (0)
 
+template <bool kRelu>
 __global__ void __launch_bounds__(kUgThreads, 1)
 up_linear_kernel(const __half* __restrict__ X, int64_t ldx, const __grid_constant__ TcTmap tmw,
-                 const __half* __restrict__ bias, int M, int n_slices, int relu, __half* __restrict__ Y,
+                 const __half* __restrict__ bias, int M, int n_slices, __half* __restrict__ Y,
                  int64_t ldy, int trace) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t wfull[kUgKB], xfull[kUgStages], xempty[kUgStages], tfull[2], tempty[2];
@@ -60,7 +61,7 @@ up_linear_kernel(const __half* __restrict__ X, int64_t ldx, const __grid_constan
     }
     for (int s = 0; s < 2; s++) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 128);
+      mbar_init(&tempty[s], 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -119,9 +120,9 @@ up_linear_kernel(const __half* __restrict__ X, int64_t ldx, const __grid_constan
     }
     if (first)                                             // no tile for this CTA: still wait for the W loads
       for (int kb = 0; kb < kUgKB; kb++) mbar_wait_spin(&wfull[kb], 0);
-  } else if (warp >= 12) {
+  } else if (warp >= 20) {
     // ===== X producers: thread owns 16-byte chunk `ch` of rows r0 + 16 j of every K block =====
-    const int ptid = tid - 12 * 32, ch = ptid & 7, r0 = ptid >> 3;
+    const int ptid = tid - 20 * 32, ch = ptid & 7, r0 = ptid >> 3;
     int it = 0;                                            // K-block counter over all tiles of this CTA
     for (int t = walker; t < n_tiles; t += n_walkers)
       for (int kb = 0; kb < kUgKB; kb++, it++) {
@@ -148,8 +149,10 @@ up_linear_kernel(const __half* __restrict__ X, int64_t ldx, const __grid_constan
     for (int d = 3; d >= 1; d--)
       if (it >= d) mbar_arrive(&xfull[(it - d) % kUgStages]);
   } else if (warp >= 4) {
-    // ===== epilogue: group g drains accumulator g (tiles lt == g mod 2), quadrant q, thread = row =====
-    const int g = (warp - 4) >> 2, q = warp & 3;
+    // ===== epilogue: group g drains accumulator g (tiles lt == g mod 2); quadrant q, thread = row; the two
+    // warps of a (group, quadrant) take alternate 32-column chunks (a single warp per scheduler issues at
+    // ~0.35 IPC on this dependent LDTM -> add -> pack -> store chain) =====
+    const int g = (warp - 4) >> 3, hf = ((warp - 4) >> 2) & 1, q = warp & 3;
     const uint32_t tlane = tmem_base + g * 256 + ((uint32_t)(q * 32) << 16);
     int lt = 0;
     for (int t = walker; t < n_tiles; t += n_walkers, lt++) {
@@ -157,16 +160,16 @@ up_linear_kernel(const __half* __restrict__ X, int64_t ldx, const __grid_constan
       const int row = t * kUgM + q * 32 + lane;
       mbar_wait(&tfull[g], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      if (q == 0 && lane == 0) UG_TRACE(4, lt);
+      if (q == 0 && hf == 0 && lane == 0) UG_TRACE(4, lt);
 #pragma unroll 1
-      for (int c0 = 0; c0 < kUgN; c0 += 32) {
+      for (int c0 = 32 * hf; c0 < kUgN; c0 += 64) {
         float v[32];
         tmem_ld32(tlane + c0, v);
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) {
           float a = v[2 * j] + bias_s[c0 + 2 * j], b = v[2 * j + 1] + bias_s[c0 + 2 * j + 1];
-          if (relu) {
+          if (kRelu) {
             a = fmaxf(a, 0.f);
             b = fmaxf(b, 0.f);
           }
@@ -199,7 +202,7 @@ up_linear_kernel(const __half* __restrict__ X, int64_t ldx, const __grid_constan
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-      if (q == 0 && lane == 0) UG_TRACE(5, lt);
+      if (q == 0 && hf == 0 && lane == 0) UG_TRACE(5, lt);
       mbar_arrive(&tempty[g]);
     }
   }
@@ -229,9 +232,16 @@ extern "C" int rvo_up_linear(const void* x16, int64_t ldx, const void* w16, cons
   int rc = make_tmap_2d_f16(w16, N, K, K, kUgN, &tmw, "rvo_up_linear(w)");
   if (rc != RVO_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  RVO_CUDA(cudaFuncSetAttribute(up_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUgSmemBytes));
-  up_linear_kernel<<<kNumSMs, kUgThreads, kUgSmemBytes, st>>>((const __half*)x16, ldx, tmw, (const __half*)bias16, M, N / kUgN, relu,
-                                                              (__half*)y16, ldy, getenv("RVO_UP_TRACE") ? atoi(getenv("RVO_UP_TRACE")) : 0);
+  const int trace = getenv("RVO_UP_TRACE") ? atoi(getenv("RVO_UP_TRACE")) : 0;
+  if (relu) {
+    RVO_CUDA(cudaFuncSetAttribute(up_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUgSmemBytes));
+    up_linear_kernel<true><<<kNumSMs, kUgThreads, kUgSmemBytes, st>>>((const __half*)x16, ldx, tmw, (const __half*)bias16,
+                                                                      M, N / kUgN, (__half*)y16, ldy, trace);
+  } else {
+    RVO_CUDA(cudaFuncSetAttribute(up_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUgSmemBytes));
+    up_linear_kernel<false><<<kNumSMs, kUgThreads, kUgSmemBytes, st>>>((const __half*)x16, ldx, tmw, (const __half*)bias16,
+                                                                       M, N / kUgN, (__half*)y16, ldy, trace);
+  }
   RVO_LAUNCH_CHECK("up_linear_kernel");
   return RVO_OK;
 }

@@ -60,13 +60,11 @@ def trace():
     assert L.rvo_up_trace(buf) == 0
     a = np.array(buf[:], dtype=np.int64).reshape(8, 64)
     t0 = a[0, 0]
-    print("W issue 0, W landed %d, kernel end %d" % (a[0, 1] - t0, a[0, 2] - t0))
-    print(" it  P.xempty  M.ready M.issued")
-    for i in range(30):
-        print("%3d %9d %8d %8d" % (i, a[1, i] - t0, a[2, i] - t0, a[3, i] - t0))
-    print("tile E.start E.end")
-    for i in range(5):
-        print("%3d %8d %8d" % (i, a[4, i] - t0, a[5, i] - t0))
+    print("kernel end %d cycles after the W loads were issued" % (a[0, 2] - t0))
+    print("tile  M.first_ready  M.last_issued   E.start    E.end    E.dur")
+    for i in range(6):
+        print("%3d %14d %14d %9d %8d %8d" % (i, a[2, i] - t0, a[3, i] - t0, a[4, i] - t0, a[5, i] - t0, a[5, i] - a[4, i]))
+    print("producer: xempty seen at", [int(v - t0) for v in a[1, :32]])
 
 
 if __name__ == "__main__":
