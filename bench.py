@@ -85,7 +85,9 @@ def build_vo(device, seed=1234):
     train_cfg = {"event_bias": True, "input_mode": "MultiScale", "num_event_bins": 5}
     cfg = preset("default")
     cfg.KEYFRAME_THRESH = 0.0                    # never drop a keyframe: the no-drop upper-bound graph
-    vo = Ramp_vo(cfg, VONet(train_cfg), train_cfg, ht=480, wd=640, device=device)
+    # pipeline: the keyframe step of frame t (its decision is a device->host read) is finished at the start
+    # of call t+1, after that frame's encoder graph was launched — same work, overlapped (Ramp_vo.sync())
+    vo = Ramp_vo(cfg, VONet(train_cfg), train_cfg, ht=480, wd=640, device=device, pipeline=True)
     # random weights: pin the data-dependent initialisation gate (Ramp_vo.py:385)
     vo.motion_probe = lambda: torch.tensor(10.0)
     return vo
@@ -137,6 +139,7 @@ def run_ours(args):
         a.record()
         for t in range(first + W, first + W + K):
             step_fn(t)
+        state["vo"].sync()                   # the last frame's deferred keyframe step belongs to the timed region
         b.record()
         barrier()
         if profile:
@@ -213,6 +216,7 @@ def run_ours(args):
         "dtype": "f16 features / f32 geometry+BA", "data": "synthetic",
         "config": {"workload": WORKLOAD, "edges": E_dev, "patches_per_frame": 96, "ba_iterations": 2,
                    "keyframe_thresh": 0.0, "weights": "random init, seed 1234",
+                   "pipeline": "keyframe step of frame t overlapped with the encoder graph of frame t+1 (Ramp_vo pipeline=True)",
                    "l2": "per-step working set (167 MB feature rings + 80 MB corr volume) exceeds the 126 MB L2",
                    "parallelism": "one independent stream per GPU" if world > 1 else "single GPU",
                    "poses_finite": finite},

@@ -49,6 +49,9 @@ class _PatchifyGraph:
         enc = vo.network.patchify.encoder
         self.state = None
         self.graph = None
+        # parallel branches of the captured graph: context CNN and patch selection on side streams
+        enc.branch_stream = torch.cuda.Stream(device=dev)
+        vo.network.patchify.branch_stream = torch.cuda.Stream(device=dev)
         # warm up on a side stream (cuDNN / cuBLAS handles, lazy module init), then capture
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
@@ -155,7 +158,7 @@ class _UpdateGraph:
 
 
 class Ramp_vo:
-    def __init__(self, cfg, network, train_cfg, ht=480, wd=640, device="cuda", use_graphs=True):
+    def __init__(self, cfg, network, train_cfg, ht=480, wd=640, device="cuda", use_graphs=True, pipeline=False):
         self.cfg = cfg
         self.event_bias = train_cfg["event_bias"]
         self.train_cfg = train_cfg
@@ -209,6 +212,12 @@ class Ramp_vo:
         self._plans = None          # GraphPlans of the current edge list
         self._pair_cnt = None       # host-side {(source frame, target frame): number of edges}
         self.use_graphs = use_graphs
+        # pipeline=True: the keyframe step of frame t (whose decision needs a device->host read) is finished at
+        # the start of the next __call__, after that frame's encoder graph has been launched, so the GPU runs
+        # encoder(t+1) while the host does the edge bookkeeping of frame t.  Same work, same results; between
+        # calls the public state is the one BEFORE the keyframe step until sync() / terminate() / the next call.
+        self.pipeline = pipeline
+        self._pending_kf = None     # (pinned host buffer, event) of a keyframe step that was begun
         self._pgraph = None         # _PatchifyGraph, captured at the first frame
         self._corr_buf = None       # [1, capacity, 896] correlation rows (882 used)
         self._corrt_buf = None      # [1, capacity, 1008] correlation rows in the tile layout
@@ -271,6 +280,7 @@ class Ramp_vo:
 
     def terminate(self):
         """interpolate missing poses; returns (poses [counter,7] camera-to-world, tstamps)."""
+        self.sync()
         self.traj = {}
         ts = self.tstamps_[:self.n].tolist()
         for i in range(self.n):
@@ -421,8 +431,17 @@ class Ramp_vo:
                              self.kk[k], beta=0.5)
         return flow.mean().item()
 
-    def keyframe(self):
-        """remove keyframe n-KEYFRAME_INDEX if motion is small (Ramp_vo.py:237-274)"""
+    def sync(self):
+        """finish a keyframe step deferred by pipeline mode (no-op otherwise)"""
+        if self._pending_kf is not None:
+            host, ev = self._pending_kf
+            self._pending_kf = None
+            ev.synchronize()
+            self._keyframe_finish(host.tolist())
+
+    def _keyframe_begin(self):
+        """launch the flow-magnitude reduction of the keyframe test (Ramp_vo.py:237-241); returns the device
+        buffer [sum_ij, count_ij, sum_ji, count_ji]"""
         i = self.n - self.cfg.KEYFRAME_INDEX - 1
         j = self.n - self.cfg.KEYFRAME_INDEX + 1
         # motionmag(i, j) + motionmag(j, i) in one launch and one device->host read
@@ -432,7 +451,25 @@ class Ramp_vo:
                 _lib.ptr(self.poses_), _lib.ptr(self.patches_), _lib.ptr(self.intrinsics_),
                 _lib.ptr(self.ii), _lib.ptr(self.jj), _lib.ptr(self.kk), self.ii.numel(), self.P, i, j,
                 0.5, _lib.ptr(out4), _lib.stream_ptr(self.device)), "rvo_pair_flow")
-        s1, c1, s2, c2 = out4.tolist()
+        return out4
+
+    def keyframe(self):
+        """remove keyframe n-KEYFRAME_INDEX if motion is small (Ramp_vo.py:237-274)"""
+        self.sync()
+        self._keyframe_finish(self._keyframe_begin().tolist())
+
+    def _keyframe_defer(self):
+        out4 = self._keyframe_begin()
+        host = getattr(self, "_kf_host", None)
+        if host is None:
+            host = self._kf_host = torch.empty(4, dtype=torch.float32).pin_memory()
+        host.copy_(out4, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._pending_kf = (host, ev)
+
+    def _keyframe_finish(self, vals):
+        s1, c1, s2, c2 = vals
         nan = float("nan")      # the reference takes the mean of an empty selection (nan) too
         m = (s1 / c1 if c1 else nan) + (s2 / c2 if c2 else nan)
         if m / 2 < self.cfg.KEYFRAME_THRESH:
@@ -495,6 +532,7 @@ class Ramp_vo:
         """one recurrent update: reproject -> corr -> update operator -> 2 BA iterations
         (Ramp_vo.py:276-310).  With use_graphs the whole body (incl. the graph-plan sorts) is a CUDA
         graph keyed by (edge count, window length), replayed while the window slides."""
+        self.sync()
         E = self.ii.numel()
         t0 = self.n - self.cfg.OPTIMIZATION_WINDOW if self.is_initialized else 1
         t0 = max(t0, 1)
@@ -557,7 +595,6 @@ class Ramp_vo:
     def __call__(self, tstamp, input_tensor, intrinsics):
         """track a new frame (Ramp_vo.py:327-410)"""
         input_ = preprocess_input(input_tensor=input_tensor)
-        slot = self.n % self.mem
         P, M = self.P, self.M
         events, images, mask = input_
         mask_l = torch.as_tensor(mask).reshape(-1).tolist()
@@ -565,9 +602,13 @@ class Ramp_vo:
                      and tuple(events.shape[-2:]) == (self.ht, self.wd))
         if graphable:
             if self._pgraph is None:
+                self.sync()
                 self._pgraph = _PatchifyGraph(self)
             g = self._pgraph
-            g.run(events, images, reinit=(tstamp == 0))
+            g.run(events, images, reinit=(tstamp == 0))      # writes only the graph's staging buffers
+        self.sync()     # pipeline mode: the previous frame's keyframe step, overlapped with the encoder graph
+        slot = self.n % self.mem
+        if graphable:
             self._gmap_store[slot * M:(slot + 1) * M] = g.gmap
             patches, clr, imap_new, f1_new, f2_new = g.patches.clone(), g.clr, g.imap, g.f1, g.f2
         else:
@@ -627,4 +668,7 @@ class Ramp_vo:
                 self.update()
         elif self.is_initialized:
             self.update()
-            self.keyframe()
+            if self.pipeline:
+                self._keyframe_defer()
+            else:
+                self.keyframe()

@@ -256,8 +256,23 @@ class MultiScaleMergerDoubleNet(nn.Module):
                        "rvo_stem_forward")
             self.super_states[k] = out
             per_scale.append(out)
-        fmap = self.fmap_encoder(per_scale[0], per_scale[1], per_scale[2], out_scale)
-        imap = self.imap_encoder(per_scale[0], per_scale[1], per_scale[2], out_scale)
+        side = getattr(self, "branch_stream", None)
+        if side is None:
+            fmap = self.fmap_encoder(per_scale[0], per_scale[1], per_scale[2], out_scale)
+            imap = self.imap_encoder(per_scale[0], per_scale[1], per_scale[2], out_scale)
+        else:
+            # the two CNNs are independent (~45 small kernels each): fork the context encoder onto a side
+            # stream so that a captured CUDA graph runs them as parallel branches
+            cur = torch.cuda.current_stream(ev.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                imap = self.imap_encoder(per_scale[0], per_scale[1], per_scale[2], out_scale)
+            fmap = self.fmap_encoder(per_scale[0], per_scale[1], per_scale[2], out_scale)
+            cur.wait_stream(side)
+            if not torch.cuda.is_current_stream_capturing():     # eager use: keep the allocator informed
+                imap.record_stream(cur)
+                for t in per_scale:
+                    t.record_stream(side)
         return fmap[None], imap[None]
 
     def forward(self, events, images, mask, reinit_hidden=False, out_scale=1.0):

@@ -287,17 +287,32 @@ class Patchifier(nn.Module):
     def forward(self, input_, patches_per_image=80, reinit_hidden=False, disps=None, event_bias=False,
                 gradient_bias=False, gmap_out=None):
         events, images, mask = input_
+        mask_l = torch.as_tensor(mask).reshape(-1).tolist()       # host-side, like evaluate.py:163
+        # the patch selection reads only the events: with a side stream it becomes a parallel branch of the
+        # captured graph (top-k alone is ~100 us of a single-CTA kernel)
+        side = getattr(self, "branch_stream", None)
+        coords = None
+        if side is not None and event_bias and all(mask_l) and events.is_cuda:
+            cur = torch.cuda.current_stream(events.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                coords = coords_from_topk_events(events, patches_per_image, non_max_supp_rad=11)
         # fmap / 4, imap / 4 (net.py:152-153) are folded into the encoders' last 1x1 convolutions
         fmap, imap = self.encoder(events=events, images=images, mask=mask, reinit_hidden=reinit_hidden,
                                   out_scale=0.25)
-        mask_l = torch.as_tensor(mask).reshape(-1).tolist()       # host-side, like evaluate.py:163
+        if coords is not None:
+            cur.wait_stream(side)
+            if not torch.cuda.is_current_stream_capturing():
+                coords.record_stream(cur)
         if not any(mask_l):
             return None, None, None, None, None, None
         if events.shape[1] == len(mask_l) and not all(mask_l):
             events = events[:, [t for t, keep in enumerate(mask_l) if keep]]
         b, n, c, h, w = fmap.shape
         dev = fmap.device
-        if event_bias:
+        if coords is not None:
+            pass
+        elif event_bias:
             coords = coords_from_topk_events(events, patches_per_image, non_max_supp_rad=11)
         else:
             x = torch.randint(1, w - 1, size=[n, patches_per_image], device=dev)

@@ -132,3 +132,36 @@ def test_update_operator_accepts_tile_layout_corr():
         n1, (d1, w1, _) = up(g["net"], g["inp"], corr_ref, None, g["ii"], g["jj"], g["kk"])
         n2, (d2, w2, _) = up(g["net"], g["inp"], tile, None, g["ii"], g["jj"], g["kk"])
     assert (n1 - n2).abs().max().item() < 2e-2 and (w1 - w2).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("thresh", [0.0, 1e9])
+def test_pipeline_mode_gives_the_same_state_after_sync(thresh):
+    """pipeline=True defers the keyframe step of frame t to the start of call t+1 (overlapped with the
+    encoder graph): after sync() the graph and the frame count equal the non-pipelined run exactly, and
+    the poses agree as well as two non-pipelined runs agree with each other (the BA / softmax reductions
+    use float atomics, and a random-weight network amplifies their rounding) — with keyframe drops never
+    (thresh 0) and always (thresh 1e9) taken (Ramp_vo.py:237-274)."""
+    seq = synth.SyntheticSequence(seed=0, device="cuda")
+    states = []
+    for pipe in (False, False, True):
+        vo = _make_vo("cfg1")
+        vo.cfg.KEYFRAME_THRESH = thresh
+        vo.pipeline = pipe
+        vo.motion_probe = lambda: torch.tensor(10.0)
+        with torch.no_grad():
+            for t in range(16):
+                vo(t, seq.frame(t), seq.intrinsics)
+            assert (vo._pending_kf is not None) == pipe
+            vo.sync()
+        states.append((vo.n, vo.m, vo.ii.clone(), vo.jj.clone(), vo.kk.clone(), vo.poses_[:vo.n].clone(),
+                       dict(vo.delta)))
+    a, a2, b = states
+    assert a[0] == b[0] and a[1] == b[1]
+    for k in (2, 3, 4):
+        assert torch.equal(a[k], b[k])
+    assert sorted(a[6]) == sorted(b[6])
+    assert torch.isfinite(b[5]).all()
+    run_to_run = (a[5] - a2[5]).abs().max().item()
+    assert (a[5] - b[5]).abs().max().item() <= 10 * run_to_run + 1e-4, run_to_run
+    if thresh > 0:
+        assert a[0] < 16          # frames were dropped
