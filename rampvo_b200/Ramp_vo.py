@@ -120,6 +120,7 @@ class _UpdateGraph:
         self.kk = torch.zeros(E, dtype=torch.long, device=dev)
         self.t0 = torch.zeros(1, dtype=torch.int32, device=dev)
         self.n_free = n_free
+        self.side = torch.cuda.Stream(device=dev)
         self.net_in = vo.net                     # view of the current ping-pong buffer
         self.net_out = vo._net_other(E)
         self._load(vo.n - n_free)
@@ -147,9 +148,15 @@ class _UpdateGraph:
 
     def _body(self):
         vo = self.vo
-        plans = vo._new_plans(self.ii, self.jj, self.kk)
+        # the graph-plan sorts depend only on the edge list: a parallel branch next to reproject + corr
+        cur = torch.cuda.current_stream(vo.device)
+        side = self.side
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            plans = vo._new_plans(self.ii, self.jj, self.kk)
         _, self.weight = vo._update_body(self.ii, self.jj, self.kk, self.net_in, self.net_out, plans,
-                                         0, self.n_free, t0_dev=self.t0)
+                                         0, self.n_free, t0_dev=self.t0,
+                                         before_update=lambda: cur.wait_stream(side))
 
     def run(self, t0):
         self._load(t0)
@@ -502,7 +509,7 @@ class Ramp_vo:
         lim = self.n - self.cfg.REMOVAL_WINDOW
         self.remove_factors(self.ii < lim, lambda i, j: i < lim)     # ix[kk] == ii (index_[f] == f)
 
-    def _update_body(self, ii, jj, kk, net_in, net_out, plans, t0, t1, t0_dev=None):
+    def _update_body(self, ii, jj, kk, net_in, net_out, plans, t0, t1, t0_dev=None, before_update=None):
         """reproject -> corr -> update operator -> 2 BA iterations on explicit buffers; every
         host-side scalar is either constant across frames or read from device memory (t0_dev)"""
         coords = self.reproject(indicies=(ii, jj, kk))
@@ -512,6 +519,8 @@ class Ramp_vo:
             else:
                 corr = self.corr(coords, indicies=(kk, jj))
             ctx = (self.imap_, kk, self.M * self.mem)     # imap[:, kk % (M*mem)], gather fused
+            if before_update is not None:
+                before_update()                           # join the branch that built `plans`
             new_net, (delta, weight, _) = self.network.update(net_in, ctx, corr, None, ii, jj, kk,
                                                               plans=plans, net_out=net_out)
         weight = weight.float()
