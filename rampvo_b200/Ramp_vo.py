@@ -49,6 +49,9 @@ class _PatchifyGraph:
         enc = vo.network.patchify.encoder
         self.state = None
         self.graph = None
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.replayed = torch.cuda.Event()
+        self.replayed.record(torch.cuda.current_stream(dev))
         # parallel branches of the captured graph: context CNN and patch selection on side streams
         enc.branch_stream = torch.cuda.Stream(device=dev)
         vo.network.patchify.branch_stream = torch.cuda.Stream(device=dev)
@@ -100,9 +103,23 @@ class _PatchifyGraph:
             for b, cur in zip(self.state, enc.super_states):
                 if cur is not None and cur is not b:
                     b.copy_(cur)
-        self.ev.copy_(events)
-        self.im.copy_(images)
+        dev = self.vo.device
+        cur = torch.cuda.current_stream(dev)
+        if events.is_cuda and images.is_cuda:
+            self.ev.copy_(events)
+            self.im.copy_(images)
+        else:
+            # host inputs (pinned memory copies asynchronously): H->D on a copy stream, so that in pipeline
+            # mode the transfer of frame t+1 overlaps the recurrent update of frame t still running on the
+            # main stream; the static input buffers are free once the previous replay has finished
+            cs = self.copy_stream
+            cs.wait_event(self.replayed)
+            with torch.cuda.stream(cs):
+                self.ev.copy_(events, non_blocking=True)
+                self.im.copy_(images, non_blocking=True)
+            cur.wait_stream(cs)
         self.graph.replay()
+        self.replayed.record(cur)
         self.vo.graph_kernel_launches += self.n_kernels
         enc.super_states = list(self.state)
 
@@ -621,6 +638,8 @@ class Ramp_vo:
             self._gmap_store[slot * M:(slot + 1) * M] = g.gmap
             patches, clr, imap_new, f1_new, f2_new = g.patches.clone(), g.clr, g.imap, g.f1, g.f2
         else:
+            if not (events.is_cuda and images.is_cuda):
+                input_ = (events.to(self.device), images.to(self.device), mask)
             gslot = self._gmap_store[slot * M:(slot + 1) * M].permute(0, 3, 1, 2)[None]   # [1,M,128,P,P]
             with torch.autocast("cuda", enabled=self.autocast):
                 fmap, gmap, imap, patches, _, clr = self.network.patchify(
