@@ -54,3 +54,24 @@ def test_no_cpu_fallback():
         altcorr.corr(torch.zeros(1, 1, 8, 3, 3), torch.zeros(1, 1, 8, 4, 4),
                      torch.zeros(1, 1, 2, 3, 3), torch.zeros(1, dtype=torch.long),
                      torch.zeros(1, dtype=torch.long), 1)
+
+
+def test_up_linear_argument_errors(lib):
+    # shape / pointer validation happens before any CUDA call (no GPU needed)
+    rc = lib.rvo_up_linear(None, 384, None, None, 8, 128, 384, 0, None, 384, None)
+    assert rc == 1 and b"K must be 384" in lib.rvo_last_error()
+    rc = lib.rvo_up_linear(None, 384, None, None, 8, 384, 100, 0, None, 384, None)
+    assert rc == 1
+    rc = lib.rvo_up_linear(None, 384, None, None, 8, 384, 384, 0, None, 384, None)
+    assert rc == 1 and b"null" in lib.rvo_last_error()
+    assert lib.rvo_up_linear(None, 384, None, None, 0, 384, 384, 0, None, 384, None) == 0     # M = 0: no-op
+
+
+def test_corr_tiles_workspace_size(lib):
+    import ctypes
+    arr = (_lib.FMap * 2)(_lib.FMap(0, _lib.RVO_F16, 32, 128, 120, 160, 120 * 160 * 128, 1, 160 * 128, 128),
+                          _lib.FMap(0, _lib.RVO_F16, 32, 128, 30, 40, 30 * 40 * 128, 1, 40 * 128, 128))
+    n0 = lib.rvo_corr_tiles_ws_bytes(arr, 2, 0)
+    n1 = lib.rvo_corr_tiles_ws_bytes(arr, 2, 45312)
+    assert 0 < n0 < n1 and n1 >= 45312 * 18 * (32 + 8)       # a 32-byte record + bin / rank per row
+    assert lib.rvo_corr_tiles_ws_bytes(arr, 2, -1) == -1
