@@ -107,7 +107,9 @@ int rvo_corr_pyramid(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const float
  *   out[e*out_ld + ((lvl*9 + pix)*7 + a)*8 + b]   a = y offset, b = x offset in 0..6; b = 7 is a
  *   zero pad (one aligned 16-byte store per row); out_ld >= 504*nlevels, % 8 == 0.  (The reference layout of
  *   ramp/Ramp_vo.py:182 is index ((b*7 + a)*9 + pix)*nlevels + lvl.)
- * ws: rvo_corr_tiles_ws_bytes(pyr, nlevels, E) bytes of device scratch. */
+ * ws: rvo_corr_tiles_ws_bytes(pyr, nlevels, E) bytes of device scratch.  Limits: E * 9 * nlevels < 2^31 rows and
+ * at most 24 576 tiles over all levels and ring frames (32 frames of up to ~1000 x 800 input pixels at 1/4 scale);
+ * larger problems return RVO_ERR_ARG — use rvo_corr_pyramid. */
 int64_t rvo_corr_tiles_ws_bytes(const rvo_fmap_t* pyr, int nlevels, int E);
 int rvo_corr_tiles(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const float* scale, int nlevels,
                    const float* coords, const int64_t* kk, const int64_t* jj, int64_t pmod,
