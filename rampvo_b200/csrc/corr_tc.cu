@@ -372,7 +372,10 @@ __device__ __forceinline__ uint4 epi_pack(const float (&h0)[7], const float (&h1
   return u;
 }
 
-// debugging aid (RVO_CORR_DBG & 16): per-block clock64 stamps of CTA 0, read back with rvo_corr_trace
+// debugging aids, env RVO_CORR_DBG (bit mask, 0 in production; results are WRONG with bits 1-8 set — they exist to
+// time the pipeline's parts in isolation, tools/corr_bench.py): 1 = epilogue reads TMEM but skips the arithmetic and
+// stores, 2 = epilogue only hands the accumulator back, 4 = no A gathers, 8 = no TMA tile loads, 16 = per-block
+// clock64 stamps of CTA 0 (read back with rvo_corr_trace, printed by `tools/corr_bench.py trace`)
 __device__ long long g_tc_trace[8 * 256];
 #define TC_TRACE(slot, i) do { if ((dbg & 16) && blockIdx.x == 0 && (i) < 256) g_tc_trace[(slot) * 256 + (i)] = clock64(); } while (0)
 
