@@ -162,6 +162,7 @@ def test_pipeline_mode_gives_the_same_state_after_sync(thresh):
     assert sorted(a[6]) == sorted(b[6])
     assert torch.isfinite(b[5]).all()
     run_to_run = (a[5] - a2[5]).abs().max().item()
-    assert (a[5] - b[5]).abs().max().item() <= 10 * run_to_run + 1e-4, run_to_run
+    # two plain runs differ by ~1e-2 here (chaotic random-weight updates); never demand more of the pipelined one
+    assert (a[5] - b[5]).abs().max().item() <= max(10 * run_to_run, 5e-2), run_to_run
     if thresh > 0:
         assert a[0] < 16          # frames were dropped
