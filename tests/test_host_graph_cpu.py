@@ -61,3 +61,66 @@ def test_remove_factors_with_a_device_mask_only(vo_cpu):
     vo.remove_factors(m)
     assert vo.ii.numel() == E - gone and not (vo.jj == jmax).any()
     assert vo.net.shape[1] == E - gone and sum(vo._pair_counts().values()) == E - gone
+
+
+def test_keyframe_drop_matches_a_restatement_of_the_reference(vo_cpu):
+    """Ramp_vo._keyframe_finish with a forced drop against a numpy restatement of ramp/Ramp_vo.py:243-274
+    (frame-by-frame shift loop, boolean-indexed renumbering, removal window)."""
+    vo = vo_cpu
+    M, life, removal, KI = vo.M, vo.cfg.PATCH_LIFETIME, vo.cfg.REMOVAL_WINDOW, vo.cfg.KEYFRAME_INDEX
+    n = 30
+    ii, jj, kk = (torch.from_numpy(a) for a in synth.replay_graph(M, life, removal, n))
+    vo.n, vo.m = n, n * M
+    vo.ii, vo.jj, vo.kk = ii.clone(), jj.clone(), kk.clone()
+    vo._pair_cnt = None
+    vo._net_bufs, vo._net_cur = [None, None], 0
+    vo.net = torch.zeros(1, 0, vo.DIM)
+    vo._net_reserve(ii.numel())
+    vo.net = vo._net_bufs[0][:, :ii.numel()]
+    vo.net[0, :, 0] = (kk * 1000 + jj).float()
+    g = torch.Generator().manual_seed(3)
+    for buf in (vo.poses_, vo.patches_, vo.intrinsics_, vo.imap_, vo._gmap_store, vo._fmap1_store, vo._fmap2_store):
+        buf.copy_(torch.rand(buf.shape, generator=g).to(buf.dtype))
+    vo.poses_[:, 3:] = torch.nn.functional.normalize(vo.poses_[:, 3:] + 0.1, dim=-1)
+    vo.tstamps_[:n] = torch.arange(n)
+    vo.colors_.copy_(torch.randint(0, 255, vo.colors_.shape, generator=g).to(torch.uint8))
+    vo.delta = {}
+    snap = {k: getattr(vo, k).clone() for k in ("tstamps_", "colors_", "poses_", "patches_", "intrinsics_", "imap_",
+                                                "_gmap_store", "_fmap1_store", "_fmap2_store")}
+    old_thresh = vo.cfg.KEYFRAME_THRESH
+    vo.cfg.KEYFRAME_THRESH = 1e9
+    try:
+        vo._keyframe_finish([0.0, 1.0, 0.0, 1.0])
+    finally:
+        vo.cfg.KEYFRAME_THRESH = old_thresh
+
+    # ---- restatement
+    k = n - KI
+    keep = ~((ii == k) | (jj == k))
+    ri, rj, rk = ii[keep].clone(), jj[keep].clone(), kk[keep].clone()
+    rk[ri > k] -= M
+    ri[ri > k] -= 1
+    rj[rj > k] -= 1
+    mem = vo.mem
+    exp = {name: t.clone() for name, t in snap.items()}
+    gview = exp["_gmap_store"].view(mem, M, vo.P, vo.P, 128)
+    for i in range(k, n - 1):
+        for name in ("tstamps_", "colors_", "poses_", "patches_", "intrinsics_"):
+            exp[name][i] = exp[name][i + 1]
+        exp["imap_"][i % mem] = exp["imap_"][(i + 1) % mem]
+        gview[i % mem] = gview[(i + 1) % mem]
+        exp["_fmap1_store"][i % mem] = exp["_fmap1_store"][(i + 1) % mem]
+        exp["_fmap2_store"][i % mem] = exp["_fmap2_store"][(i + 1) % mem]
+    n2 = n - 1
+    keep2 = ~(ri < n2 - removal)                     # ix[kk] == ii for the identity index map
+    ri, rj, rk = ri[keep2], rj[keep2], rk[keep2]
+
+    assert vo.n == n2 and vo.m == n2 * M
+    assert torch.equal(vo.ii, ri) and torch.equal(vo.jj, rj) and torch.equal(vo.kk, rk)
+    for name, t in exp.items():
+        assert torch.equal(getattr(vo, name), t), name
+    assert list(vo.delta) == [k] and vo.delta[k][0] == k - 1
+    # hidden states followed their edges (tags carry the OLD patch / frame numbers)
+    old_tag = (kk[keep][keep2] * 1000 + jj[keep][keep2]).float()
+    assert torch.equal(vo.net[0, :, 0], old_tag)
+    assert sum(vo._pair_counts().values()) == ri.numel()
