@@ -124,3 +124,62 @@ def test_keyframe_drop_matches_a_restatement_of_the_reference(vo_cpu):
     old_tag = (kk[keep][keep2] * 1000 + jj[keep][keep2]).float()
     assert torch.equal(vo.net[0, :, 0], old_tag)
     assert sum(vo._pair_counts().values()) == ri.numel()
+
+
+def _q_mul(a, b):
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def _q_rot(q, v):
+    uv = 2 * np.cross(q[:3], v)
+    return v + q[3] * uv + np.cross(q[:3], uv)
+
+
+def _se3_mul(A, B):          # [t, q xyzw]: (A * B)(x) = A(B(x))
+    return np.concatenate([A[:3] + _q_rot(A[3:], B[:3]), _q_mul(A[3:], B[3:])])
+
+
+def _se3_inv(A):
+    qi = A[3:] * np.array([-1, -1, -1, 1.0])
+    return np.concatenate([-_q_rot(qi, A[:3]), qi])
+
+
+def test_terminate_interpolates_dropped_frames_like_the_reference(vo_cpu):
+    """terminate() / get_pose (ramp/Ramp_vo.py:155-173): poses of dropped frames are rebuilt from the stored
+    relative motions dP = T_k * T_{k-1}^-1 and everything is returned as camera-to-world."""
+    vo = vo_cpu
+    rng = np.random.default_rng(5)
+    kept = [0, 1, 2, 4, 5, 8]                      # timestamps that still own a keyframe slot
+    P = rng.normal(0, 0.3, (len(kept), 7))
+    P[:, 3:] /= np.linalg.norm(P[:, 3:], axis=1, keepdims=True)
+    vo.n, vo.counter = len(kept), 9
+    vo.sync()
+    vo.poses_[:vo.n] = torch.from_numpy(P).float()
+    vo.tstamps_[:vo.n] = torch.tensor(kept)
+    vo.tlist = list(range(100, 109))
+    D = {}
+    for t, t0 in ((3, 2), (6, 5), (7, 6)):          # 7 chains through the dropped 6
+        d = rng.normal(0, 0.1, 7)
+        d[3:] = d[3:] * 0.1 + np.array([0, 0, 0, 1.0])
+        d[3:] /= np.linalg.norm(d[3:])
+        D[t] = (t0, d)
+    from rampvo_b200.lietorch import SE3
+    vo.delta = {t: (t0, SE3(torch.from_numpy(d).float()[None])[0]) for t, (t0, d) in D.items()}
+    poses, tstamps = vo.terminate()
+
+    traj = {t: P[i] for i, t in enumerate(kept)}
+
+    def get(t):
+        if t in traj:
+            return traj[t]
+        t0, d = D[t]
+        return _se3_mul(d, get(t0))
+    exp = np.stack([_se3_inv(get(t)) for t in range(9)])
+    assert poses.shape == (9, 7) and np.array_equal(tstamps, np.arange(100, 109, dtype=float))
+    # quaternion sign is free
+    sgn = np.sign((poses[:, 3:] * exp[:, 3:]).sum(1, keepdims=True))
+    assert np.abs(poses[:, :3] - exp[:, :3]).max() < 1e-5
+    assert np.abs(poses[:, 3:] * sgn - exp[:, 3:]).max() < 1e-5
