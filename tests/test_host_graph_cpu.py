@@ -183,3 +183,26 @@ def test_terminate_interpolates_dropped_frames_like_the_reference(vo_cpu):
     sgn = np.sign((poses[:, 3:] * exp[:, 3:]).sum(1, keepdims=True))
     assert np.abs(poses[:, :3] - exp[:, :3]).max() < 1e-5
     assert np.abs(poses[:, 3:] * sgn - exp[:, 3:]).max() < 1e-5
+
+
+def test_tile_layout_weight_permutation_is_the_same_linear_map():
+    """The tcgen05 corr kernel writes [E, 1008] in the tile layout; the update operator reads it through
+    column-permuted first-layer weights (net.py: corr0t).  On CPU: the permuted layer applied to the tile
+    layout equals the reference layer (ramp/net.py:52, Linear(882, 384)) applied to the reference layout."""
+    from rampvo_b200 import altcorr
+    from rampvo_b200.net import Update
+    torch.manual_seed(1)
+    up = Update(3)
+    W = up._fused_weights()
+    cols, ref = altcorr.tile_layout_index(2)
+    assert len(cols) == 882 and sorted(ref.tolist()) == list(range(882)) and int(cols.max()) < 1008
+    c_ref = torch.randn(50, 882).half()
+    tile = torch.zeros(50, 1008, dtype=torch.float16)
+    tile[:, cols] = c_ref[:, ref]
+    a = c_ref.double() @ W["corr0"][0].double().t()
+    b = tile.double() @ W["corr0t"].double().t()
+    assert torch.allclose(a, b, rtol=0, atol=1e-9)
+    # pad columns of the tile layout carry zero weights
+    pad = torch.ones(1008, dtype=torch.bool)
+    pad[cols] = False
+    assert (W["corr0t"][:, pad] == 0).all()
