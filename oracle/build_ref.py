@@ -53,9 +53,38 @@ def _stage():
     open(p, "w").write(s)
 
 
+PY_OUT = os.path.join(OUT, "ref_py")
+
+
+def stage_python():
+    """Copies the reference's Python package `ramp/` (UNMODIFIED .py files only) into oracle/_ref/ref_py/ramp so
+    that oracle/ref_gpu_vo.py can import the reference's own Ramp_vo / VONet / Update / extractor / projective_ops
+    / ba on the GPU box, which has no /root/reference.  oracle/_ref is git-ignored: no reference source enters the
+    repository history; the copy ships to the box like the compiled .so files."""
+    if not os.path.isdir(REF):
+        raise RuntimeError("reference checkout not found at %s" % REF)
+    dst = os.path.join(PY_OUT, "ramp")
+    shutil.rmtree(PY_OUT, ignore_errors=True)
+    src = os.path.join(REF, "ramp")
+    n = 0
+    for root, dirs, files in os.walk(src):
+        dirs[:] = [d for d in dirs if d not in ("src", "include", "__pycache__")]
+        for f in files:
+            if f.endswith(".py"):
+                rel = os.path.relpath(os.path.join(root, f), src)
+                os.makedirs(os.path.dirname(os.path.join(dst, rel)), exist_ok=True)
+                shutil.copy(os.path.join(root, f), os.path.join(dst, rel))
+                n += 1
+    # the 5-bin event stack builder (utils/transformers.py:128-161) is the checker of the GPU event-stacking kernel
+    os.makedirs(os.path.join(PY_OUT, "ref_utils"), exist_ok=True)
+    shutil.copy(os.path.join(REF, "utils", "transformers.py"), os.path.join(PY_OUT, "ref_utils", "transformers.py"))
+    return n
+
+
 def build(verbose=False):
     if not os.path.isdir(REF):
         raise RuntimeError("reference checkout not found at %s" % REF)
+    stage_python()
     import torch  # noqa: F401
     from torch.utils.cpp_extension import load
     _stage()
@@ -97,5 +126,8 @@ def load_ref(name):
 
 
 if __name__ == "__main__":
+    if "--python-only" in sys.argv:
+        print(stage_python(), "python files staged")
+        sys.exit(0)
     build(verbose="-v" in sys.argv)
     print(sorted(os.listdir(OUT)))

@@ -167,7 +167,7 @@ def update_operator(p, net, inp, corr, ii, jj, kk):
 
 # --------------------------------------------------------------------------- corr (vectorised)
 
-def corr_pyramid_torch(gmap, pyramid, coords, kk, jj, radius=3, chunk=1024):
+def corr_pyramid_torch(gmap, pyramid, coords, kk, jj, radius=3, chunk=2048):
     """Ramp_vo.corr (ramp/Ramp_vo.py:175-182) with torch ops: gmap [Np,C,P,P], pyramid list of
     [Nf,C,H,W], coords [E,2,P,P], kk/jj already reduced modulo the ring sizes -> [E, 882]."""
     E, P = coords.shape[0], coords.shape[-1]
@@ -177,7 +177,8 @@ def corr_pyramid_torch(gmap, pyramid, coords, kk, jj, radius=3, chunk=1024):
     outs = []
     for lvl, fm in enumerate(pyramid):
         Nf, C, H, W = fm.shape
-        flat = fm.permute(1, 0, 2, 3).reshape(C, Nf * H * W)                 # channel-major frame table
+        # pixel-major frame table: one window tap = one contiguous C-vector (a CPU gathers rows, not scalars)
+        table = fm.permute(0, 2, 3, 1).reshape(Nf * H * W, C).contiguous()
         c = coords / (1, 4)[lvl]
         res = torch.empty(E, d, d, P, P)
         for s in range(0, E, chunk):
@@ -185,13 +186,14 @@ def corr_pyramid_torch(gmap, pyramid, coords, kk, jj, radius=3, chunk=1024):
             n = cc.shape[0]
             fx, fy = cc[:, 0].floor(), cc[:, 1].floor()
             dx, dy = (cc[:, 0] - fx)[:, None, None], (cc[:, 1] - fy)[:, None, None]
-            xs = fx.long()[:, None, None] + offs.view(1, 1, D, 1, 1)          # [n,1,D,P,P] (columns)
-            ys = fy.long()[:, None, None] + offs.view(1, D, 1, 1, 1)          # [n,D,1,P,P] (rows)
+            xs = fx.long()[:, :, :, None, None] + offs.view(1, 1, 1, 1, D)    # [n,P,P,1,D] (columns)
+            ys = fy.long()[:, :, :, None, None] + offs.view(1, 1, 1, D, 1)    # [n,P,P,D,1] (rows)
             ok = ((xs >= 0) & (xs < W) & (ys >= 0) & (ys < H))
-            lin = (ys.clamp(0, H - 1) * W + xs.clamp(0, W - 1)).expand(n, D, D, P, P)
+            lin = (ys.clamp(0, H - 1) * W + xs.clamp(0, W - 1))
             lin = lin + (jj[s:s + chunk] * (H * W)).view(n, 1, 1, 1, 1)
-            win = flat.index_select(1, lin.reshape(-1)).view(C, n, D, D, P, P)
-            raw = torch.einsum("ncij,cnabij->nabij", gmap[kk[s:s + chunk]], win) * ok
+            win = table.index_select(0, lin.reshape(-1)).view(n * P * P, D * D, C)
+            g = gmap[kk[s:s + chunk]].permute(0, 2, 3, 1).reshape(n * P * P, C, 1)
+            raw = (torch.bmm(win, g).view(n, P, P, D, D) * ok).permute(0, 3, 4, 1, 2)   # [n,a,b,i,j]
             o = ((1 - dx) * (1 - dy) * raw[:, :d, :d] + dx * (1 - dy) * raw[:, :d, 1:] +
                  (1 - dx) * dy * raw[:, 1:, :d] + dx * dy * raw[:, 1:, 1:])
             res[s:s + n] = o.permute(0, 2, 1, 3, 4)

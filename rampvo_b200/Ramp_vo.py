@@ -75,6 +75,7 @@ class _PatchifyGraph:
             for buf, new in zip(self.state, enc.super_states):
                 buf.copy_(new)
         self.n_kernels = _lib.lib().rvo_launch_count() - l0   # librampvo kernels inside the graph
+        self._held = _lib.Workspace.snapshot(dev)             # scratch the capture baked pointers to
         enc.super_states = saved
         for b in self.state:
             b.zero_()
@@ -143,20 +144,31 @@ class _UpdateGraph:
         self._load(vo.n - n_free)
         vo.corr_tiles(vo.reproject())            # sizes the persistent corr buffer outside the capture
         snap = (vo.poses_.clone(), vo.patches_.clone(), self.net_in.clone())
-        s = torch.cuda.Stream(device=dev)
-        s.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(s):
-            for _ in range(2):                   # warm-up (workspaces, cuBLAS handles) on a side stream
+        try:
+            # the capture stream is where the replays' scratch lives: warm up ON it so that every workspace
+            # (keyed by stream) has its final size before pointers are baked in
+            self.graph = torch.cuda.CUDAGraph()
+            if vo._capture_stream is None:       # one per Ramp_vo: its graphs share scratch, instances do not
+                vo._capture_stream = torch.cuda.Stream(device=dev)
+            s = vo._capture_stream
+            s.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s):
+                for _ in range(2):               # warm-up (workspaces, cuBLAS handles) on a side stream
+                    self._body()
+            torch.cuda.current_stream(dev).wait_stream(s)
+            torch.cuda.synchronize(dev)
+            vo.poses_.copy_(snap[0]); vo.patches_.copy_(snap[1]); self.net_in.copy_(snap[2])
+            l0 = _lib.lib().rvo_launch_count()
+            with torch.cuda.graph(self.graph, stream=s):
                 self._body()
-        torch.cuda.current_stream(dev).wait_stream(s)
-        torch.cuda.synchronize(dev)
-        vo.poses_.copy_(snap[0]); vo.patches_.copy_(snap[1]); self.net_in.copy_(snap[2])
-        self.graph = torch.cuda.CUDAGraph()
-        l0 = _lib.lib().rvo_launch_count()
-        with torch.cuda.graph(self.graph):
-            self._body()
-        self.n_kernels = _lib.lib().rvo_launch_count() - l0   # librampvo kernels inside the graph
-        vo.poses_.copy_(snap[0]); vo.patches_.copy_(snap[1]); self.net_in.copy_(snap[2])
+            self.n_kernels = _lib.lib().rvo_launch_count() - l0   # librampvo kernels inside the graph
+        finally:
+            # the warm-up / capture passes ran BA on the live state: always put it back
+            vo.poses_.copy_(snap[0]); vo.patches_.copy_(snap[1]); self.net_in.copy_(snap[2])
+        # every buffer the capture baked a raw pointer to and does not own stays alive with the graph: the
+        # correlation rows, both hidden-state buffers and the library scratch (they are replaced, not resized
+        # in place, when they grow — a cached graph then keeps using its own, still valid, copies)
+        self._held = (vo._corrt_buf, vo._corr_buf, tuple(vo._net_bufs), _lib.Workspace.snapshot(dev))
 
     def _load(self, t0):
         vo = self.vo
@@ -246,6 +258,7 @@ class Ramp_vo:
         self._corr_buf = None       # [1, capacity, 896] correlation rows (882 used)
         self._corrt_buf = None      # [1, capacity, 1008] correlation rows in the tile layout
         self._ugraphs = {}          # (E, window, buffer parity) -> _UpdateGraph
+        self._capture_stream = None # warm-up + capture stream of the update graphs (keys their scratch buffers)
         self._ukey_prev, self._ukey_hist = None, []
         self.graph_kernel_launches = 0   # librampvo kernels executed through CUDA-graph replays
 
@@ -544,8 +557,13 @@ class Ramp_vo:
         target = coords[..., self.P // 2, self.P // 2] + delta.float()
         weight = filter_features(confidences=weight, target=target,
                                  data_shape=(self.ht // 4, self.wd // 4))
-        fastba.BA(self.poses, self.patches, self.intrinsics, target, weight, self.lmbda, ii, jj, kk,
-                  t0, t1, M=self.M, iterations=2, eff_impl=False, plan=plans.plan_k, t0_dev=t0_dev)
+        try:
+            fastba.BA(self.poses, self.patches, self.intrinsics, target, weight, self.lmbda, ii, jj, kk,
+                      t0, t1, M=self.M, iterations=2, eff_impl=False, plan=plans.plan_k, t0_dev=t0_dev)
+        except RuntimeError as e:           # only a BA failure is non-fatal, like the reference (:302-306)
+            if torch.cuda.is_current_stream_capturing():
+                raise
+            print(f"WARNING: BA failed...{e}")
         return new_net, weight
 
     def _new_plans(self, ii, jj, kk):
@@ -568,22 +586,15 @@ class Ramp_vo:
         self._ukey_prev = key
         if (self.use_graphs and self.autocast and E > 0 and self.network.update._fused_ready()
                 and (repeat or (key + (self._net_bufs[0].data_ptr(),)) in self._ugraphs)):
-            try:
-                self._update_graphed(E, t0, self.n)
-            except RuntimeError as e:   # BA failure is non-fatal, like the reference (:302-306)
-                print(f"WARNING: BA failed...{e}")
+            self._update_graphed(E, t0, self.n)
         else:
             plans = self._graph_plans()
             other = self._net_other(E)
-            try:
-                new_net, weight = self._update_body(self.ii, self.jj, self.kk, self.net, other, plans,
-                                                    t0, self.n)
-                if new_net.data_ptr() != other.data_ptr():
-                    other.copy_(new_net)   # generic (non-fused) path returned its own tensor
-                self._net_swap(E)
-                self.last_weight = weight
-            except RuntimeError as e:
-                print(f"WARNING: BA failed...{e}")
+            new_net, weight = self._update_body(self.ii, self.jj, self.kk, self.net, other, plans, t0, self.n)
+            if new_net.data_ptr() != other.data_ptr():
+                other.copy_(new_net)   # generic (non-fused) path returned its own tensor
+            self._net_swap(E)
+            self.last_weight = weight
         pts = pops.point_cloud_centers(SE3(self.poses), self.patches[:, :self.m], self.intrinsics,
                                        self.ix[:self.m])
         self.points_[:len(pts)] = pts

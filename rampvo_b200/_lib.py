@@ -155,14 +155,23 @@ def fmap_view(t):
 
 
 class Workspace:
-    """Grow-only device scratch buffer, one per (device, tag)."""
+    """Grow-only device scratch buffers, one per (device, tag, stream): two Ramp_vo instances on different streams
+    never share scratch.  A CUDA graph that captured a buffer must keep it alive: `snapshot()` returns the tensors
+    currently registered for a device so that the graph object can hold references (a buffer that later grows is
+    replaced here, but the captured one stays valid for as long as its graph lives)."""
     _bufs = {}
 
     @classmethod
     def get(cls, device, nbytes, tag="default"):
-        key = (str(device), tag)
+        dev = torch.device(device)
+        key = (str(dev), tag, torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0)
         buf = cls._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
             cls._bufs[key] = buf
         return buf
+
+    @classmethod
+    def snapshot(cls, device):
+        d = str(torch.device(device))
+        return [b for (dev, _, _), b in cls._bufs.items() if dev == d]

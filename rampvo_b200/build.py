@@ -47,9 +47,11 @@ def find_nvcc():
     return nvcc
 
 
-def build_library(force=False, verbose=False):
-    """Compile every .cu under csrc/ into one shared library; returns its path."""
-    fp = _fingerprint()
+def build_library(force=False, verbose=False, debug=False):
+    """Compile every .cu under csrc/ into one shared library; returns its path.  debug=True adds -DRVO_DEBUG
+    (the RVO_CORR_DBG / RVO_UP_TRACE isolation switches of tools/corr_bench.py and tools/gemm_bench.py; with them
+    set the kernels produce WRONG results by design, so the release library compiles them out)."""
+    fp = _fingerprint() + ("-debug" if debug else "")
     if not force and os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:
             if fh.read().strip() == fp:
@@ -61,7 +63,8 @@ def build_library(force=False, verbose=False):
     os.makedirs(bdir, exist_ok=True)
     for src in _sources():
         obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = ([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DRVO_DEBUG"] if debug else []) +
+               ["-c", src, "-o", obj])
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
         objs.append(obj)
     for src, p in procs:
@@ -78,4 +81,4 @@ def build_library(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

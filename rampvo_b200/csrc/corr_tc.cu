@@ -383,7 +383,12 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
 corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__ TcTmap tm1,
                      const __half* __restrict__ gmap, const TcHdr* __restrict__ hdr,
                      const TcRow* __restrict__ rows, const int32_t* __restrict__ total_blocks,
-                     __half* __restrict__ out, int dbg) {
+                     __half* __restrict__ out, int dbg_arg) {
+#ifdef RVO_DEBUG
+  const int dbg = dbg_arg;          // -DRVO_DEBUG builds only (python -m rampvo_b200.build --debug)
+#else
+  constexpr int dbg = 0;            // release library: every debug branch below is compiled out
+#endif
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bfull[2], bempty[2], afull[kTmaAStages], aempty[kTmaAStages], tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
@@ -759,8 +764,12 @@ extern "C" int rvo_corr_tiles(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, co
                                               out_ld, R, w.rowbin, w.rowrank, w.rowstart, w.blkstart, w.cnt, w.tot, w.rows,
                                               w.hdr);
   RVO_LAUNCH_CHECK("tc_bin_scatter_kernel");
+#ifdef RVO_DEBUG
   const char* dbg_s = getenv("RVO_CORR_DBG");      // debugging aid: see the kernel's dbg bits
   const int dbg = dbg_s ? atoi(dbg_s) : 0;
+#else
+  const int dbg = 0;                               // the release library never reads the environment
+#endif
   RVO_CHECK_ARG((int64_t)fmap1->N * fmap1->sN < 0x7fffffff, "rvo_corr_tiles: fmap1 too large for 32-bit offsets");
   TcTmap tm[kTcMaxLevels];
   for (int l = 0; l < kTcMaxLevels; l++) {

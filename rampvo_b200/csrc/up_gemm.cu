@@ -42,7 +42,12 @@ template <bool kRelu>
 __global__ void __launch_bounds__(kUgThreads, 1)
 up_linear_kernel(const __half* __restrict__ X, int64_t ldx, const __grid_constant__ TcTmap tmw,
                  const __half* __restrict__ bias, int M, int n_slices, __half* __restrict__ Y,
-                 int64_t ldy, int trace) {
+                 int64_t ldy, int trace_arg) {
+#ifdef RVO_DEBUG
+  const int trace = trace_arg;      // -DRVO_DEBUG builds only
+#else
+  constexpr int trace = 0;          // release library: trace stamps and the store-skipping mode are compiled out
+#endif
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t wfull[kUgKB], xfull[kUgStages], xempty[kUgStages], tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
@@ -232,7 +237,11 @@ extern "C" int rvo_up_linear(const void* x16, int64_t ldx, const void* w16, cons
   int rc = make_tmap_2d_f16(w16, N, K, K, kUgN, &tmw, "rvo_up_linear(w)");
   if (rc != RVO_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+#ifdef RVO_DEBUG
   const int trace = getenv("RVO_UP_TRACE") ? atoi(getenv("RVO_UP_TRACE")) : 0;
+#else
+  const int trace = 0;
+#endif
   if (relu) {
     RVO_CUDA(cudaFuncSetAttribute(up_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUgSmemBytes));
     up_linear_kernel<true><<<kNumSMs, kUgThreads, kUgSmemBytes, st>>>((const __half*)x16, ldx, tmw, (const __half*)bias16,
