@@ -272,6 +272,16 @@ int rvo_ba_forward_dyn(float* poses, float* patches, const float* intrinsics, co
                        const int32_t* t0_dev, int iterations, void* ws, int64_t ws_bytes,
                        void* stream);
 
+/* rvo_ba_forward_dyn with the target formation of ramp/Ramp_vo.py:288-296 folded into the edge load:
+ *   target[e] = coords[e, :, P/2, P/2] + delta[e]        (coords [E,2,P,P]: the reprojected patches)
+ *   weight[e] = 0 where target lies outside [0,wd] x [0,ht]   (filter_features, ramp/utils.py:557-570)
+ * weight_out (optional, [E,2]) receives the filtered confidences (Ramp_vo.last_weight). */
+int rvo_ba_forward_fused(float* poses, float* patches, const float* intrinsics, const float* coords,
+                         const float* delta, const float* weight, float ht, float wd, float* weight_out,
+                         const float* lmbda, const int64_t* ii, const int64_t* jj, const void* plan, int E,
+                         int64_t n_patches, int P, int n_free, const int32_t* t0_dev, int iterations,
+                         void* ws, int64_t ws_bytes, void* stream);
+
 /* One Gauss-Newton iteration in three steps, split where a patch graph sharded by source frame
  * needs its all-reduce:
  *   rvo_ba_plan      once per graph: sort / group the edges into `ws`;
@@ -359,6 +369,57 @@ int rvo_up_gated_tail(const float* x32, const void* a16, const void* r16, int E,
                       const float* gamma, const float* beta, float* out32, void* out16,
                       const float* Wd, const float* bd, const float* Ww, const float* bw, float* delta,
                       float* weight, void* stream);
+
+/* ---- SingleScale encoder front end (csrc/scene_lstm.cu) ----------------------------------------- */
+
+/* ramp/extractor.py:233-261 (MergerLSTMsceneEncoder.forward) for one event stack [Ce,H,W] + one image [Ci,H,W]
+ * (fp32, planar): per-pixel nn.LSTM step for both modalities with the (h, c) state carried across calls, the
+ * events/image presence tests (any(x != 0)) evaluated on the device, the shared 1x1 super-state convolution.
+ *   params       packed fp32 block of rvo_scene_lstm_params_floats(Ce, Ci) floats:
+ *                events  W_ih [4h,Ce] | W_hh [4h,h] | b_ih + b_hh [4h];  image likewise;  superstate W [h,2h] | b [h]
+ *   state_ev/im  [2,h,H*W] fp32 (h then c), super_state [h,H*W] fp32: read unless `first`, always written
+ *   flags        2 x int32 device scratch (presence flags of this call)
+ *   out16        fp16 channels-last [H,W,16]: the new super state, channel 15 zero (h = 15) */
+int rvo_scene_lstm_params_floats(int Ce, int Ci);
+int rvo_scene_lstm_forward(const float* params, int Ce, int Ci, const float* events, const float* image, int H,
+                           int W, float* state_ev, float* state_im, float* super_state, int32_t* flags, int first,
+                           void* out16, void* stream);
+
+/* ---- per-frame glue (csrc/frame_ops.cu) ------------------------------------------------------- */
+
+/* Event-biased patch selection: ramp/utils.py:186-226 (get_coords_from_topk_events) with nms_image
+ * (:157-183).  events [C,H,W] fp32 (one event stack), H and W multiples of 4 -> coords [M,2] fp32 =
+ * (idx / H' as torch's true division, idx % H') of the top-M cells of the transposed, NMS-filtered mean
+ * |event| map, ordered like torch.topk on CUDA (value descending, ties by ascending flat index).
+ * border: border_suppression_size; nms: odd window (non_max_supp_rad, 0 = off).
+ * ws: rvo_select_ws_bytes(H, W) bytes of device scratch. */
+int64_t rvo_select_ws_bytes(int H, int W);
+int rvo_select_patches(const float* events, int C, int H, int W, int M, int border, int nms, float* coords,
+                       void* ws, int64_t ws_bytes, void* stream);
+
+/* Pyramid level 2 (ramp/Ramp_vo.py:381, F.avg_pool2d(fmap, 4, 4)) on a channels-last map [H,W,C] ->
+ * [H/4,W/4,C]; fp32 accumulation, one rounding. */
+int rvo_pyramid_level2(const void* fmap, int dtype, int H, int W, int C, void* out, void* stream);
+
+/* Up to 8 device-to-device copies in one launch: the ring-buffer slot writes of a new frame
+ * (ramp/Ramp_vo.py:374-381).  src / dst / bytes are HOST arrays of n entries. */
+int rvo_copy_segments(const void* const* src, void* const* dst, const int64_t* bytes, int n, void* stream);
+
+/* The state writes of a new frame (ramp/Ramp_vo.py:345-372) in one launch: tstamps[n] = counter,
+ * intrinsics[n] = intr4 (HOST array, already / RES), index[n+1,:] = n+1, index_map[n+1] = m_next,
+ * colors[n] = uint8((clr[:, [2,1,0]] + 0.5) * 127.5), patches[n] = patches_new with the inverse depth set to
+ * depth_rand[m] (median_frames == 0; null keeps the staged value) or to the lower median of the depths of the
+ * previous `median_frames` frames (torch.median semantics, :370-371). */
+int rvo_frame_commit(const float* patches_new, const float* clr, const float* depth_rand, float* patches,
+                     int64_t* tstamps, float* intrinsics, int64_t* index, int64_t* index_map, uint8_t* colors,
+                     const float* intr4, int n, int M, int P, int N, int64_t counter, int64_t m_next,
+                     int median_frames, void* stream);
+
+/* utils/transformers.py:128-161 (EventToStack_Numpy): events in arrival order (x, y uint16 pixel, p polarity
+ * value) -> [bins,H,W] stack; bin = int32(float32(bins * i) / N), out-of-image events dropped, the sum cast to
+ * int8.  stack_f32 (required) is the tensor the encoder consumes; stack_i8 (optional) the int8 stack itself. */
+int rvo_event_stack(const uint16_t* x, const uint16_t* y, const float* p, int64_t n_events, int bins, int H,
+                    int W, float* stack_f32, int8_t* stack_i8, void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,8 @@ Same constructor, `__call__(tstamp, input_tensor, intrinsics)`, `update()`, `key
 Python keeps what the reference keeps in Python: ring-buffer index math, edge-list append/remove,
 the motion model on two SE3 elements, keyframe decisions.
 """
+import ctypes
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -23,7 +25,7 @@ from . import _lib, altcorr, fastba, lietorch
 from . import projective_ops as pops
 from .lietorch import SE3
 from .net import GraphPlans, VONet
-from .vo_utils import filter_features, flatmeshgrid, preprocess_input
+from .vo_utils import copy_segments, filter_features, flatmeshgrid, preprocess_input, pyramid_level2
 
 
 class _PatchifyGraph:
@@ -88,9 +90,11 @@ class _PatchifyGraph:
             fmap, gmap, imap, patches, _, clr = vo.network.patchify(
                 input_=(self.ev, self.im, self.mask), patches_per_image=vo.M, event_bias=vo.event_bias,
                 reinit_hidden=False, gmap_out=gslot)
-        f = fmap[0, 0]
-        self.f1.copy_(f.permute(1, 2, 0))
-        self.f2.copy_(F.avg_pool2d(f[None].float(), 4, 4)[0].permute(1, 2, 0))
+        f = fmap[0, 0].permute(1, 2, 0)             # channels-last storage: this view is contiguous
+        if not f.is_contiguous():
+            f = f.contiguous()
+        self.f1.copy_(f)
+        self.f2.copy_(pyramid_level2(f if f.dtype == self.f2.dtype else f.to(self.f2.dtype)))
         self.imap.copy_(imap.view(vo.M, vo.DIM))
         self.patches.copy_(patches)
         self.clr.copy_(clr)
@@ -553,13 +557,24 @@ class Ramp_vo:
                 before_update()                           # join the branch that built `plans`
             new_net, (delta, weight, _) = self.network.update(net_in, ctx, corr, None, ii, jj, kk,
                                                               plans=plans, net_out=net_out)
-        weight = weight.float()
-        target = coords[..., self.P // 2, self.P // 2] + delta.float()
-        weight = filter_features(confidences=weight, target=target,
-                                 data_shape=(self.ht // 4, self.wd // 4))
+        fused = (delta.dtype == torch.float32 and weight.dtype == torch.float32 and delta.is_contiguous()
+                 and weight.is_contiguous() and coords.is_contiguous())
         try:
-            fastba.BA(self.poses, self.patches, self.intrinsics, target, weight, self.lmbda, ii, jj, kk,
-                      t0, t1, M=self.M, iterations=2, eff_impl=False, plan=plans.plan_k, t0_dev=t0_dev)
+            if fused:
+                # target formation + filter_features (Ramp_vo.py:288-296) happen inside the BA kernels' edge load
+                if t0_dev is None:
+                    t0_dev = torch.tensor([t0], dtype=torch.int32, device=self.device)
+                    t1 = t1 - t0
+                wf = torch.empty_like(weight)
+                fastba.BA_fused(self.poses, self.patches, self.intrinsics, coords, delta, weight, self.ht // 4,
+                                self.wd // 4, self.lmbda, ii, jj, plans.plan_k, t1, t0_dev, 2, weight_out=wf)
+                weight = wf
+            else:
+                weight = weight.float()
+                target = coords[..., self.P // 2, self.P // 2] + delta.float()
+                weight = filter_features(confidences=weight, target=target, data_shape=(self.ht // 4, self.wd // 4))
+                fastba.BA(self.poses, self.patches, self.intrinsics, target, weight, self.lmbda, ii, jj, kk,
+                          t0, t1, M=self.M, iterations=2, eff_impl=False, plan=plans.plan_k, t0_dev=t0_dev)
         except RuntimeError as e:           # only a BA failure is non-fatal, like the reference (:302-306)
             if torch.cuda.is_current_stream_capturing():
                 raise
@@ -636,7 +651,8 @@ class Ramp_vo:
         events, images, mask = input_
         mask_l = torch.as_tensor(mask).reshape(-1).tolist()
         graphable = (self.use_graphs and events.shape[1] == 1 and images.shape[1] == 1 and mask_l == [True]
-                     and tuple(events.shape[-2:]) == (self.ht, self.wd))
+                     and tuple(events.shape[-2:]) == (self.ht, self.wd)
+                     and self.network.input_mode == "MultiScale")    # the SingleScale encoder runs eagerly
         if graphable:
             if self._pgraph is None:
                 self.sync()
@@ -645,31 +661,40 @@ class Ramp_vo:
             g.run(events, images, reinit=(tstamp == 0))      # writes only the graph's staging buffers
         self.sync()     # pipeline mode: the previous frame's keyframe step, overlapped with the encoder graph
         slot = self.n % self.mem
+        gslot_store = self._gmap_store[slot * M:(slot + 1) * M]
         if graphable:
-            self._gmap_store[slot * M:(slot + 1) * M] = g.gmap
-            patches, clr, imap_new, f1_new, f2_new = g.patches.clone(), g.clr, g.imap, g.f1, g.f2
+            patches, clr = g.patches, g.clr
+            ring = [(g.gmap, gslot_store), (g.imap, self.imap_[slot]), (g.f1, self._fmap1_store[slot]),
+                    (g.f2, self._fmap2_store[slot])]
         else:
             if not (events.is_cuda and images.is_cuda):
                 input_ = (events.to(self.device), images.to(self.device), mask)
-            gslot = self._gmap_store[slot * M:(slot + 1) * M].permute(0, 3, 1, 2)[None]   # [1,M,128,P,P]
+            gslot = gslot_store.permute(0, 3, 1, 2)[None]                                  # [1,M,128,P,P]
             with torch.autocast("cuda", enabled=self.autocast):
                 fmap, gmap, imap, patches, _, clr = self.network.patchify(
                     input_=input_, patches_per_image=M, event_bias=self.event_bias,
                     reinit_hidden=True if tstamp == 0 else False, gmap_out=gslot)
             if fmap is None:
                 return      # events only: the super state was updated, the VO is not
-            f = fmap[0, 0]                                               # [128,h,w]
-            imap_new = imap.view(M, self.DIM)
-            f1_new = f.permute(1, 2, 0)
-            f2_new = F.avg_pool2d(f[None].float(), 4, 4)[0].permute(1, 2, 0)
+            f1_new = fmap[0, 0].permute(1, 2, 0).to(self.fdtype).contiguous()             # [h,w,128]
+            ring = [(imap.reshape(M, self.DIM).to(self.fdtype).contiguous(), self.imap_[slot]),
+                    (f1_new, self._fmap1_store[slot]), (pyramid_level2(f1_new), self._fmap2_store[slot])]
 
+        # state writes of the new frame (Ramp_vo.py:345-372) in one launch: tstamps / intrinsics / index rows,
+        # colours, depth initialisation (uniform draw, or the median of the last 3 frames) and patches_[n]
         self.tlist.append(tstamp)
-        self.tstamps_[self.n] = self.counter
-        self.intrinsics_[self.n] = torch.as_tensor(intrinsics, device=self.device) / self.RES
-        self.index_[self.n + 1] = self.n + 1
-        self.index_map_[self.n + 1] = self.m + self.M
-        clr = (clr[0, :, [2, 1, 0]] + 0.5) * (255.0 / 2)
-        self.colors_[self.n] = clr.to(torch.uint8)
+        intr = torch.as_tensor(intrinsics, dtype=torch.float32).reshape(-1).tolist() \
+            if not (torch.is_tensor(intrinsics) and intrinsics.is_cuda) else intrinsics.float().cpu().tolist()
+        intr4 = (ctypes.c_float * 4)(*[v / self.RES for v in intr])
+        rnd = None if self.is_initialized else torch.rand_like(patches[:, :, 2, 0, 0, None, None]).contiguous()
+        pn = patches if patches.dtype == torch.float32 and patches.is_contiguous() else patches.float().contiguous()
+        cl = clr if clr.dtype == torch.float32 and clr.is_contiguous() else clr.float().contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().rvo_frame_commit(
+                _lib.ptr(pn), _lib.ptr(cl), _lib.ptr(rnd), _lib.ptr(self.patches_), _lib.ptr(self.tstamps_),
+                _lib.ptr(self.intrinsics_), _lib.ptr(self.index_), _lib.ptr(self.index_map_), _lib.ptr(self.colors_),
+                intr4, self.n, M, P, self.N, self.counter, self.m + M, 3 if self.is_initialized else 0,
+                _lib.stream_ptr(self.device)), "rvo_frame_commit")
 
         if self.n > 1:
             if self.cfg.MOTION_MODEL == 'DAMPED_LINEAR':
@@ -680,15 +705,8 @@ class Ramp_vo:
             else:
                 self.poses_[self.n] = self.poses_[self.n - 1]
 
-        patches[:, :, 2] = torch.rand_like(patches[:, :, 2, 0, 0, None, None])
-        if self.is_initialized:
-            patches[:, :, 2] = torch.median(self.patches_[self.n - 3:self.n, :, 2])
-        self.patches_[self.n] = patches
-
-        # network attributes: gmap is already in its ring slot; fmap pyramid written channels-last
-        self.imap_[slot] = imap_new.to(self.fdtype)
-        self._fmap1_store[slot] = f1_new.to(self.fdtype)
-        self._fmap2_store[slot] = f2_new.to(self.fdtype)
+        # network attributes: gmap / imap / fmap pyramid into their ring slots (Ramp_vo.py:376-381), one launch
+        copy_segments(ring)
 
         self.counter += 1
         if self.n > 0 and not self.is_initialized:

@@ -214,6 +214,13 @@ __device__ __forceinline__ void linearise_edge(const float* __restrict__ poses,
 constexpr int kBaWarps = 8;
 constexpr int kBaThreads = kBaWarps * 32;
 
+// optional fused target formation (rvo_ba_forward_fused): coords [E,2,P,P] of the reprojected patches
+struct BaFuse {
+  const float* coords;
+  float ht, wd;
+  float* weight_out;    // filtered confidences [E,2] (Ramp_vo.last_weight), may be null
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -232,7 +239,7 @@ ba_assemble_kernel(const int32_t* __restrict__ count, const int32_t* __restrict_
                    const float* __restrict__ weight, const float* __restrict__ lmbda,
                    const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, int P, int t0_arg,
                    const int32_t* __restrict__ t0_dev, int N, int cap, float* __restrict__ Sy_g,
-                   float* __restrict__ Qg, float* __restrict__ ug, float* __restrict__ Eg) {
+                   float* __restrict__ Qg, float* __restrict__ ug, float* __restrict__ Eg, const BaFuse fz) {
   extern __shared__ float sm[];
   const int t0 = t0_dev ? t0_dev[0] : t0_arg;   // device-side window start keeps CUDA graphs replayable
   const int n6 = 6 * N, ld = n6 + 1;
@@ -269,8 +276,19 @@ ba_assemble_kernel(const int32_t* __restrict__ count, const int32_t* __restrict_
         if (act) {
           const int e = perm[s];
           const int64_t i = ii[e], j = jj[e];
-          const float2 tg = reinterpret_cast<const float2*>(target)[e];
-          const float2 wg = reinterpret_cast<const float2*>(weight)[e];
+          float2 tg = reinterpret_cast<const float2*>(target)[e];
+          float2 wg = reinterpret_cast<const float2*>(weight)[e];
+          if (fz.coords) {
+            // `target` holds the update operator's delta: target = reprojected patch centre + delta
+            // (Ramp_vo.py:289) and filter_features (utils.py:557-570) zeroes the confidence of targets outside
+            // [0, wd] x [0, ht] — both folded into this load instead of ~10 elementwise launches
+            const float* c = fz.coords + (size_t)e * 2 * PP;
+            tg.x += c[ctr];
+            tg.y += c[PP + ctr];
+            const bool bad = (tg.x < 0.0f) | (tg.x > fz.wd) | (tg.y < 0.0f) | (tg.y > fz.ht);
+            if (bad) { wg.x = 0.0f; wg.y = 0.0f; }
+            if (fz.weight_out) reinterpret_cast<float2*>(fz.weight_out)[e] = wg;
+          }
           linearise_edge(poses, patches, fx, fy, cx, cy, i, j, k, PP, ctr, tg.x, tg.y, wg.x, wg.y, L);
           ip = (int)(i - t0);
           jp = (int)(j - t0);
@@ -632,7 +650,7 @@ static int ba_assemble(const BaWs& w, const float* poses, const float* patches,
                        const float* intrinsics, const float* target, const float* weight,
                        const float* lmbda, const int64_t* ii, const int64_t* jj, int E, int64_t cap,
                        int P, int t0, int t1, float* Sy_out, cudaStream_t st,
-                       const int32_t* t0_dev = nullptr) {
+                       const int32_t* t0_dev = nullptr, BaFuse fz = BaFuse{nullptr, 0.f, 0.f, nullptr}) {
   const int N = t1 - t0, n6 = 6 * N;
   if (n6 > 0) RVO_CUDA(cudaMemsetAsync(Sy_out, 0, (size_t)n6 * (n6 + 1) * sizeof(float), st));
   const bool smem_s = assemble_smem_bytes(n6, true) <= kSmemMax;
@@ -646,11 +664,11 @@ static int ba_assemble(const BaWs& w, const float* poses, const float* patches,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     ba_assemble_kernel<true><<<grid, kBaThreads, smem, st>>>(
         w.plan.count, w.plan.perm, w.plan.seg_start, w.plan.kx, poses, patches, intrinsics, target,
-        weight, lmbda, ii, jj, P, t0, t0_dev, N, (int)cap, Sy_out, w.Qg, w.ug, w.Eg);
+        weight, lmbda, ii, jj, P, t0, t0_dev, N, (int)cap, Sy_out, w.Qg, w.ug, w.Eg, fz);
   } else {
     ba_assemble_kernel<false><<<grid, kBaThreads, smem, st>>>(
         w.plan.count, w.plan.perm, w.plan.seg_start, w.plan.kx, poses, patches, intrinsics, target,
-        weight, lmbda, ii, jj, P, t0, t0_dev, N, (int)cap, Sy_out, w.Qg, w.ug, w.Eg);
+        weight, lmbda, ii, jj, P, t0, t0_dev, N, (int)cap, Sy_out, w.Qg, w.ug, w.Eg, fz);
   }
   RVO_LAUNCH_CHECK("ba_assemble_kernel");
   if (n6 > 0) {
@@ -795,7 +813,8 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
                            const int64_t* ii, const int64_t* jj, const int64_t* kk, int E,
                            int64_t n_poses, int64_t n_patches, int P, int PPF, int t0, int t1,
                            int iterations, int eff_impl, const void* ext_plan, void* ws,
-                           int64_t ws_bytes, void* stream, const int32_t* t0_dev = nullptr) {
+                           int64_t ws_bytes, void* stream, const int32_t* t0_dev = nullptr,
+                           BaFuse fz = BaFuse{nullptr, 0.f, 0.f, nullptr}) {
   (void)PPF; (void)eff_impl;  // block-sparse E is the only implementation; results do not depend on it
   int rc = ba_check("rvo_ba_forward", poses, patches, intrinsics, E, P, t0, t1);
   if (rc != RVO_OK) return rc;
@@ -816,8 +835,10 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
     if (rc != RVO_OK) return rc;
   }
   for (int it = 0; it < iterations; it++) {
+    BaFuse f = fz;
+    if (it > 0) f.weight_out = nullptr;      // the filtered confidences do not change between iterations
     rc = ba_assemble(w, poses, patches, intrinsics, target, weight, lmbda, ii, jj, E, cap, P, t0, t1,
-                     w.Sy, st, t0_dev);
+                     w.Sy, st, t0_dev, f);
     if (rc != RVO_OK) return rc;
     rc = ba_solve(w, poses, patches, w.Sy, cap, P, t0, t1, st, t0_dev);
     if (rc != RVO_OK) return rc;
@@ -873,6 +894,20 @@ extern "C" int rvo_ba_forward_dyn(float* poses, float* patches, const float* int
   RVO_CHECK_ARG(t0_dev && n_free >= 0, "rvo_ba_forward_dyn: needs the device-side window start");
   return ba_forward_impl(poses, patches, intrinsics, target, weight, lmbda, ii, jj, nullptr, E, 0,
                          n_patches, P, 0, 0, n_free, iterations, 0, plan, ws, ws_bytes, stream, t0_dev);
+}
+
+extern "C" int rvo_ba_forward_fused(float* poses, float* patches, const float* intrinsics,
+                                    const float* coords, const float* delta, const float* weight,
+                                    float ht, float wd, float* weight_out, const float* lmbda,
+                                    const int64_t* ii, const int64_t* jj, const void* plan, int E,
+                                    int64_t n_patches, int P, int n_free, const int32_t* t0_dev,
+                                    int iterations, void* ws, int64_t ws_bytes, void* stream) {
+  RVO_CHECK_ARG(plan || E == 0, "rvo_ba_forward_fused: null plan");
+  RVO_CHECK_ARG(t0_dev && n_free >= 0, "rvo_ba_forward_fused: needs the device-side window start");
+  RVO_CHECK_ARG(coords || E == 0, "rvo_ba_forward_fused: null coords");
+  BaFuse fz{coords, ht, wd, weight_out};
+  return ba_forward_impl(poses, patches, intrinsics, delta, weight, lmbda, ii, jj, nullptr, E, 0,
+                         n_patches, P, 0, 0, n_free, iterations, 0, plan, ws, ws_bytes, stream, t0_dev, fz);
 }
 
 extern "C" int rvo_ba_forward_host(float* poses, float* patches, const float* intrinsics,

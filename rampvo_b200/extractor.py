@@ -137,6 +137,133 @@ class MultiScaleBasicEncoder4(nn.Module):
         return self.conv3(torch.cat((x, x_down4), dim=1)) * out_scale
 
 
+class BasicEncoder4(nn.Module):
+    """extractor.py:60-130 (norm_fn 'instance' / 'none'): conv 7x7 s2 -> norm -> relu -> 2 ResBlocks(32) ->
+    ResBlock(32->64, s2) + ResBlock(64) -> 1x1 conv.  InstanceNorm2d has no parameters, so the state-dict keys
+    are the convolutions only, exactly like the reference's."""
+
+    def __init__(self, output_dim=128, norm_fn='instance', channel_dim=15):
+        super().__init__()
+        if norm_fn not in ('instance', 'none'):
+            raise NotImplementedError("norm_fn %r: the RAMP encoders use 'instance' / 'none'" % norm_fn)
+        self.instance = norm_fn == 'instance'
+        self.conv1 = nn.Conv2d(channel_dim, DIM, kernel_size=7, stride=2, padding=3)
+        self.layer1 = nn.Sequential(ResidualBlock(DIM, DIM, norm_fn, 1), ResidualBlock(DIM, DIM, norm_fn, 1))
+        self.layer2 = nn.Sequential(ResidualBlock(DIM, 2 * DIM, norm_fn, 2), ResidualBlock(2 * DIM, 2 * DIM, norm_fn, 1))
+        self.conv2 = nn.Conv2d(2 * DIM, output_dim, kernel_size=1)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+
+    def forward_fast(self, x16, out_scale=1.0):
+        """x16 [1,16,H,W] fp16 channels-last (15 channels + a zero pad, see MergerLSTMsceneEncoder)"""
+        w = getattr(self.conv1, "_w16p", None)
+        if w is None:   # first-layer weights padded to 16 input channels
+            wt = F.pad(self.conv1.weight.detach(), (0, 0, 0, 0, 0, x16.shape[1] - self.conv1.in_channels))
+            w = self.conv1._w16p = (wt.half().contiguous(memory_format=CL), self.conv1.bias.detach().half())
+        with torch.autocast("cuda", enabled=False):
+            t = F.conv2d(x16, w[0], w[1], stride=2, padding=3)
+        t = t if t.is_contiguous(memory_format=CL) else t.contiguous(memory_format=CL)
+        x = _apply(t, _stats(t) if self.instance else None)
+        x = self.layer2(self.layer1(x))
+        return _conv16(self.conv2, x, out_scale)
+
+    def forward(self, x):
+        """x [b,n,C,H,W] -> [b,n,out,H/4,W/4] (extractor.py:107-126)"""
+        b, n, c, h, w = x.shape
+        x = self.conv1(x.view(b * n, c, h, w))
+        if self.instance:
+            x = F.instance_norm(x)
+        x = self.conv2(self.layer2(self.layer1(F.relu(x))))
+        return x.view(b, n, *x.shape[1:])
+
+
+class MergerLSTMsceneEncoder(nn.Module):
+    """extractor.py:187-269, the SingleScale RAMP encoder (BASELINE.json configs[0]): two full-resolution per-pixel
+    LSTMs whose (h, c) state is CARRIED across calls (:242-243), one shared 1x1 super-state convolution applied for
+    the events and then for the image when they are non-zero (:253-258), two BasicEncoder4 CNNs."""
+
+    def __init__(self, evs_ch_dim=5, img_ch_dim=3, output_lstm_dim=15, output_dim_f=128, output_dim_i=384,
+                 norm_fn_fmap="instance", norm_fn_imap="none", kernel_size_superstate=1):
+        super().__init__()
+        if kernel_size_superstate != 1:
+            raise NotImplementedError("kernel_size_superstate %d: every caller uses 1 (net.py:110)" % kernel_size_superstate)
+        self.hidden_size = output_lstm_dim
+        self.events_convlstm = nn.LSTM(input_size=evs_ch_dim, hidden_size=output_lstm_dim, batch_first=True)
+        self.image_convlstm = nn.LSTM(input_size=img_ch_dim, hidden_size=output_lstm_dim, batch_first=True)
+        self.superstate_encoder = nn.Conv2d(2 * output_lstm_dim, output_lstm_dim, kernel_size=1, padding=0)
+        self.fmap_encoder = BasicEncoder4(output_dim_f, norm_fn_fmap, output_lstm_dim)
+        self.imap_encoder = BasicEncoder4(output_dim_i, norm_fn_imap, output_lstm_dim)
+        self.states_events, self.states_image, self.super_state = None, None, None
+        self._dev_state = None          # fused path: (state_ev, state_im, super, flags) device buffers
+
+    def reset_state(self):
+        self.states_events, self.states_image, self.super_state = None, None, None
+        self._dev_state = None
+
+    def _packed_params(self, device):
+        c = getattr(self, "_pp", None)
+        if c is not None and c.device == device:
+            return c
+        parts = []
+        for lstm in (self.events_convlstm, self.image_convlstm):
+            parts += [lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0 + lstm.bias_hh_l0]
+        h = self.hidden_size
+        parts += [self.superstate_encoder.weight.reshape(h, 2 * h), self.superstate_encoder.bias]
+        buf = torch.cat([t.detach().float().reshape(-1) for t in parts]).contiguous().to(device)
+        n = _lib.lib().rvo_scene_lstm_params_floats(self.events_convlstm.input_size, self.image_convlstm.input_size)
+        if n != buf.numel():
+            raise RuntimeError("scene LSTM parameter block: %d floats, library expects %d" % (buf.numel(), n))
+        self._pp = buf
+        return buf
+
+    def _forward_fast(self, events, images, reinit_hidden, out_scale):
+        """one event stack + one image: rvo_scene_lstm_forward (2 launches) + the two channels-last CNNs"""
+        ev = events[0, 0].float().contiguous()
+        im = images[0, 0].float().contiguous()
+        H, W = ev.shape[-2:]
+        dev, h = ev.device, self.hidden_size
+        st = self._dev_state
+        first = reinit_hidden or st is None or st[0].shape[-1] != H * W
+        if st is None or st[0].shape[-1] != H * W:
+            st = self._dev_state = (torch.zeros(2, h, H * W, device=dev), torch.zeros(2, h, H * W, device=dev),
+                                    torch.zeros(h, H * W, device=dev), torch.zeros(2, dtype=torch.int32, device=dev))
+        out = torch.empty(1, 16, H, W, dtype=torch.float16, device=dev).contiguous(memory_format=CL)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().rvo_scene_lstm_forward(
+                _lib.ptr(self._packed_params(dev)), ev.shape[0], im.shape[0], _lib.ptr(ev), _lib.ptr(im), H, W,
+                _lib.ptr(st[0]), _lib.ptr(st[1]), _lib.ptr(st[2]), _lib.ptr(st[3]), int(first), _lib.ptr(out),
+                _lib.stream_ptr(dev)), "rvo_scene_lstm_forward")
+        fmap = self.fmap_encoder.forward_fast(out, out_scale)
+        imap = self.imap_encoder.forward_fast(out, out_scale)
+        return fmap[None], imap[None], None
+
+    def forward(self, events, images, reinit_hidden=False, out_scale=1.0):
+        """events [1,T,Ce,H,W], images [1,T,3,H,W] -> fmap [1,T,128,H/4,W/4], imap [1,T,384,H/4,W/4], lstm states"""
+        if _fast(events) and events.shape[1] == 1 and images.shape[1] == 1 and events.shape[0] == 1:
+            return self._forward_fast(events, images, reinit_hidden, out_scale)
+        if reinit_hidden:
+            self.states_events, self.states_image, self.super_state = None, None, None
+        B, T, Ce, H, W = events.shape
+        Ti, Ci = images.shape[1], images.shape[2]
+        ev_seq = events.permute(0, 3, 4, 1, 2).contiguous().view(B * H * W, T, Ce)
+        im_seq = images.permute(0, 3, 4, 1, 2).contiguous().view(B * H * W, Ti, Ci)
+        oe, self.states_events = self.events_convlstm(ev_seq, self.states_events)
+        oi, self.states_image = self.image_convlstm(im_seq, self.states_image)
+        oe = oe.view(B, H, W, T, self.hidden_size).permute(0, 3, 4, 1, 2)
+        oi = oi.view(B, H, W, Ti, self.hidden_size).permute(0, 3, 4, 1, 2)
+        outs = []
+        for t in range(min(T, Ti)):
+            for data, present in ((oe[0, t], bool(torch.any(events[:, t] != 0))),
+                                  (oi[0, t], bool(torch.any(images[:, t] != 0)))):
+                if present:
+                    prev = torch.zeros_like(data) if self.super_state is None else self.super_state
+                    self.super_state = self.superstate_encoder(torch.cat((prev, data), dim=0)[None])[0]
+            outs.append(self.super_state)
+        ss = torch.stack(outs, dim=0)[None]
+        return self.fmap_encoder(ss) * out_scale, self.imap_encoder(ss) * out_scale, [(oe, oi)]
+
+
 class LSTMEncoder(nn.Module):
     """extractor.py:314-390: strided conv (k = s+1, stride s, pad 1; 1x1 at s <= 1) followed by the
     per-pixel LSTM cell evaluated for one step from a zero state."""

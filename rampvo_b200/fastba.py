@@ -86,6 +86,40 @@ def BA(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, M,
     return []
 
 
+def BA_fused(poses, patches, intrinsics, coords, delta, weight, ht, wd, lmbda, ii, jj, plan, n_free, t0_dev,
+             iterations, weight_out=None):
+    """fastba.BA with the caller-side target formation of ramp/Ramp_vo.py:288-296 folded into the kernels' edge
+    load: target = coords[..., P//2, P//2] + delta, weight zeroed where the target leaves [0,wd] x [0,ht]
+    (ramp/utils.py:557-570).  coords [1,E,2,P,P] fp32; delta / weight [1,E,2] fp32; plan: rvo_graph_plan(kk, jj);
+    the window is [t0_dev[0], t0_dev[0] + n_free).  weight_out [1,E,2] receives the filtered confidences."""
+    poses = getattr(poses, "data", poses)
+    _lib.require_cuda(poses, patches, intrinsics, coords, delta, weight, lmbda, ii, jj, plan, t0_dev)
+    P = patches.shape[-1]
+    pv = _flat(poses, "poses", (7,))
+    qv = _flat(patches, "patches", (3, P, P))
+    kv = _flat(intrinsics, "intrinsics", (4,))
+    E = ii.numel()
+    cv = _flat(coords, "coords", (2, P, P))
+    dv = _flat(delta, "delta", (2,))
+    wv = _flat(weight, "weight", (2,))
+    if cv.shape[0] != E or dv.shape[0] != E or wv.shape[0] != E or jj.numel() != E:
+        raise RuntimeError("fastba.BA_fused: coords/delta/weight/ii/jj disagree on the number of edges")
+    if weight_out is not None:
+        weight_out = _flat(weight_out, "weight_out", (2,))
+    lm = lmbda.to(torch.float32).contiguous().view(-1)
+    ii, jj = _i64(ii), _i64(jj)
+    L = _lib.lib()
+    nb = L.rvo_ba_ws_bytes(E, qv.shape[0], max(int(n_free), 0))
+    ws = _lib.Workspace.get(pv.device, nb, "ba")
+    with torch.cuda.device(pv.device):
+        _lib.check(L.rvo_ba_forward_fused(_lib.ptr(pv), _lib.ptr(qv), _lib.ptr(kv), _lib.ptr(cv), _lib.ptr(dv),
+                                          _lib.ptr(wv), float(ht), float(wd), _lib.ptr(weight_out), _lib.ptr(lm),
+                                          _lib.ptr(ii), _lib.ptr(jj), _lib.ptr(plan), E, qv.shape[0], P,
+                                          int(n_free), _lib.ptr(t0_dev), int(iterations), _lib.ptr(ws), ws.numel(),
+                                          _lib.stream_ptr()), "rvo_ba_forward_fused")
+    return []
+
+
 def reproject(poses, patches, intrinsics, ii, jj, kk):
     """cuda_ba.reproject (ba.cpp:49-57, ba_cuda.cu:379-429,585-617): coords [1,E,2,P,P]; no depth
     clamp and intrinsics[0] for every frame, exactly like the reference kernel."""

@@ -20,7 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib, altcorr, fastba
-from .extractor import MultiScaleMergerDoubleNet
+from .extractor import MergerLSTMsceneEncoder, MultiScaleMergerDoubleNet
 from .vo_utils import coords_from_topk_events, get_channel_dim
 
 DIM = 384
@@ -275,14 +275,18 @@ class Patchifier(nn.Module):
         super().__init__()
         self.input_mode = input_mode
         self.P = patch_size
-        if input_mode != "MultiScale":
-            raise NotImplementedError("input_mode %r: only the MultiScale RAMP encoder is built "
-                                      "(BASELINE.json configs[1..4])" % input_mode)
         evs, img = channels_dim
-        self.encoder = MultiScaleMergerDoubleNet(evs_ch_dim=evs, img_ch_dim=img, lstm_dim=16,
-                                                 output_dim_f=128, output_dim_i=DIM,
-                                                 norm_fn_fmap="instance", norm_fn_imap="none",
-                                                 norm_superstate=False)
+        if input_mode == "SingleScale":       # net.py:101-111
+            self.encoder = MergerLSTMsceneEncoder(evs_ch_dim=evs, img_ch_dim=img, output_lstm_dim=15,
+                                                  output_dim_f=128, output_dim_i=DIM, norm_fn_fmap="instance",
+                                                  norm_fn_imap="none", kernel_size_superstate=1)
+        elif input_mode == "MultiScale":      # net.py:112-123
+            self.encoder = MultiScaleMergerDoubleNet(evs_ch_dim=evs, img_ch_dim=img, lstm_dim=16,
+                                                     output_dim_f=128, output_dim_i=DIM,
+                                                     norm_fn_fmap="instance", norm_fn_imap="none",
+                                                     norm_superstate=False)
+        else:
+            raise ValueError(f"Invalid input mode: {input_mode}")
 
     def forward(self, input_, patches_per_image=80, reinit_hidden=False, disps=None, event_bias=False,
                 gradient_bias=False, gmap_out=None):
@@ -298,8 +302,12 @@ class Patchifier(nn.Module):
             with torch.cuda.stream(side):
                 coords = coords_from_topk_events(events, patches_per_image, non_max_supp_rad=11)
         # fmap / 4, imap / 4 (net.py:152-153) are folded into the encoders' last 1x1 convolutions
-        fmap, imap = self.encoder(events=events, images=images, mask=mask, reinit_hidden=reinit_hidden,
-                                  out_scale=0.25)
+        if self.input_mode == "SingleScale":   # net.py:141-145: no mask, the presence tests are data-dependent
+            fmap, imap, _ = self.encoder(events=events, images=images, reinit_hidden=reinit_hidden, out_scale=0.25)
+            mask_l = [True] * fmap.shape[1]
+        else:
+            fmap, imap = self.encoder(events=events, images=images, mask=mask, reinit_hidden=reinit_hidden,
+                                      out_scale=0.25)
         if coords is not None:
             cur.wait_stream(side)
             if not torch.cuda.is_current_stream_capturing():

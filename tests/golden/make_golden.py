@@ -194,6 +194,37 @@ def main():
     coords = ns["get_coords_from_topk_events"](events=ev, patches_per_image=96, border_suppression_size=0,
                                                non_max_supp_rad=11)
     np.savez_compressed(os.path.join(HERE, "patch_selection.npz"), coords=coords.numpy())
+    # ---- (g) SingleScale encoder (ramp/extractor.py:187-269), three frames with carried LSTM state, fp32 CPU
+    from rampvo_b200.extractor import MergerLSTMsceneEncoder as MySS
+    torch.manual_seed(GI.ENCODER_SEED)
+    mine = MySS(5, 3)
+    ref_ss = extractor.MergerLSTMsceneEncoder(evs_ch_dim=5, img_ch_dim=3, output_lstm_dim=15, output_dim_f=128,
+                                              output_dim_i=384, norm_fn_fmap="instance", norm_fn_imap="none",
+                                              kernel_size_superstate=1)
+    ref_ss.load_state_dict(mine.state_dict(), strict=True)
+    ref_ss.eval()
+    outs = {}
+    with torch.no_grad():
+        for f, (ev, im) in enumerate(GI.single_scale_inputs()):
+            fmap, imap, _ = ref_ss(events=ev, images=im, reinit_hidden=(f == 0))
+            outs["fmap_%d" % f] = fmap[0, 0].numpy().astype(np.float32)
+            outs["imap_%d" % f] = imap[0, 0].numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "single_scale_encoder.npz"), **outs)
+
+    # ---- (f) 5-bin event stack (utils/transformers.py:128-161 EventToStack_Numpy), run as is
+    data_stub = types.ModuleType("data")
+    data_stub.Events = object
+    sys.modules["data"] = data_stub
+    spec = importlib.util.spec_from_file_location("ref_transformers", os.path.join(REF, "utils", "transformers.py"))
+    tr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tr)
+
+    class _Ev:
+        def __len__(self):
+            return len(self.x)
+    e = _Ev()
+    e.x, e.y, e.p, e.height, e.width = GI.event_stream()
+    np.savez_compressed(os.path.join(HERE, "event_stack.npz"), stack=tr.EventToStack_Numpy(5)(e))
     print("golden fixtures written:", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 

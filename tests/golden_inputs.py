@@ -64,3 +64,30 @@ def selection_events(device="cpu"):
     ys, xs = torch.meshgrid(torch.arange(480.0), torch.arange(640.0), indexing="ij")
     blob = torch.exp(-((xs - 300) ** 2 + (ys - 200) ** 2) / (2 * 150.0 ** 2))
     return (ev * (0.25 + blob)).to(device)
+
+
+def event_stream(n=120000, ht=96, wd=128, seed=80):
+    """raw events in arrival order like data/events.py: x, y uint16, p int8 in {-1, +1}; a hot cluster makes some
+    cells collect > 127 events so that the int8 cast (utils/transformers.py:159) wraps"""
+    rng = np.random.default_rng(seed)
+    x = rng.integers(0, wd, n).astype(np.uint16)
+    y = rng.integers(0, ht, n).astype(np.uint16)
+    p = (rng.integers(0, 2, n) * 2 - 1).astype(np.int8)
+    hot = rng.random(n) < 0.02
+    x[hot], y[hot], p[hot] = 7, 5, 1
+    return x, y, p, ht, wd
+
+
+def single_scale_inputs(device="cpu", ht=32, wd=48):
+    """three (event stack, image) pairs; the second image is all zero so that the data-dependent
+    `image_is_present` branch of ramp/extractor.py:254-258 is exercised"""
+    g = torch.Generator().manual_seed(81)
+    frames = []
+    for f in range(3):
+        ev = torch.poisson(torch.full((1, 1, 5, ht, wd), 0.3), generator=g)
+        ev = ev * (torch.randint(0, 2, ev.shape, generator=g) * 2 - 1)
+        im = torch.rand(1, 1, 3, ht, wd, generator=g) * 2 - 0.5
+        if f == 1:
+            im = torch.zeros_like(im)
+        frames.append((ev.to(device), im.to(device)))
+    return frames

@@ -123,3 +123,34 @@ def test_oracle_torch_corr_matches_numpy_corr():
                                     torch.from_numpy(coords), torch.from_numpy(kk), torch.from_numpy(jj),
                                     chunk=17)
     assert np.abs(got.numpy() - exp).max() < 1e-5
+
+
+def test_oracle_event_stack_matches_reference_fixture():
+    """oracle.event_stack vs the reference's EventToStack_Numpy output (int8, incl. wrapped hot cells)"""
+    z = np.load(os.path.join(G, "event_stack.npz"))["stack"]
+    x, y, p, ht, wd = GI.event_stream()
+    got = O.event_stack(x, y, p, 5, ht, wd)
+    assert got.dtype == z.dtype == np.int8 and (got == z).all()
+    assert z.min() < -30       # the hot cell collects ~480 (+1) events per bin: the int8 cast wrapped it negative
+
+
+def test_oracle_selection_matches_reference_fixture():
+    """oracle.select_patches (value descending, ties by ascending index) vs get_coords_from_topk_events"""
+    z = np.load(os.path.join(G, "patch_selection.npz"))["coords"]
+    ev = GI.selection_events()
+    got = O.select_patches(ev[0, 0].numpy(), 96, 0, 11)
+    assert got.dtype == np.float32 and (got == z[0]).all()
+
+
+def test_single_scale_encoder_matches_reference_on_cpu():
+    """MergerLSTMsceneEncoder (SingleScale, BASELINE.json configs[0]) vs ramp/extractor.py:187-269: carried per-pixel
+    LSTM state over three calls, absent image on the second"""
+    from rampvo_b200.extractor import MergerLSTMsceneEncoder
+    z = np.load(os.path.join(G, "single_scale_encoder.npz"))
+    torch.manual_seed(GI.ENCODER_SEED)
+    enc = MergerLSTMsceneEncoder(5, 3).eval()
+    with torch.no_grad():
+        for f, (ev, im) in enumerate(GI.single_scale_inputs()):
+            fmap, imap, _ = enc(events=ev, images=im, reinit_hidden=(f == 0))
+            assert rel_err(fmap[0, 0].numpy(), z["fmap_%d" % f]) < 1e-5
+            assert rel_err(imap[0, 0].numpy(), z["imap_%d" % f]) < 1e-5
