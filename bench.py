@@ -26,6 +26,14 @@ UNIT = "frames/s"
 WORKLOAD = ("MultiScale RAMP-VO default.yaml (96 patches/frame, lifetime 13, removal 22, opt window 10), "
             "synthetic TartanEvent-shape 640x480 event-stack + image stream, steady-state graph")
 SETUP_FRAMES = 40          # the graph reaches its steady state (E = 45 312) at frame 34
+WORKLOADS = {
+    "default": (WORKLOAD, 40),
+    # BASELINE.json configs[2]: deep BA window, E = 660 600 edges once frame 75 has been added
+    "precise": ("MultiScale RAMP-VO precise.yaml (300 patches/frame, lifetime 33, removal 42, opt window 30), "
+                "synthetic TartanEvent-shape 640x480 event-stack + image stream, steady-state graph", 80),
+    "fast": ("MultiScale RAMP-VO fast.yaml (48 patches/frame, lifetime 11, removal 16, opt window 7), synthetic "
+             "TartanEvent-shape 640x480 event-stack + image stream, steady-state graph", 32),
+}
 
 
 def _peaks():
@@ -76,18 +84,19 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
-def build_vo(device, seed=1234):
+def build_vo(device, seed=1234, config="default", world_size=1, rank=0):
     import torch
     from rampvo_b200.Ramp_vo import Ramp_vo
     from rampvo_b200.config import preset
     from rampvo_b200.net import VONet
     torch.manual_seed(seed)                      # evaluate.py:40 seeds everything with 1234
     train_cfg = {"event_bias": True, "input_mode": "MultiScale", "num_event_bins": 5}
-    cfg = preset("default")
+    cfg = preset(config)
     cfg.KEYFRAME_THRESH = 0.0                    # never drop a keyframe: the no-drop upper-bound graph
     # pipeline: the keyframe step of frame t (its decision is a device->host read) is finished at the start
     # of call t+1, after that frame's encoder graph was launched — same work, overlapped (Ramp_vo.sync())
-    vo = Ramp_vo(cfg, VONet(train_cfg), train_cfg, ht=480, wd=640, device=device, pipeline=True)
+    vo = Ramp_vo(cfg, VONet(train_cfg), train_cfg, ht=480, wd=640, device=device, pipeline=True,
+                 world_size=world_size, rank=rank)
     # random weights: pin the data-dependent initialisation gate (Ramp_vo.py:385)
     vo.motion_probe = lambda: torch.tensor(10.0)
     return vo
@@ -109,8 +118,14 @@ def run_ours(args):
     assert L.rvo_device_cc() >= 100, "bench.py expects a Blackwell GPU (sm_100a kernels)"
 
     K, W = args.steps, args.warmup
+    global SETUP_FRAMES
+    workload, SETUP_FRAMES = WORKLOADS[args.config]
+    # N > 1: "sharded" = ONE stream whose patch graph is sharded by source frame across the ranks, [S|y] all-reduced
+    # per Gauss-Newton iteration (BASELINE.json configs[3], strong scaling); "replicas" = one independent stream
+    # per GPU (weak scaling, no data-path collective)
+    sharded = world > 1 and args.mode == "sharded"
     n_frames = SETUP_FRAMES + 2 * (W + K)
-    seq = synth.SyntheticSequence(seed=rank, device=dev)
+    seq = synth.SyntheticSequence(seed=0 if sharded else rank, device=dev)
     intr = seq.intrinsics
     frames = [seq.frame(t) for t in range(n_frames)]                       # resident in HBM
     host = [(e.cpu().pin_memory(), i.cpu().pin_memory()) for (e, i, _) in frames[SETUP_FRAMES + W + K:]]
@@ -156,7 +171,7 @@ def run_ours(args):
         return ms, launches, sampler.summary()
 
     with torch.no_grad():
-        vo = build_vo(dev)
+        vo = build_vo(dev, config=args.config, world_size=world if sharded else 1, rank=rank if sharded else 0)
         state["vo"] = vo
         for t in range(SETUP_FRAMES):
             vo(t, frames[t], intr)
@@ -176,6 +191,14 @@ def run_ours(args):
         ms_e2e, _, _ = timed(step_e2e, SETUP_FRAMES + W + K)
         finite = bool(torch.isfinite(vo.poses_[:vo.n]).all())
 
+        E_local = int(vo.ii.numel())
+        coll = (vo.collective_calls, vo.collective_bytes)
+        if sharded:     # the roofline launch below is measured on the FULL graph: gather nothing, rebuild it
+            from rampvo_b200 import synth as _s
+            M_, life, rem, _ = _s.CONFIGS[args.config]
+            gi, gj, gk = _s.replay_graph(M_, life, rem, vo.n)
+            vo.ii, vo.jj, vo.kk = [torch.from_numpy(x).to(dev) for x in (gi, gj, gk)]
+            E_dev = int(vo.ii.numel())
         # roofline of the dominant hand-written kernel (altcorr lookup), timed live on this stream
         coords = vo.reproject()
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -198,7 +221,7 @@ def run_ours(args):
         for (h, w) in ((120, 160), (30, 40)):
             alg += min(Fr * 128 * h * w * 2, E * 100 * 128 * 2)
         del out, flush
-        stages_ours = our_stages(vo, frames) if (rank == 0 and world == 1) else None
+        stages_ours = our_stages(vo, frames) if (rank == 0 and world == 1 and args.config == "default") else None
         state["sd"] = {k: v.detach().clone() for k, v in vo.network.state_dict().items()}
 
     peaks, which = _peaks()
@@ -208,18 +231,27 @@ def run_ours(args):
             traffic = json.load(fh).get("dram_bytes_per_launch")
     except Exception:
         pass
-    fps = world * K / (ms_dev * 1e-3)
-    fps_e2e = world * K / (ms_e2e * 1e-3)
+    streams = 1 if sharded else world
+    fps = streams * K / (ms_dev * 1e-3)
+    fps_e2e = streams * K / (ms_e2e * 1e-3)
+    M_cfg = vo.M
+    par = "single GPU"
+    if world > 1 and sharded:
+        par = ("ONE stream, patch graph sharded by source frame over %d ranks (this rank: %d of %d edges); per update "
+               "2 NCCL all-reduces of [S|y] (%d B each) + 1 depth exchange + 1 keyframe-flow all-reduce; encoder "
+               "replicated" % (world, E_local, E_dev, 6 * (vo.n - max(vo.n - vo.cfg.OPTIMIZATION_WINDOW, 1)) *
+                               (6 * (vo.n - max(vo.n - vo.cfg.OPTIMIZATION_WINDOW, 1)) + 1) * 4))
+    elif world > 1:
+        par = "one independent stream per GPU"
     line = {
         "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 features / f32 geometry+BA", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "edges": E_dev, "patches_per_frame": 96, "ba_iterations": 2,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
+        "vs_baseline": None, "dtype": "f16 features / f32 geometry+BA", "data": "synthetic",
+        "config": {"workload": workload, "edges": E_dev, "patches_per_frame": M_cfg, "ba_iterations": 2,
                    "keyframe_thresh": 0.0, "weights": "random init, seed 1234",
                    "pipeline": "keyframe step of frame t overlapped with the encoder graph of frame t+1 (Ramp_vo pipeline=True)",
                    "l2": "per-step working set (167 MB feature rings + 80 MB corr volume) exceeds the 126 MB L2",
-                   "parallelism": "one independent stream per GPU" if world > 1 else "single GPU",
-                   "poses_finite": finite},
+                   "parallelism": par, "poses_finite": finite},
         "e2e": {"value": fps_e2e, "unit": UNIT,
                 "h2d_bytes_per_step": int(host[0][0].numel() * 4 + host[0][1].numel() * 4),
                 "d2h_bytes_per_step": 28},
@@ -231,14 +263,17 @@ def run_ours(args):
                      "frac": alg / corr_s / 1e9 / peaks["hbm_gbs"], "traffic": traffic,
                      "peak_source": which, "algorithmic_bytes": alg, "launch_us": corr_s * 1e6},
     }
-    if rank == 0 and world == 1:
+    if sharded:
+        line["collectives"] = {"calls_total": coll[0], "bytes_total": coll[1], "frames": vo.counter,
+                               "note": "per rank, since the start of the stream (setup + warm-up + timed frames)"}
+    if rank == 0 and world == 1 and stages_ours is not None:
         line["stages"] = stages_ours
-    if rank == 0 and world == 1 and not args.no_ref_gpu:
+    if rank == 0 and world == 1 and not args.no_ref_gpu and args.config == "default":
         try:
             line["ref_gpu"] = ref_gpu_block(state["sd"], frames, intr, min(K, 20), 3, dev)
         except Exception as e:   # a baseline leg must never take the product line down
             line["ref_gpu"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "default":
         line["cpu_baseline"] = cpu_reference(steps=2, warmup=0, budget_s=20.0)["cpu_baseline"]
     if rank == 0:
         print(json.dumps(line))
@@ -422,6 +457,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--config", default="default", choices=sorted(WORKLOADS),
+                    help="VO preset: default.yaml (the metric's configuration), precise.yaml, fast.yaml")
+    ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"],
+                    help="N > 1 only: shard ONE stream's patch graph over the ranks (default, BASELINE.json "
+                         "configs[3]) or run one independent stream per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

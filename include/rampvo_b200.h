@@ -282,6 +282,13 @@ int rvo_ba_forward_fused(float* poses, float* patches, const float* intrinsics, 
                          int64_t n_patches, int P, int n_free, const int32_t* t0_dev, int iterations,
                          void* ws, int64_t ws_bytes, void* stream);
 
+/* rvo_ba_assemble with the fused target formation of rvo_ba_forward_fused (sharded graphs: local edges ->
+ * [S | y] before the all-reduce). */
+int rvo_ba_assemble_fused(const float* poses, const float* patches, const float* intrinsics, const float* coords,
+                          const float* delta, const float* weight, float ht, float wd, float* weight_out,
+                          const float* lmbda, const int64_t* ii, const int64_t* jj, int E, int64_t n_patches, int P,
+                          int t0, int t1, float* Sy, void* ws, int64_t ws_bytes, void* stream);
+
 /* One Gauss-Newton iteration in three steps, split where a patch graph sharded by source frame
  * needs its all-reduce:
  *   rvo_ba_plan      once per graph: sort / group the edges into `ws`;
@@ -388,14 +395,18 @@ int rvo_scene_lstm_forward(const float* params, int Ce, int Ci, const float* eve
 /* ---- per-frame glue (csrc/frame_ops.cu) ------------------------------------------------------- */
 
 /* Event-biased patch selection: ramp/utils.py:186-226 (get_coords_from_topk_events) with nms_image
- * (:157-183).  events [C,H,W] fp32 (one event stack), H and W multiples of 4 -> coords [M,2] fp32 =
- * (idx / H' as torch's true division, idx % H') of the top-M cells of the transposed, NMS-filtered mean
- * |event| map, ordered like torch.topk on CUDA (value descending, ties by ascending flat index).
- * border: border_suppression_size; nms: odd window (non_max_supp_rad, 0 = off).
+ * (:157-183).  events [C,H,W] fp32 (one event stack), H and W multiples of 4; the top-M cells of the transposed,
+ * NMS-filtered mean |event| map.  border: border_suppression_size; nms: odd window (non_max_supp_rad, 0 = off).
+ *   gather_order == 0: coords [M,2] fp32 = (idx * (1/H'), idx % H') — torch's CUDA true division by a scalar
+ *     multiplies by the reciprocal — ordered by value descending, ties by ascending flat index: what torch.topk
+ *     returns on CUDA whenever its final key/value sort is stable (k > 32); idx_out / val_out optional.
+ *   gather_order != 0: idx_out [M] int64 and val_out [M] fp32 in torch.topk's PRE-sort order (values above the
+ *     k-th value by ascending index, then ties with it by ascending index); for k <= 32 torch finishes with an
+ *     unstable bitonic sort, which the caller reproduces by applying the same sort to val_out.  coords unused.
  * ws: rvo_select_ws_bytes(H, W) bytes of device scratch. */
 int64_t rvo_select_ws_bytes(int H, int W);
-int rvo_select_patches(const float* events, int C, int H, int W, int M, int border, int nms, float* coords,
-                       void* ws, int64_t ws_bytes, void* stream);
+int rvo_select_patches(const float* events, int C, int H, int W, int M, int border, int nms, int gather_order,
+                       float* coords, int64_t* idx_out, float* val_out, void* ws, int64_t ws_bytes, void* stream);
 
 /* Pyramid level 2 (ramp/Ramp_vo.py:381, F.avg_pool2d(fmap, 4, 4)) on a channels-last map [H,W,C] ->
  * [H/4,W/4,C]; fp32 accumulation, one rounding. */

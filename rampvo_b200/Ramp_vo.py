@@ -189,7 +189,8 @@ class _UpdateGraph:
             plans = vo._new_plans(self.ii, self.jj, self.kk)
         _, self.weight = vo._update_body(self.ii, self.jj, self.kk, self.net_in, self.net_out, plans,
                                          0, self.n_free, t0_dev=self.t0,
-                                         before_update=lambda: cur.wait_stream(side))
+                                         before_update=lambda: cur.wait_stream(side),
+                                         with_ba=vo.world_size == 1)
 
     def run(self, t0):
         self._load(t0)
@@ -198,8 +199,19 @@ class _UpdateGraph:
 
 
 class Ramp_vo:
-    def __init__(self, cfg, network, train_cfg, ht=480, wd=640, device="cuda", use_graphs=True, pipeline=False):
+    def __init__(self, cfg, network, train_cfg, ht=480, wd=640, device="cuda", use_graphs=True, pipeline=False,
+                 world_size=1, rank=0, group=None):
+        """world_size > 1 (extension): the patch graph is SHARDED across the ranks of a
+        torch.distributed group by source frame — every rank sees the same frames and keeps the full pose /
+        patch / feature state, but only the edges of the frames it owns: reproject, corr, the update operator and
+        the patch blocks of BA are rank-local; per Gauss-Newton iteration the reduced camera system [S | y] is
+        all-reduced (NCCL over NVLink), every rank solves it identically, and the refined depths of the window
+        are exchanged once per update."""
         self.cfg = cfg
+        self.world_size, self.rank, self.group = int(world_size), int(rank), group
+        self._owner = []            # owner rank of every live frame slot (follows frames through keyframe drops)
+        self.collective_bytes = 0   # bytes this rank put through collectives (sharded mode)
+        self.collective_calls = 0
         self.event_bias = train_cfg["event_bias"]
         self.train_cfg = train_cfg
         self.device = torch.device(device)
@@ -492,6 +504,11 @@ class Ramp_vo:
                 _lib.ptr(self.poses_), _lib.ptr(self.patches_), _lib.ptr(self.intrinsics_),
                 _lib.ptr(self.ii), _lib.ptr(self.jj), _lib.ptr(self.kk), self.ii.numel(), self.P, i, j,
                 0.5, _lib.ptr(out4), _lib.stream_ptr(self.device)), "rvo_pair_flow")
+        if self.world_size > 1:     # edges i->j live on owner(i), j->i on owner(j): sum the partial flow sums
+            import torch.distributed as dist
+            dist.all_reduce(out4, op=dist.ReduceOp.SUM, group=self.group)
+            self.collective_bytes += 16
+            self.collective_calls += 1
         return out4
 
     def keyframe(self):
@@ -538,14 +555,19 @@ class Ramp_vo:
                 g[dst] = g[src]
                 self._fmap1_store[dst] = self._fmap1_store[src]
                 self._fmap2_store[dst] = self._fmap2_store[src]
+            if len(self._owner) > k:
+                del self._owner[k]
             self.n -= 1
             self.m -= self.M
         lim = self.n - self.cfg.REMOVAL_WINDOW
         self.remove_factors(self.ii < lim, lambda i, j: i < lim)     # ix[kk] == ii (index_[f] == f)
 
-    def _update_body(self, ii, jj, kk, net_in, net_out, plans, t0, t1, t0_dev=None, before_update=None):
+    def _update_body(self, ii, jj, kk, net_in, net_out, plans, t0, t1, t0_dev=None, before_update=None,
+                     with_ba=True):
         """reproject -> corr -> update operator -> 2 BA iterations on explicit buffers; every
-        host-side scalar is either constant across frames or read from device memory (t0_dev)"""
+        host-side scalar is either constant across frames or read from device memory (t0_dev).
+        with_ba=False (sharded graphs): stops after the update operator and returns
+        (net, (coords, delta, weight)) — BA then runs with its all-reduce outside the captured graph."""
         coords = self.reproject(indicies=(ii, jj, kk))
         with torch.autocast("cuda", enabled=self.autocast):
             if self.autocast and self.P == 3:
@@ -557,6 +579,8 @@ class Ramp_vo:
                 before_update()                           # join the branch that built `plans`
             new_net, (delta, weight, _) = self.network.update(net_in, ctx, corr, None, ii, jj, kk,
                                                               plans=plans, net_out=net_out)
+        if not with_ba:
+            return new_net, (coords, delta.float().contiguous(), weight.float().contiguous())
         fused = (delta.dtype == torch.float32 and weight.dtype == torch.float32 and delta.is_contiguous()
                  and weight.is_contiguous() and coords.is_contiguous())
         try:
@@ -595,6 +619,8 @@ class Ramp_vo:
         E = self.ii.numel()
         t0 = self.n - self.cfg.OPTIMIZATION_WINDOW if self.is_initialized else 1
         t0 = max(t0, 1)
+        if self.world_size > 1:
+            return self._update_sharded(E, t0)
         key = (E, self.n - t0, self._net_cur)
         repeat = key == self._ukey_prev or key in self._ukey_hist   # capture only shapes that recur
         self._ukey_hist = (self._ukey_hist + [self._ukey_prev])[-4:]
@@ -614,6 +640,56 @@ class Ramp_vo:
                                        self.ix[:self.m])
         self.points_[:len(pts)] = pts
 
+    def _update_sharded(self, E, t0):
+        """one recurrent update over THIS rank's edges: reproject / corr / update operator
+        are local (a CUDA graph once the shape recurs); BA = local assembly -> all-reduce of [S | y] -> identical
+        solve on every rank, twice; then the refined depths of the active frames are exchanged."""
+        from . import sharded
+        key = (E, self.n - t0, self._net_cur)
+        repeat = key == self._ukey_prev or key in self._ukey_hist
+        self._ukey_hist = (self._ukey_hist + [self._ukey_prev])[-4:]
+        self._ukey_prev = key
+        P = self.P
+        if E == 0:      # this rank owns no edge yet: it still takes part in the collectives
+            z = torch.zeros(1, 0, 2, device=self.device)
+            coords, delta, weight = torch.zeros(1, 0, 2, P, P, device=self.device), z, z
+        elif (self.use_graphs and self.autocast and self.network.update._fused_ready()
+              and (repeat or (key + (self._net_bufs[0].data_ptr(),)) in self._ugraphs)):
+            gkey = key + (self._net_bufs[0].data_ptr(),)
+            g = self._ugraphs.get(gkey)
+            if g is None:
+                if len(self._ugraphs) >= 8:
+                    self._ugraphs.pop(next(iter(self._ugraphs)))
+                g = self._ugraphs[gkey] = _UpdateGraph(self, E, self.n - t0)
+            g.run(t0)
+            self._net_swap(E)
+            coords, delta, weight = g.weight
+        else:
+            plans = self._graph_plans()
+            other = self._net_other(E)
+            new_net, (coords, delta, weight) = self._update_body(self.ii, self.jj, self.kk, self.net, other, plans,
+                                                                 t0, self.n, with_ba=False)
+            if new_net.data_ptr() != other.data_ptr():
+                other.copy_(new_net)
+            self._net_swap(E)
+        wf = torch.empty_like(weight)
+        n6 = 6 * (self.n - t0)
+        try:
+            sharded.sharded_BA_fused(self.poses, self.patches, self.intrinsics, coords, delta, weight, self.ht // 4,
+                                     self.wd // 4, self.lmbda, self.ii, self.jj, self.kk, t0, self.n, iterations=2,
+                                     weight_out=wf, group=self.group)
+        except RuntimeError as e:
+            print(f"WARNING: BA failed...{e}")
+        self.last_weight = wf
+        self.collective_bytes += 2 * n6 * (n6 + 1) * 4
+        self.collective_calls += 2
+        lo = max(self.n - self.cfg.REMOVAL_WINDOW - 2, 0)
+        sharded.exchange_depths_owned(self.patches_, self._owner, lo, self.n, self.rank, self.group)
+        self.collective_bytes += (self.n - lo) * self.M * P * P * 4
+        self.collective_calls += 1
+        pts = pops.point_cloud_centers(SE3(self.poses), self.patches[:, :self.m], self.intrinsics, self.ix[:self.m])
+        self.points_[:len(pts)] = pts
+
     def _update_graphed(self, E, t0, t1):
         key = (E, t1 - t0, self._net_cur, self._net_bufs[0].data_ptr())
         g = self._ugraphs.get(key)
@@ -629,6 +705,11 @@ class Ramp_vo:
         """patches of frames [n-r, n-1) -> frame n-1 (Ramp_vo.py:312-318): (kk, jj, pair counts)"""
         r = self.cfg.PATCH_LIFETIME
         f0, f1 = max(self.n - r, 0), max(self.n - 1, 0)
+        if self.world_size > 1:     # only the patches of the frames this rank owns
+            fr = [f for f in range(f0, f1) if self._owner[f] == self.rank]
+            base = torch.tensor(fr, dtype=torch.long, device=self.device) * self.M
+            kk = (base[:, None] + torch.arange(self.M, device=self.device)[None]).reshape(-1)
+            return kk, torch.full_like(kk, self.n - 1), {(i, self.n - 1): self.M for i in fr}
         kk = torch.arange(self.M * f0, self.M * f1, device=self.device)
         return kk, torch.full_like(kk, self.n - 1), {(i, self.n - 1): self.M for i in range(f0, f1)}
 
@@ -638,6 +719,9 @@ class Ramp_vo:
         t0 = self.M * max((self.n - 1), 0)
         t1 = self.M * max((self.n - 0), 0)
         j0 = max(self.n - r, 0)
+        if self.world_size > 1 and self.n > 0 and self._owner[self.n - 1] != self.rank:
+            e = torch.zeros(0, dtype=torch.long, device=self.device)
+            return e, e.clone(), {}
         k = torch.arange(t0, t1, device=self.device)
         j = torch.arange(j0, self.n, device=self.device)
         pairs = {(self.n - 1, jf): t1 - t0 for jf in range(j0, self.n)} if t1 > t0 else {}
@@ -714,6 +798,7 @@ class Ramp_vo:
                 self.delta[self.counter - 1] = (self.counter - 2, self.Id[0])
                 return
 
+        self._owner = self._owner[:self.n] + [(self.counter - 1) % self.world_size]
         self.n += 1
         self.m += self.M
         self.append_factors(*self._edges_forw())

@@ -72,7 +72,7 @@ _SIGNATURES = {
     "rvo_ba_forward_fused": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, c_int, _I64,
                                      c_int, c_int, _P, c_int, _P, _I64, _P]),
     "rvo_select_ws_bytes": (_I64, [c_int, c_int]),
-    "rvo_select_patches": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _I64, _P]),
+    "rvo_select_patches": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _I64, _P]),
     "rvo_pyramid_level2": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "rvo_copy_segments": (c_int, [POINTER(_P), POINTER(_P), POINTER(_I64), c_int, _P]),
     "rvo_scene_lstm_params_floats": (c_int, [c_int, c_int]),
@@ -83,6 +83,8 @@ _SIGNATURES = {
     "rvo_ba_plan": (c_int, [_P, _P, c_int, _I64, _I64, c_int, _P, _I64, _P]),
     "rvo_ba_assemble": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, _I64, c_int, c_int, c_int,
                                 _P, _P, _I64, _P]),
+    "rvo_ba_assemble_fused": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, c_int, _I64, c_int,
+                                      c_int, c_int, _P, _P, _I64, _P]),
     "rvo_ba_solve": (c_int, [_P, _P, _P, c_int, _I64, c_int, c_int, c_int, _P, _I64, _P]),
     "rvo_softagg": (c_int, [_P, _P, c_int, _P, c_int, c_int, _I64, _P, c_int, _P]),
     "rvo_expand_add": (c_int, [_P, c_int, _P, c_int, c_int, _P, _P]),

@@ -796,6 +796,27 @@ extern "C" int rvo_ba_assemble(const float* poses, const float* patches, const f
                      t1, Sy ? Sy : w.Sy, (cudaStream_t)stream);
 }
 
+extern "C" int rvo_ba_assemble_fused(const float* poses, const float* patches, const float* intrinsics,
+                                     const float* coords, const float* delta, const float* weight, float ht,
+                                     float wd, float* weight_out, const float* lmbda, const int64_t* ii,
+                                     const int64_t* jj, int E, int64_t n_patches, int P, int t0, int t1, float* Sy,
+                                     void* ws, int64_t ws_bytes, void* stream) {
+  int rc = ba_check("rvo_ba_assemble_fused", poses, patches, intrinsics, E, P, t0, t1);
+  if (rc != RVO_OK) return rc;
+  if (E == 0) {
+    const size_t n6 = 6 * (size_t)(t1 - t0);
+    if (n6 && Sy) RVO_CUDA(cudaMemsetAsync(Sy, 0, n6 * (n6 + 1) * sizeof(float), (cudaStream_t)stream));
+    return RVO_OK;
+  }
+  RVO_CHECK_ARG(coords && delta && weight && lmbda && ii && jj && ws, "rvo_ba_assemble_fused: null pointer");
+  const int64_t cap = patch_cap(E, n_patches);
+  BaWs w = ba_layout(ws, E, cap, t1 - t0);
+  RVO_CHECK_ARG((int64_t)w.total <= ws_bytes, "rvo_ba_assemble_fused: workspace too small");
+  BaFuse fz{coords, ht, wd, weight_out};
+  return ba_assemble(w, poses, patches, intrinsics, delta, weight, lmbda, ii, jj, E, cap, P, t0, t1,
+                     Sy ? Sy : w.Sy, (cudaStream_t)stream, nullptr, fz);
+}
+
 extern "C" int rvo_ba_solve(float* poses, float* patches, const float* Sy, int E, int64_t n_patches,
                             int P, int t0, int t1, void* ws, int64_t ws_bytes, void* stream) {
   int rc = ba_check("rvo_ba_solve", poses, patches, poses, E, P, t0, t1);

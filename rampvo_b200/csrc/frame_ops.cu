@@ -53,7 +53,8 @@ constexpr int kSelMaxM = 1024;
 // sort is stable), coordinates.  Shared memory: two n-float planes + the candidate keys.
 __global__ void __launch_bounds__(kSelThreads, 1)
 sel_topk_kernel(const float* __restrict__ score, int n_rows /*W4*/, int n_cols /*H4*/, int border, int nms,
-                int M, float* __restrict__ coords /*[M,2]*/) {
+                int M, int gather_order, float* __restrict__ coords /*[M,2]*/, long long* __restrict__ idx_out,
+                float* __restrict__ val_out) {
   extern __shared__ float sm[];
   const int n = n_rows * n_cols;
   float* a = sm;                    // scores, then NMS-filtered scores
@@ -164,11 +165,48 @@ sel_topk_kernel(const float* __restrict__ score, int n_rows /*W4*/, int n_cols /
       __syncthreads();
     }
   }
+  if (gather_order) {
+    // torch.topk's PRE-sort order (sbtopk::gatherTopK): values above the k-th value by ascending index, then the
+    // ties with the k-th value by ascending index.  Used for M <= 32, where torch finishes with an unstable
+    // bitonic sort that the caller reproduces by running the same torch sort on these values.
+    const float pv = __uint_as_float((unsigned)(pivot >> 32));
+    unsigned long long k = ~0ull;
+    if (tid < M) {
+      k = top[tid];
+      const unsigned idx = 0xffffffffu - (unsigned)(k & 0xffffffffull);
+      const float v = __uint_as_float((unsigned)(k >> 32));
+      k = ((unsigned long long)(v == pv ? 1u : 0u) << 32) | (unsigned long long)idx;      // (class, index) order
+    }
+    __syncthreads();
+    top[tid] = k;
+    __syncthreads();
+    for (int k2 = 2; k2 <= kSelMaxM; k2 <<= 1) {
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        const int i = tid, l = i ^ j;
+        if (l > i) {
+          const unsigned long long x = top[i], y = top[l];
+          const bool asc = (i & k2) == 0;
+          if (asc ? (x > y) : (x < y)) { top[i] = y; top[l] = x; }
+        }
+        __syncthreads();
+      }
+    }
+    for (int m = tid; m < M; m += kSelThreads) {
+      const unsigned idx = (unsigned)(top[m] & 0xffffffffull);
+      idx_out[m] = (long long)idx;
+      val_out[m] = a[idx];
+    }
+    return;
+  }
+  // rows = indices / H' : torch's CUDA true division by a host scalar multiplies by the reciprocal
+  // (div_true_kernel_cuda: a * (1 / b)), which is what the reference computes on the GPU (utils.py:212)
+  const float inv = __fdiv_rn(1.0f, (float)n_cols);
   for (int m = tid; m < M; m += kSelThreads) {
     const unsigned idx = 0xffffffffu - (unsigned)(top[m] & 0xffffffffull);
-    // rows = indices / H' is torch's true division of an int64 tensor: float(idx) / float(H') (utils.py:212)
-    coords[2 * m] = __fdiv_rn((float)idx, (float)n_cols);
+    coords[2 * m] = __fmul_rn((float)idx, inv);
     coords[2 * m + 1] = (float)(idx % (unsigned)n_cols);
+    if (idx_out) idx_out[m] = (long long)idx;
+    if (val_out) val_out[m] = a[idx];
   }
 }
 
@@ -352,8 +390,11 @@ extern "C" int64_t rvo_select_ws_bytes(int H, int W) {
 }
 
 extern "C" int rvo_select_patches(const float* events, int C, int H, int W, int M, int border, int nms,
-                                  float* coords, void* ws, int64_t ws_bytes, void* stream) {
-  RVO_CHECK_ARG(events && coords && ws, "rvo_select_patches: null pointer");
+                                  int gather_order, float* coords, int64_t* idx_out, float* val_out, void* ws,
+                                  int64_t ws_bytes, void* stream) {
+  RVO_CHECK_ARG(events && ws, "rvo_select_patches: null pointer");
+  RVO_CHECK_ARG(gather_order ? (idx_out && val_out) : (coords != nullptr),
+                "rvo_select_patches: gather order needs idx_out + val_out, sorted order needs coords");
   RVO_CHECK_ARG(C >= 1 && H >= 4 && W >= 4 && H % 4 == 0 && W % 4 == 0, "rvo_select_patches: events [%d,%d,%d]", C, H, W);
   RVO_CHECK_ARG((reinterpret_cast<uintptr_t>(events) & 15u) == 0, "rvo_select_patches: events must be 16-byte aligned");
   const int H4 = H / 4, W4 = W / 4, n = H4 * W4;
@@ -369,7 +410,8 @@ extern "C" int rvo_select_patches(const float* events, int C, int H, int W, int 
   sel_score_kernel<<<cdiv(n, 256), 256, 0, st>>>(events, C, H, W, factor, score);
   RVO_LAUNCH_CHECK("sel_score_kernel");
   RVO_CUDA(cudaFuncSetAttribute(sel_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sel_topk_kernel<<<1, kSelThreads, smem, st>>>(score, W4, H4, border, nms, M, coords);
+  sel_topk_kernel<<<1, kSelThreads, smem, st>>>(score, W4, H4, border, nms, M, gather_order, coords,
+                                                (long long*)idx_out, val_out);
   RVO_LAUNCH_CHECK("sel_topk_kernel");
   return RVO_OK;
 }

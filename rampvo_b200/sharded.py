@@ -88,3 +88,58 @@ def sharded_BA(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0
                        L.rvo_ba_solve(_lib.ptr(pv), _lib.ptr(qv), _lib.ptr(Sy), E, qv.shape[0], P, t0, t1,
                                       _lib.ptr(ws), ws.numel(), st), "rvo_ba_solve")
     return []
+
+
+def exchange_depths_owned(patches_, owners, frame_lo, frame_hi, rank, group=None):
+    """exchange_depths for an explicit per-frame owner list (Ramp_vo keeps one: ownership follows a frame through
+    keyframe removals, which renumber the frames).  patches_ [N, M, 3, P, P]."""
+    if frame_hi <= frame_lo or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    sl = patches_[frame_lo:frame_hi, :, 2]                                   # [F, M, P, P] view
+    mine = torch.tensor([1.0 if o == rank else 0.0 for o in owners[frame_lo:frame_hi]], device=patches_.device,
+                        dtype=sl.dtype).view(-1, 1, 1, 1)
+    buf = (sl * mine).contiguous()
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    sl.copy_(buf)
+
+
+def sharded_BA_fused(poses, patches, intrinsics, coords, delta, weight, ht, wd, lmbda, ii, jj, kk, t0, t1,
+                     iterations=2, weight_out=None, group=None):
+    """sharded_BA with the target formation / filter_features folded into the assembly (rvo_ba_assemble_fused):
+    coords [1,E,2,P,P], delta / weight [1,E,2] of THIS rank's edges.  Collective per iteration: one all-reduce of
+    [S | y] (6N x (6N+1) fp32)."""
+    _lib.require_cuda(poses, patches, intrinsics, coords, delta, weight, lmbda, ii, jj, kk)
+    L = _lib.lib()
+    P = patches.shape[-1]
+    pv, qv, kv = poses.view(-1, 7), patches.view(-1, 3, P, P), intrinsics.view(-1, 4)
+    cv = coords.to(torch.float32).contiguous().view(-1, 2, P, P)
+    dv = delta.to(torch.float32).contiguous().view(-1, 2)
+    wv = weight.to(torch.float32).contiguous().view(-1, 2)
+    lm = lmbda.to(torch.float32).contiguous().view(-1)
+    ii, jj, kk = [t.to(torch.int64).contiguous() for t in (ii, jj, kk)]
+    E, N = ii.numel(), t1 - t0
+    n6 = 6 * N
+    dev = pv.device
+    ws = _lib.Workspace.get(dev, L.rvo_ba_ws_bytes(max(E, 1), qv.shape[0], N), "ba_sharded")
+    Sy = torch.zeros(max(n6, 1), n6 + 1, dtype=torch.float32, device=dev)
+    st = _lib.stream_ptr(dev)
+    with torch.cuda.device(dev):
+        if E:
+            _lib.check(L.rvo_ba_plan(_lib.ptr(kk), _lib.ptr(jj), E, pv.shape[0], qv.shape[0], N,
+                                     _lib.ptr(ws), ws.numel(), st), "rvo_ba_plan")
+        for it in range(iterations):
+            if E:
+                _lib.check(L.rvo_ba_assemble_fused(
+                    _lib.ptr(pv), _lib.ptr(qv), _lib.ptr(kv), _lib.ptr(cv), _lib.ptr(dv), _lib.ptr(wv), float(ht),
+                    float(wd), _lib.ptr(weight_out) if (weight_out is not None and it == 0) else None, _lib.ptr(lm),
+                    _lib.ptr(ii), _lib.ptr(jj), E, qv.shape[0], P, t0, t1, _lib.ptr(Sy), _lib.ptr(ws), ws.numel(),
+                    st), "rvo_ba_assemble_fused")
+            else:
+                Sy.zero_()
+            if n6:
+                reduce_system(Sy, group)
+            _lib.check(L.rvo_ba_solve_poses(_lib.ptr(pv), _lib.ptr(Sy), t0, t1, _lib.ptr(ws), ws.numel(), st)
+                       if E == 0 else
+                       L.rvo_ba_solve(_lib.ptr(pv), _lib.ptr(qv), _lib.ptr(Sy), E, qv.shape[0], P, t0, t1,
+                                      _lib.ptr(ws), ws.numel(), st), "rvo_ba_solve")
+    return []

@@ -72,11 +72,22 @@ def _select_patches_cuda(events, M, border, nms):
     coords = torch.empty(n, M, 2, dtype=torch.float32, device=ev.device)
     nb = L.rvo_select_ws_bytes(H, W)
     ws = _lib.Workspace.get(ev.device, max(nb, 16), "select")
+    # torch.topk on CUDA ends with a key/value sort that is stable for k > 32 (ties by ascending index — done in
+    # the kernel) and an unstable bitonic network for k <= 32: there the kernel returns the pre-sort order and the
+    # very same torch sort is applied, so ties come out exactly as the reference's torch.topk orders them
+    small = M <= 32
+    idx = torch.empty(n, M, dtype=torch.int64, device=ev.device) if small else None
+    val = torch.empty(n, M, dtype=torch.float32, device=ev.device) if small else None
     with torch.cuda.device(ev.device):
         for f in range(n):
-            _lib.check(L.rvo_select_patches(_lib.ptr(ev[f]), C, H, W, M, int(border), int(nms), _lib.ptr(coords[f]),
-                                            _lib.ptr(ws), ws.numel(), _lib.stream_ptr(ev.device)),
-                       "rvo_select_patches")
+            _lib.check(L.rvo_select_patches(_lib.ptr(ev[f]), C, H, W, M, int(border), int(nms), int(small),
+                                            _lib.ptr(coords[f]), _lib.ptr(idx[f]) if small else None,
+                                            _lib.ptr(val[f]) if small else None, _lib.ptr(ws), ws.numel(),
+                                            _lib.stream_ptr(ev.device)), "rvo_select_patches")
+    if small:
+        _, pos = torch.sort(val, dim=-1, descending=True)
+        idx = torch.gather(idx, 1, pos)
+        coords = torch.stack((idx / (H // 4), (idx % (H // 4)).to(torch.float32)), dim=-1)
     return coords
 
 

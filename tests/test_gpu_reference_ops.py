@@ -131,3 +131,108 @@ def test_ba_vs_reference(ref_ba, config, n_frames):
               prob["M"], 2)
     assert (b["poses"] == a["poses"]).all()
     assert rel_err(b["patches"][0, :, 2].cpu().numpy(), a["patches"][0, :, 2].cpu().numpy()) < 1e-4
+
+
+def test_tile_corr_full_size_vs_reference(ref_corr):
+    """The tcgen05 tile kernel (the path Ramp_vo uses) at the FULL default.yaml problem — E = 45 312 edges,
+    120x160 + 30x40 maps, 32-frame ring — directly against the reference's cuda_corr.forward x 2 levels run in
+    fp32 on the same fp16 feature values (= exact products, fp32 accumulation: the ground truth both fp16 paths
+    approximate), in the reference's call order (ramp/Ramp_vo.py:175-182)."""
+    from rampvo_b200 import projective_ops as pops
+    from rampvo_b200.lietorch import SE3
+    prob = synth.make_problem("default", 40, seed=0)
+    M, mem = prob["M"], 32
+    gmap, pyr = synth.make_features(mem, M * mem, seed=0)
+    t = problem_tensors(prob)
+    g_t = torch.from_numpy(gmap).cuda().permute(0, 3, 1, 2)[None]                   # channels-last views
+    p_t = [torch.from_numpy(p).cuda().permute(0, 3, 1, 2)[None] for p in pyr]
+    coords = pops.reproject_cf(SE3(t["poses"]), t["patches"], t["intrinsics"], t["ii"], t["jj"], t["kk"])
+    E = prob["E"]
+    assert E == 45312
+    tiles = altcorr.corr_tiles(g_t, p_t, coords, t["kk"], t["jj"], M * mem, mem)
+    cols, ref_idx = altcorr.tile_layout_index(2)
+    got = torch.empty(E, 882, dtype=torch.float16, device="cuda")
+    got[:, ref_idx.cuda()] = tiles[0][:, cols.cuda()]
+    ii1, jj1 = t["kk"] % (M * mem), t["jj"] % mem
+    g32 = g_t.float().contiguous()
+    c1, = ref_corr.forward(g32, p_t[0].float().contiguous(), coords / 1, ii1, jj1, 3)
+    c2, = ref_corr.forward(g32, p_t[1].float().contiguous(), coords / 4, ii1, jj1, 3)
+    ref = torch.stack([c1, c2], -1).view(E, -1)
+    d = (got.float() - ref).abs()
+    tol = 2.0 ** -10 * ref.abs() + 2e-4                                             # one fp16 rounding of the output
+    assert bool((d <= tol).all()), "max |d| %.3e" % d.max().item()
+    # and the reference's own fp16 path (fp16 accumulation) is further from that ground truth than we are
+    c1h, = ref_corr.forward(g_t.contiguous(), p_t[0].contiguous(), coords / 1, ii1, jj1, 3)
+    c2h, = ref_corr.forward(g_t.contiguous(), p_t[1].contiguous(), coords / 4, ii1, jj1, 3)
+    refh = torch.stack([c1h, c2h], -1).view(E, -1)
+    assert d.max().item() <= (refh.float() - ref).abs().max().item()
+
+
+def test_corr_pyramid_host_variant():
+    """rvo_corr_pyramid_host: every pointer is host memory (the plain C-ABI entry a non-torch caller binds)"""
+    import ctypes
+    from rampvo_b200 import _lib
+    prob = synth.make_problem("cfg1", 8, seed=2)
+    M, mem = prob["M"], 8
+    gmap, pyr = synth.make_features(mem, M * mem, ht=60, wd=80, seed=2)
+    c = O.transform(prob["poses"], prob["patches"], prob["intrinsics"], prob["ii"], prob["jj"], prob["kk"],
+                    dtype=np.float32)[0]
+    coords = np.ascontiguousarray((c * 0.5).transpose(0, 3, 1, 2)).astype(np.float32)   # inside the 60x80 maps
+    E = prob["E"]
+    g_h = torch.from_numpy(gmap).permute(0, 3, 1, 2)                                   # host, channels-last views
+    p_h = [torch.from_numpy(p).permute(0, 3, 1, 2) for p in pyr]
+    out = torch.zeros(E, 882, dtype=torch.float16)
+    fm = _lib.fmap_view(g_h)
+    views = (_lib.FMap * 2)(_lib.fmap_view(p_h[0]), _lib.fmap_view(p_h[1]))
+    sc = (ctypes.c_float * 2)(1.0, 0.25)
+    kk, jj = torch.from_numpy(prob["kk"]), torch.from_numpy(prob["jj"])
+    _lib.check(_lib.lib().rvo_corr_pyramid_host(ctypes.byref(fm), views, sc, 2, coords.ctypes.data, _lib.ptr(kk),
+                                                _lib.ptr(jj), M * mem, mem, E, 3, _lib.ptr(out), _lib.stream_ptr()),
+               "rvo_corr_pyramid_host")
+    sel = np.arange(0, E, 16)
+    exp = O.corr_pyramid(gmap.transpose(0, 3, 1, 2), [p.transpose(0, 3, 1, 2) for p in pyr], coords[sel],
+                         prob["kk"][sel], prob["jj"][sel], M * mem, mem, 3)
+    got = out.float().numpy()[sel]
+    assert (np.abs(got - exp) <= 2.0 ** -10 * np.abs(exp) + 2e-4).all()
+
+
+def test_ba_precise_full_size_vs_reference(ref_ba):
+    """precise.yaml at full size (BASELINE.json configs[2]): E = 660 600 edges, 12 600 patches, 30 free poses
+    (180x180 reduced system) against cuda_ba.forward, with eff_impl False and True on the reference side."""
+    prob = synth.make_problem("precise", 80, seed=5)
+    assert prob["E"] == 660600 and prob["t1"] - prob["t0"] == 30
+    tgt = targets_from_reprojection(prob, O)
+    prob["poses"] = perturb_poses(prob)
+    tg = torch.from_numpy(tgt).cuda()[None]
+    wg = torch.from_numpy(prob["weight"]).cuda()[None]
+    lm = torch.tensor([1e-4], device="cuda")
+    for iters in (1, 2, 4):
+        b = problem_tensors(prob)
+        fastba.BA(b["poses"], b["patches"], b["intrinsics"], tg, wg, lm, b["ii"], b["jj"], b["kk"],
+                  prob["t0"], prob["t1"], prob["M"], iters)
+        for eff in (False, True):
+            a = problem_tensors(prob)
+            ref_ba.forward(a["poses"], a["patches"], a["intrinsics"], tg, wg, lm, a["ii"], a["jj"], a["kk"],
+                           prob["M"], prob["t0"], prob["t1"], iters, eff)
+            ep = rel_err(b["poses"].cpu().numpy(), a["poses"].cpu().numpy())
+            ed = rel_err(b["patches"][0, :, 2].cpu().numpy(), a["patches"][0, :, 2].cpu().numpy())
+            print("[precise BA] iterations %d eff_impl %s: pose rel err %.2e depth rel err %.2e" % (iters, eff, ep, ed))
+            assert ep < 1e-4, (iters, eff, ep)
+            assert ed < 1e-3, (iters, eff, ed)
+
+
+def test_eff_impl_flag_vs_reference_eff_impl(ref_ba):
+    """cuda_ba.forward(..., eff_impl=True) (block-sparse EfficentE, ramp/fastba/block_e.cu) on the default graph"""
+    prob = synth.make_problem("default", 40, seed=6)
+    tgt = targets_from_reprojection(prob, O)
+    prob["poses"] = perturb_poses(prob)
+    tg = torch.from_numpy(tgt).cuda()[None]
+    wg = torch.from_numpy(prob["weight"]).cuda()[None]
+    lm = torch.tensor([1e-4], device="cuda")
+    a, b = problem_tensors(prob), problem_tensors(prob)
+    ref_ba.forward(a["poses"], a["patches"], a["intrinsics"], tg, wg, lm, a["ii"], a["jj"], a["kk"], prob["M"],
+                   prob["t0"], prob["t1"], 2, True)
+    fastba.BA(b["poses"], b["patches"], b["intrinsics"], tg, wg, lm, b["ii"], b["jj"], b["kk"], prob["t0"],
+              prob["t1"], prob["M"], 2, eff_impl=True)
+    assert rel_err(b["poses"].cpu().numpy(), a["poses"].cpu().numpy()) < 1e-4
+    assert rel_err(b["patches"][0, :, 2].cpu().numpy(), a["patches"][0, :, 2].cpu().numpy()) < 1e-3

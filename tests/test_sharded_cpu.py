@@ -80,3 +80,41 @@ def test_partition_is_balanced_on_default_graph():
         counts = [int(sharded.partition_edges(ii, world, r).sum()) for r in range(world)]
         assert sum(counts) == prob["E"]
         assert max(counts) / (prob["E"] / world) < 1.35      # 22 source frames round-robin
+
+
+def test_sharded_edge_rules_partition_the_reference_graph():
+    """Ramp_vo(world_size=G): the forward / backward edges each rank appends (ramp/Ramp_vo.py:312-325 restricted to
+    the frames it owns) are a partition of the single-GPU edge set, every edge sits on the owner of its source
+    frame, and ownership follows a frame through a keyframe removal."""
+    import types
+    from rampvo_b200.Ramp_vo import Ramp_vo
+    from rampvo_b200.config import preset
+    cfg = preset("default")
+    M = 4
+    for world in (2, 3, 8):
+        vos = [types.SimpleNamespace(cfg=cfg, M=M, n=0, counter=0, world_size=world, rank=r, _owner=[],
+                                     device=torch.device("cpu")) for r in range(world)]
+        full = types.SimpleNamespace(cfg=cfg, M=M, n=0, counter=0, world_size=1, rank=0, _owner=[],
+                                     device=torch.device("cpu"))
+        for t in range(20):
+            for v in vos + [full]:
+                v.counter += 1
+                v._owner = v._owner[:v.n] + [(v.counter - 1) % v.world_size]
+                v.n += 1
+            want = set()
+            for fn in (Ramp_vo._edges_forw, Ramp_vo._edges_back):
+                kk, jj, pairs = fn(full)
+                want |= set(zip(kk.tolist(), jj.tolist()))
+                assert sum(pairs.values()) == kk.numel()
+            got = []
+            for v in vos:
+                for fn in (Ramp_vo._edges_forw, Ramp_vo._edges_back):
+                    kk, jj, pairs = fn(v)
+                    assert sum(pairs.values()) == kk.numel()
+                    assert all(v._owner[k // M] == v.rank for k in kk.tolist())
+                    got += list(zip(kk.tolist(), jj.tolist()))
+            assert len(got) == len(set(got)) and set(got) == want
+            if t == 12:     # a keyframe drop renumbers the frames; the owner list shifts with them
+                for v in vos + [full]:
+                    del v._owner[v.n - 4]
+                    v.n -= 1
