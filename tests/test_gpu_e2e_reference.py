@@ -129,10 +129,13 @@ def test_one_update_from_the_reference_state_matches(cfg_name, n_frames):
           % (cfg_name, E, d_net, d_w, moved, dt, dq, dd, dpts))
     # hidden state / weights: both sides run the 21 Linear layers in fp16 (autocast) — the reference accumulates
     # the correlation dot products in fp16 as well (correlation_kernel.cu:121-130), we accumulate in fp32.
-    assert d_net < 3e-2
-    assert d_w < 3e-2
-    # poses after 2 Gauss-Newton iterations driven by those fp16 weights / targets
-    assert dt < 2e-2 and dq < 2e-3
+    # (measured, profiles/r02_e2e_parity.txt: net 6e-4 / 8e-4, weight 4.9e-4 = one fp16 ulp of a sigmoid output)
+    assert d_net < 5e-3
+    assert d_w < 2e-3
+    # poses after 2 Gauss-Newton iterations driven by those fp16 weights / targets (measured: dt 1.6e-5 / 2.8e-5
+    # of the trajectory extent, dq 1e-6 / 2e-6 rad, depths 6e-4 / 1.2e-3)
+    assert dt < 5e-4 and dq < 5e-5
+    assert dd < 1e-2
 
 
 @pytest.mark.parametrize("cfg_name", ["cfg1", "default"])
@@ -159,11 +162,14 @@ def test_free_run_tracks_the_reference(cfg_name):
     t, dt, dq = errs[0]
     assert np.isfinite([e[1] for e in errs]).all()
     if cfg_name == "default":
-        assert dt < 5e-2 and dq < 5e-3, "after the 12 initialisation updates (frame %d)" % t
-        assert max(e[1] for e in errs) < 5e-2 and max(e[2] for e in errs) < 5e-3
-    # cfg1 (32 patches, every pose but the first free, random weights): the 12 chained initialisation updates
-    # amplify the fp16 differences of the two implementations along the gauge directions of a barely constrained
-    # window (the one-update test above bounds a single step at 2e-5); its drift is reported, not asserted.
+        # measured (profiles/r02_e2e_parity.txt): dt 5e-3 right after the initialisation, 2e-3 afterwards; dq 4e-5
+        assert dt < 3e-2 and dq < 1e-3, "after the 12 initialisation updates (frame %d)" % t
+        assert max(e[1] for e in errs) < 3e-2 and max(e[2] for e in errs) < 1e-3
+    else:
+        # cfg1 (32 patches, every pose but the first free, random weights): the 12 chained initialisation updates
+        # amplify the fp16 differences along the gauge directions of a barely constrained window (the one-update
+        # test above bounds a single step at 2e-5).  Measured: dt 1.4e-2, dq 1e-3.
+        assert max(e[1] for e in errs) < 0.15 and max(e[2] for e in errs) < 1e-2
     assert torch.equal(ref.tstamps_[:ref.n], ours.tstamps_[:ours.n])
 
 
