@@ -99,6 +99,7 @@ def build_vo(device, seed=1234, config="default", world_size=1, rank=0):
                  world_size=world_size, rank=rank)
     # random weights: pin the data-dependent initialisation gate (Ramp_vo.py:385)
     vo.motion_probe = lambda: torch.tensor(10.0)
+    vo.inputs_complete = True                    # the resident frames are generated and synchronised up front
     return vo
 
 
@@ -130,7 +131,9 @@ def run_ours(args):
     frames = [seq.frame(t) for t in range(n_frames)]                       # resident in HBM
     host = [(e.cpu().pin_memory(), i.cpu().pin_memory()) for (e, i, _) in frames[SETUP_FRAMES + W + K:]]
     mask = torch.tensor([True])
-    pose_host = torch.empty(7).pin_memory()
+    pose_host = [torch.empty(7).pin_memory() for _ in range(2)]
+    pose_evt = [None, None]
+    torch.cuda.synchronize()                     # every resident frame is complete before the first call
 
     def barrier():
         if world > 1:
@@ -185,10 +188,16 @@ def run_ours(args):
         def step_e2e(t):
             e, i = host[t - (SETUP_FRAMES + W + K)]
             vo(t, (e, i, mask), intr)                                       # pinned HOST buffers: Ramp_vo copies H->D
-            pose_host.copy_(vo.poses_[vo.n - 1], non_blocking=True)
-            torch.cuda.current_stream().synchronize()                      # the caller reads the pose
+            # every frame's pose is read back into a 2-deep pinned ring: the caller consumes pose t-1 while frame t
+            # is in flight (streaming consumer, one frame of latency); the last poses are awaited before the clock stops
+            k = t & 1
+            if pose_evt[k] is not None:
+                pose_evt[k].synchronize()
+            pose_host[k].copy_(vo.poses_[vo.n - 1], non_blocking=True)
+            pose_evt[k] = torch.cuda.Event()
+            pose_evt[k].record()
 
-        ms_e2e, _, _ = timed(step_e2e, SETUP_FRAMES + W + K)
+        ms_e2e, _, _ = timed(step_e2e, SETUP_FRAMES + W + K)    # timed() ends with a device synchronise: all poses landed
         finite = bool(torch.isfinite(vo.poses_[:vo.n]).all())
 
         E_local = int(vo.ii.numel())
@@ -249,7 +258,9 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f16 features / f32 geometry+BA", "data": "synthetic",
         "config": {"workload": workload, "edges": E_dev, "patches_per_frame": M_cfg, "ba_iterations": 2,
                    "keyframe_thresh": 0.0, "weights": "random init, seed 1234",
-                   "pipeline": "keyframe step of frame t overlapped with the encoder graph of frame t+1 (Ramp_vo pipeline=True)",
+                   "pipeline": "encoder graph of frame t+1 runs on its own stream while the update graph / keyframe "
+                               "step of frame t finish (Ramp_vo pipeline=True); e2e: the pose of every frame is copied "
+                               "D->H into a 2-deep pinned ring and consumed one frame later",
                    "l2": "per-step working set (167 MB feature rings + 80 MB corr volume) exceeds the 126 MB L2",
                    "parallelism": par, "poses_finite": finite},
         "e2e": {"value": fps_e2e, "unit": UNIT,

@@ -377,6 +377,20 @@ int rvo_up_gated_tail(const float* x32, const void* a16, const void* r16, int E,
                       const float* Wd, const float* bd, const float* Ww, const float* bw, float* delta,
                       float* weight, void* stream);
 
+/* ---- encoder convolutions on the tensor cores (csrc/conv_tc.cu) --------------------------------- */
+
+/* nn.Conv2d of the RAMP encoder CNNs (ramp/extractor.py:12-13,47,79,88,286: 7x7 s2, 3x3 s1/s2, 1x1 s1/s2) as a
+ * tcgen05 implicit GEMM, channels-last fp16 in / fp32 accumulate / fp16 out:
+ *   src0 [H,W,C0] (+ src1 [H,W,C1]: the input is their channel concatenation, extractor.py:302,309 torch.cat),
+ *   w_packed [Cout, Kpad] fp16 with k = (ky*ks + kx)*(C0+C1) + ci, zero padded to Kpad = rvo_conv2d_kpad(ks, C0+C1),
+ *   bias [Cout] fp32 (or NULL), out [Ho,Wo,Cout] fp16 with Ho = (H + 2 pad - ks)/stride + 1.
+ * stats (optional, [2*Cout] fp32): per-channel sum and sum of squares of the rounded outputs = the statistics pass
+ * of nn.InstanceNorm2d (extractor.py:30-34), in the layout rvo_in_apply consumes; zeroed by this call.
+ * Limits: C0, C1 multiples of 8; Cout a multiple of 16; ks*ks*(C0+C1) <= 832. */
+int rvo_conv2d_kpad(int ks, int Cin);
+int rvo_conv2d_nhwc(const void* src0, int C0, const void* src1, int C1, int H, int W, int ks, int stride, int pad,
+                    const void* w_packed, const float* bias, int Cout, void* out, float* stats, void* stream);
+
 /* ---- SingleScale encoder front end (csrc/scene_lstm.cu) ----------------------------------------- */
 
 /* ramp/extractor.py:233-261 (MergerLSTMsceneEncoder.forward) for one event stack [Ce,H,W] + one image [Ci,H,W]

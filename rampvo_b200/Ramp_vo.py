@@ -52,8 +52,13 @@ class _PatchifyGraph:
         self.state = None
         self.graph = None
         self.copy_stream = torch.cuda.Stream(device=dev)
+        # the encoder graph replays on its OWN stream: frame t+1 is encoded while the recurrent update of frame t
+        # (main stream) is still running — the two only meet at the staging buffers (events `replayed` / `consumed`)
+        self.enc_stream = torch.cuda.Stream(device=dev)
         self.replayed = torch.cuda.Event()
         self.replayed.record(torch.cuda.current_stream(dev))
+        self.consumed = torch.cuda.Event()
+        self.consumed.record(torch.cuda.current_stream(dev))
         # parallel branches of the captured graph: context CNN and patch selection on side streams
         enc.branch_stream = torch.cuda.Stream(device=dev)
         vo.network.patchify.branch_stream = torch.cuda.Stream(device=dev)
@@ -100,31 +105,42 @@ class _PatchifyGraph:
         self.clr.copy_(clr)
 
     def run(self, events, images, reinit):
+        """launch the encoder graph of a new frame on the encoder stream; the caller waits for `replayed` on its own
+        stream before it reads the staging buffers and records `consumed` once it has copied them out"""
         enc = self.vo.network.patchify.encoder
-        if reinit:
-            for b in self.state:
-                b.zero_()
-        else:   # pick up a state left by an eager (events-only) call
-            for b, cur in zip(self.state, enc.super_states):
-                if cur is not None and cur is not b:
-                    b.copy_(cur)
         dev = self.vo.device
         cur = torch.cuda.current_stream(dev)
+        es = self.enc_stream
+        es.wait_event(self.consumed)              # the previous frame's outputs have left the staging buffers
+        with torch.cuda.stream(es):
+            if reinit:
+                for b in self.state:
+                    b.zero_()
+            else:   # pick up a state left by an eager (events-only) call
+                for b, st in zip(self.state, enc.super_states):
+                    if st is not None and st is not b:
+                        es.wait_stream(cur)
+                        b.copy_(st)
         if events.is_cuda and images.is_cuda:
-            self.ev.copy_(events)
-            self.im.copy_(images)
+            # device inputs are ordered after whatever the caller queued on its stream, unless it declares them
+            # complete (vo.inputs_complete: e.g. frames pre-loaded and synchronised) — only then can this frame's
+            # encoder overlap the previous frame's update
+            if not self.vo.inputs_complete:
+                es.wait_stream(cur)
+            with torch.cuda.stream(es):
+                self.ev.copy_(events)
+                self.im.copy_(images)
         else:
-            # host inputs (pinned memory copies asynchronously): H->D on a copy stream, so that in pipeline
-            # mode the transfer of frame t+1 overlaps the recurrent update of frame t still running on the
-            # main stream; the static input buffers are free once the previous replay has finished
+            # host inputs (pinned memory copies asynchronously): H->D on a copy stream
             cs = self.copy_stream
-            cs.wait_event(self.replayed)
+            cs.wait_event(self.replayed)          # the static input buffers are free once the last replay is done
             with torch.cuda.stream(cs):
                 self.ev.copy_(events, non_blocking=True)
                 self.im.copy_(images, non_blocking=True)
-            cur.wait_stream(cs)
-        self.graph.replay()
-        self.replayed.record(cur)
+            es.wait_stream(cs)
+        with torch.cuda.stream(es):
+            self.graph.replay()
+            self.replayed.record(es)
         self.vo.graph_kernel_launches += self.n_kernels
         enc.super_states = list(self.state)
 
@@ -269,6 +285,9 @@ class Ramp_vo:
         # encoder(t+1) while the host does the edge bookkeeping of frame t.  Same work, same results; between
         # calls the public state is the one BEFORE the keyframe step until sync() / terminate() / the next call.
         self.pipeline = pipeline
+        # True: device-resident input tensors handed to __call__ are already complete (produced and synchronised
+        # before the call), so the encoder stream need not wait for the work queued on the caller's stream
+        self.inputs_complete = False
         self._pending_kf = None     # (pinned host buffer, event) of a keyframe step that was begun
         self._pgraph = None         # _PatchifyGraph, captured at the first frame
         self._corr_buf = None       # [1, capacity, 896] correlation rows (882 used)
@@ -747,6 +766,7 @@ class Ramp_vo:
         slot = self.n % self.mem
         gslot_store = self._gmap_store[slot * M:(slot + 1) * M]
         if graphable:
+            torch.cuda.current_stream(self.device).wait_event(g.replayed)     # join the encoder stream
             patches, clr = g.patches, g.clr
             ring = [(g.gmap, gslot_store), (g.imap, self.imap_[slot]), (g.f1, self._fmap1_store[slot]),
                     (g.f2, self._fmap2_store[slot])]
@@ -791,6 +811,8 @@ class Ramp_vo:
 
         # network attributes: gmap / imap / fmap pyramid into their ring slots (Ramp_vo.py:376-381), one launch
         copy_segments(ring)
+        if graphable:
+            g.consumed.record(torch.cuda.current_stream(self.device))        # staging buffers may be overwritten
 
         self.counter += 1
         if self.n > 0 and not self.is_initialized:

@@ -75,6 +75,8 @@ _SIGNATURES = {
     "rvo_select_patches": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _I64, _P]),
     "rvo_pyramid_level2": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "rvo_copy_segments": (c_int, [POINTER(_P), POINTER(_P), POINTER(_I64), c_int, _P]),
+    "rvo_conv2d_kpad": (c_int, [c_int, c_int]),
+    "rvo_conv2d_nhwc": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P]),
     "rvo_scene_lstm_params_floats": (c_int, [c_int, c_int]),
     "rvo_scene_lstm_forward": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P]),
     "rvo_frame_commit": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, POINTER(c_float), c_int, c_int, c_int, c_int,

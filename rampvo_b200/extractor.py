@@ -8,8 +8,9 @@ restructured for one (event voxel, image) pair per call:
     applied per pixel; no permute/contiguous round trips, no cuDNN RNN launch with batch = H*W;
   * everything runs channels-last (NHWC) so the fmap lands directly in the layout the altcorr
     tensor-core path reads, and the level-2 pyramid entry is produced with it;
-  * the dense 3x3 / 7x7 convolutions currently go through cuDNN (library GEMMs; the hand-written
-    tcgen05 implicit-GEMM path is the next step of DESIGN.md section "encoder").
+  * the dense 7x7 / 3x3 / 1x1 convolutions run on the hand-written tcgen05 implicit-GEMM kernel
+    (rvo_conv2d_nhwc, csrc/conv_tc.cu): resident weights, im2col gather by cp.async, the channel concatenations
+    read from their two sources, InstanceNorm statistics in the epilogue — no cuDNN on the fast path.
 """
 import torch
 import torch.nn as nn
@@ -26,16 +27,54 @@ def _fast(x):
     return x.is_cuda and torch.is_autocast_enabled() and not torch.is_grad_enabled()
 
 
-def _conv16(conv, x, scale=1.0):
-    """cuDNN convolution on fp16 channels-last operands with cached fp16 weights.  `scale` (a power
-    of two) is folded into the cached weights and bias — exact in fp16 up to subnormals."""
-    w = getattr(conv, "_w16", None)
-    if w is None or w[2] != scale:
-        w = conv._w16 = ((conv.weight.detach() * scale).half().contiguous(memory_format=CL),
-                         (conv.bias.detach() * scale).half(), scale)
-    with torch.autocast("cuda", enabled=False):
-        y = F.conv2d(x, w[0], w[1], stride=conv.stride, padding=conv.padding)
-    return y if y.is_contiguous(memory_format=CL) else y.contiguous(memory_format=CL)
+def _packed_conv(conv, scale, pad_in):
+    """fp16 [Cout, Kpad] weight matrix in the K order of rvo_conv2d_nhwc (tap-major, then input channel; the input
+    channels optionally zero-padded to `pad_in`) + fp32 bias, both times `scale`; cached on the module and rebuilt
+    whenever the parameters are replaced or modified in place (load_state_dict, .to(), optimiser steps)."""
+    w, b = conv.weight, conv.bias
+    key = (w.data_ptr(), w._version, b.data_ptr() if b is not None else 0, b._version if b is not None else 0,
+           scale, pad_in)
+    c = getattr(conv, "_wtc", None)
+    if c is not None and c[0] == key:
+        return c[1], c[2], c[3]
+    Cout, Cin, ks, _ = w.shape
+    wt = w.detach().float() * scale
+    if pad_in and pad_in > Cin:
+        wt = F.pad(wt, (0, 0, 0, 0, 0, pad_in - Cin))
+        Cin = pad_in
+    kpad = _lib.lib().rvo_conv2d_kpad(ks, Cin)
+    if kpad < 0:
+        raise RuntimeError("rvo_conv2d_nhwc: %d input channels (must be a multiple of 8)" % Cin)
+    wp = torch.zeros(Cout, kpad, dtype=torch.float16, device=w.device)
+    wp[:, :ks * ks * Cin] = wt.permute(0, 2, 3, 1).reshape(Cout, -1).half()
+    bias = (b.detach().float() * scale).contiguous() if b is not None else None
+    conv._wtc = (key, wp, bias, Cin)
+    return wp, bias, Cin
+
+
+def _conv_tc(conv, x, x2=None, scale=1.0, stats=False, pad_in=0):
+    """nn.Conv2d on the tcgen05 implicit-GEMM kernel (rvo_conv2d_nhwc, csrc/conv_tc.cu).  x [1,C0,H,W] (and x2
+    [1,C1,H,W]: the convolution sees their channel concatenation without materialising it) fp16 channels-last ->
+    ([1,Cout,Ho,Wo] fp16 channels-last, InstanceNorm statistics [2*Cout] or None).  `scale` (a power of two) is
+    folded into the packed weights and bias."""
+    wp, bias, Cin = _packed_conv(conv, scale, pad_in)
+    for t in (x, x2):
+        if t is not None and not (t.dtype == torch.float16 and t.shape[0] == 1 and t.is_contiguous(memory_format=CL)):
+            raise RuntimeError("rvo_conv2d_nhwc: inputs must be [1,C,H,W] fp16 channels-last")
+    C0, C1 = x.shape[1], (x2.shape[1] if x2 is not None else 0)
+    if C0 + C1 != Cin:
+        raise RuntimeError("rvo_conv2d_nhwc: %d + %d input channels, the layer has %d" % (C0, C1, Cin))
+    H, W = x.shape[-2:]
+    ks, sd, pd = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+    Cout = conv.out_channels
+    Ho, Wo = (H + 2 * pd - ks) // sd + 1, (W + 2 * pd - ks) // sd + 1
+    out = torch.empty(1, Cout, Ho, Wo, dtype=torch.float16, device=x.device, memory_format=CL)
+    st = torch.empty(2 * Cout, dtype=torch.float32, device=x.device) if stats else None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().rvo_conv2d_nhwc(_lib.ptr(x), C0, _lib.ptr(x2), C1, H, W, ks, sd, pd, _lib.ptr(wp),
+                                              _lib.ptr(bias), Cout, _lib.ptr(out), _lib.ptr(st),
+                                              _lib.stream_ptr(x.device)), "rvo_conv2d_nhwc")
+    return out, st
 
 
 def _stats(t):
@@ -74,15 +113,17 @@ class ResidualBlock(nn.Module):
     def _norm(self, x):
         return F.instance_norm(x) if self.instance else x
 
-    def _forward_fast(self, x):
-        """x: [1,C,H,W] fp16 channels-last.  conv -> stats -> apply, twice."""
-        t = _conv16(self.conv1, x)
-        y = _apply(t, _stats(t) if self.instance else None)
-        t = _conv16(self.conv2, y)
-        st = _stats(t) if self.instance else None
+    def _forward_fast(self, x, x2=None):
+        """x (+ x2: channel concat) [1,C,H,W] fp16 channels-last.  Tensor-core conv with the InstanceNorm statistics
+        in its epilogue -> normalise + ReLU (+ shortcut) in one pass, twice."""
+        t, st = _conv_tc(self.conv1, x, x2, stats=self.instance)
+        y = _apply(t, st)
+        t, st = _conv_tc(self.conv2, y, stats=self.instance)
         if self.downsample is not None:
-            d = _conv16(self.downsample[0], x)
-            return _apply(t, st, d, _stats(d) if self.instance else None)
+            d, sd = _conv_tc(self.downsample[0], x, x2, stats=self.instance)
+            return _apply(t, st, d, sd)
+        if x2 is not None:
+            raise RuntimeError("ResidualBlock: a concatenated input needs the strided (downsample) variant")
         return _apply(t, st, x)
 
     def forward(self, x):
@@ -122,12 +163,14 @@ class MultiScaleBasicEncoder4(nn.Module):
         out_scale: the /4 of net.py:152-153 folded into the last 1x1 conv on the fast path)."""
         if _fast(x) and x.shape[0] == 1:
             h16 = lambda t: t.half().contiguous(memory_format=CL)
-            t = _conv16(self.conv1, h16(x))
-            x = _apply(t, _stats(t) if self.instance else None)
+            t, st = _conv_tc(self.conv1, h16(x), stats=self.instance)
+            x = _apply(t, st)
             x = self.layer1(x)
-            x = self.layer3(torch.cat((x, h16(x_down2)), dim=1).contiguous(memory_format=CL))
-            return _conv16(self.conv3, torch.cat((x, h16(x_down4)), dim=1).contiguous(memory_format=CL),
-                           out_scale)
+            # torch.cat((x, x_down2)) / torch.cat((x, x_down4)) (extractor.py:302,309) are never materialised: the
+            # convolutions read their K range from the two tensors
+            x = self.layer3[0]._forward_fast(x, h16(x_down2))
+            x = self.layer3[1](x)
+            return _conv_tc(self.conv3, x, h16(x_down4), scale=out_scale)[0]
         x = self.conv1(x)
         if self.instance:
             x = F.instance_norm(x)
@@ -157,16 +200,10 @@ class BasicEncoder4(nn.Module):
 
     def forward_fast(self, x16, out_scale=1.0):
         """x16 [1,16,H,W] fp16 channels-last (15 channels + a zero pad, see MergerLSTMsceneEncoder)"""
-        w = getattr(self.conv1, "_w16p", None)
-        if w is None:   # first-layer weights padded to 16 input channels
-            wt = F.pad(self.conv1.weight.detach(), (0, 0, 0, 0, 0, x16.shape[1] - self.conv1.in_channels))
-            w = self.conv1._w16p = (wt.half().contiguous(memory_format=CL), self.conv1.bias.detach().half())
-        with torch.autocast("cuda", enabled=False):
-            t = F.conv2d(x16, w[0], w[1], stride=2, padding=3)
-        t = t if t.is_contiguous(memory_format=CL) else t.contiguous(memory_format=CL)
-        x = _apply(t, _stats(t) if self.instance else None)
+        t, st = _conv_tc(self.conv1, x16, stats=self.instance, pad_in=x16.shape[1])
+        x = _apply(t, st)
         x = self.layer2(self.layer1(x))
-        return _conv16(self.conv2, x, out_scale)
+        return _conv_tc(self.conv2, x, scale=out_scale)[0]
 
     def forward(self, x):
         """x [b,n,C,H,W] -> [b,n,out,H/4,W/4] (extractor.py:107-126)"""
