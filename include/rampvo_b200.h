@@ -122,6 +122,19 @@ int rvo_corr_pyramid_host(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const 
                           int nlevels, const float* coords, const int64_t* kk, const int64_t* jj,
                           int64_t pmod, int64_t fmod, int E, int radius, void* out, void* stream);
 
+/* cuda_corr.backward (ramp/altcorr/correlation.cpp:50-55; correlation_kernel.cu:140-190,236-290): gradients of
+ * rvo_corr_forward w.r.t. fmap1 [Np,C,P,P] and fmap2 [Nf,C,H2,W2] (strided views, fp16 / fp32) given corr_grad
+ * [E,d,d,P,P] fp32 (x-offset dim first, d = 2R+1; the 4-corner blend adjoint is applied inside).  Outputs are DENSE
+ * fp32 tensors of the logical shapes (zeroed here); the reference returns the inputs' dtype — the Python layer casts. */
+int rvo_corr_backward(const rvo_fmap_t* fmap1, const rvo_fmap_t* fmap2, const float* coords, const int64_t* ii,
+                      const int64_t* jj, const float* corr_grad, int E, int radius, float* fmap1_grad,
+                      float* fmap2_grad, void* stream);
+
+/* cuda_corr.patchify_backward (correlation_kernel.cu:50-80,306-331) for ONE map: patch_grad [M,C,D,D] (D = 2R+2,
+ * fp16 / fp32), coords [M,2] -> net_grad [C,H,W] dense fp32 (zeroed here). */
+int rvo_patchify_backward(const void* patch_grad, int dtype, const float* coords, int M, int C, int H, int W,
+                          int radius, float* net_grad, void* stream);
+
 /* ------------------------------------------------------- projective_ops -------- */
 
 /* flags for rvo_transform */
@@ -385,7 +398,8 @@ int rvo_up_gated_tail(const float* x32, const void* a16, const void* r16, int E,
  *   w_packed [Cout, Kpad] fp16 with k = (ky*ks + kx)*(C0+C1) + ci, zero padded to Kpad = rvo_conv2d_kpad(ks, C0+C1),
  *   bias [Cout] fp32 (or NULL), out [Ho,Wo,Cout] fp16 with Ho = (H + 2 pad - ks)/stride + 1.
  * stats (optional, [2*Cout] fp32): per-channel sum and sum of squares of the rounded outputs = the statistics pass
- * of nn.InstanceNorm2d (extractor.py:30-34), in the layout rvo_in_apply consumes; zeroed by this call.
+ * of nn.InstanceNorm2d (extractor.py:30-34), in the layout rvo_in_apply consumes; ACCUMULATED into the buffer,
+ * which the caller zeroes (one memset for all the layers of a frame instead of one per layer).
  * Limits: C0, C1 multiples of 8; Cout a multiple of 16; ks*ks*(C0+C1) <= 832. */
 int rvo_conv2d_kpad(int ks, int Cin);
 int rvo_conv2d_nhwc(const void* src0, int C0, const void* src1, int C1, int H, int W, int ks, int stride, int pad,
@@ -434,7 +448,8 @@ int rvo_copy_segments(const void* const* src, void* const* dst, const int64_t* b
  * intrinsics[n] = intr4 (HOST array, already / RES), index[n+1,:] = n+1, index_map[n+1] = m_next,
  * colors[n] = uint8((clr[:, [2,1,0]] + 0.5) * 127.5), patches[n] = patches_new with the inverse depth set to
  * depth_rand[m] (median_frames == 0; null keeps the staged value) or to the lower median of the depths of the
- * previous `median_frames` frames (torch.median semantics, :370-371). */
+ * previous `median_frames` frames (torch.median semantics, :370-371; evaluated on the patch-centre depths, which
+ * every pixel of a patch shares). */
 int rvo_frame_commit(const float* patches_new, const float* clr, const float* depth_rand, float* patches,
                      int64_t* tstamps, float* intrinsics, int64_t* index, int64_t* index_map, uint8_t* colors,
                      const float* intr4, int n, int M, int P, int N, int64_t counter, int64_t m_next,

@@ -37,6 +37,8 @@ _SIGNATURES = {
     "rvo_corr_forward": (c_int, [POINTER(FMap), POINTER(FMap), _P, _P, _P, c_int, c_int, _P, _P]),
     "rvo_corr_pyramid": (c_int, [POINTER(FMap), POINTER(FMap), POINTER(c_float), c_int, _P, _P, _P,
                                  _I64, _I64, c_int, c_int, _P, _I64, _P]),
+    "rvo_corr_backward": (c_int, [POINTER(FMap), POINTER(FMap), _P, _P, _P, _P, c_int, c_int, _P, _P, _P]),
+    "rvo_patchify_backward": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "rvo_up_linear": (c_int, [_P, _I64, _P, _P, c_int, c_int, c_int, c_int, _P, _I64, _P]),
     "rvo_corr_tiles_ws_bytes": (_I64, [POINTER(FMap), c_int, c_int]),
     "rvo_corr_tiles": (c_int, [POINTER(FMap), POINTER(FMap), POINTER(c_float), c_int, _P, _P, _P, _I64,

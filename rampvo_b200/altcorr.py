@@ -1,8 +1,9 @@
 """Drop-in for ramp.altcorr (ramp/altcorr/correlation.py:51-74, cuda_corr ramp/altcorr/correlation.cpp:57-62).
 
 Same names, argument order and tensor layouts as the reference; the work is done by
-librampvo_b200.so (rvo_patchify_*, rvo_corr_*).  Forward only: the backward kernels belong to the
-training row and raise until that row is built.
+librampvo_b200.so (rvo_patchify_*, rvo_corr_*).  With gradients enabled `corr` and `patchify` are
+autograd Functions like the reference's CorrLayer / PatchLayer (correlation.py:4-47), backed by
+rvo_corr_backward / rvo_patchify_backward (csrc/altcorr_bwd.cu).
 """
 import ctypes
 
@@ -11,12 +12,82 @@ import torch
 from . import _lib
 
 
-def _no_grad_inputs(*ts):
-    for t in ts:
-        if torch.is_tensor(t) and t.requires_grad and torch.is_grad_enabled():
-            raise NotImplementedError(
-                "rampvo_b200.altcorr: backward (cuda_corr.backward / patchify_backward) is not built "
-                "yet; call under torch.no_grad()")
+def _needs_grad(*ts):
+    return torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in ts)
+
+
+class _PatchLayer(torch.autograd.Function):
+    """correlation.py:33-47: raw (2R+2)^2 gather with a scatter-add backward"""
+
+    @staticmethod
+    def forward(ctx, net, coords, radius):
+        ctx.radius = radius
+        ctx.save_for_backward(coords)
+        ctx.net_shape, ctx.net_dtype = tuple(net.shape), net.dtype
+        return patchify_forward(net, coords, radius)[0]
+
+    @staticmethod
+    def backward(ctx, grad):
+        coords, = ctx.saved_tensors
+        return patchify_backward(ctx.net_shape, ctx.net_dtype, coords, grad, ctx.radius)[0], None, None
+
+
+class _CorrLayer(torch.autograd.Function):
+    """correlation.py:4-30: dropout < 1 keeps a random subset of the edges in the backward pass only"""
+
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, coords, ii, jj, radius, dropout):
+        ctx.save_for_backward(fmap1, fmap2, coords, ii, jj)
+        ctx.radius, ctx.dropout = radius, dropout
+        with torch.no_grad():
+            return corr(fmap1, fmap2, coords, ii, jj, radius)
+
+    @staticmethod
+    def backward(ctx, grad):
+        fmap1, fmap2, coords, ii, jj = ctx.saved_tensors
+        if ctx.dropout < 1:
+            perm = torch.rand(len(ii), device=ii.device) < ctx.dropout
+            coords, grad, ii, jj = coords[:, perm], grad[:, perm], ii[perm], jj[perm]
+        g1, g2 = corr_backward(fmap1, fmap2, coords, ii, jj, grad, ctx.radius)
+        return g1, g2, None, None, None, None, None
+
+
+def patchify_backward(net_shape, net_dtype, coords, grad, radius):
+    """cuda_corr.patchify_backward: grad [B,M,C,D,D] -> [net_grad [B,C,H,W]] in net's dtype"""
+    _lib.require_cuda(coords, grad)
+    B, C, H, W = net_shape
+    M = coords.shape[1]
+    coords = coords.to(torch.float32).contiguous()
+    grad = grad.contiguous()
+    if grad.dtype not in (torch.float16, torch.float32):
+        grad = grad.float()
+    out = torch.empty(B, C, H, W, dtype=torch.float32, device=grad.device)
+    with torch.cuda.device(grad.device):
+        for b in range(B):
+            _lib.check(_lib.lib().rvo_patchify_backward(_lib.ptr(grad[b]), _lib.dtype_code(grad), _lib.ptr(coords[b]),
+                                                        M, C, H, W, radius, _lib.ptr(out[b]), _lib.stream_ptr()),
+                       "rvo_patchify_backward")
+    return [out.to(net_dtype)]
+
+
+def corr_backward(fmap1, fmap2, coords, ii, jj, grad, radius):
+    """cuda_corr.backward: gradients w.r.t. fmap1 [B,Np,C,P,P] and fmap2 [B,Nf,C,H2,W2] given grad
+    [B,E,2R+1,2R+1,P,P]; returned in the inputs' dtype like the reference's zeros_like buffers."""
+    _lib.require_cuda(fmap1, fmap2, coords, ii, jj, grad)
+    B, E = coords.shape[0], coords.shape[1]
+    coords = coords.to(torch.float32).contiguous()
+    grad = grad.to(torch.float32).contiguous()
+    ii, jj = ii.to(torch.int64).contiguous(), jj.to(torch.int64).contiguous()
+    g1 = torch.empty(fmap1.shape, dtype=torch.float32, device=fmap1.device)
+    g2 = torch.empty(fmap2.shape, dtype=torch.float32, device=fmap2.device)
+    with torch.cuda.device(fmap1.device):
+        for b in range(B):
+            v1, v2 = _views(fmap1[b], fmap2[b])
+            _lib.check(_lib.lib().rvo_corr_backward(ctypes.byref(v1), ctypes.byref(v2), _lib.ptr(coords[b]),
+                                                    _lib.ptr(ii), _lib.ptr(jj), _lib.ptr(grad[b]), E, radius,
+                                                    _lib.ptr(g1[b]), _lib.ptr(g2[b]), _lib.stream_ptr()),
+                       "rvo_corr_backward")
+    return [g1.to(fmap1.dtype), g2.to(fmap2.dtype)]
 
 
 def patchify_forward(net, coords, radius):
@@ -44,7 +115,21 @@ def patchify(net, coords, radius, mode='bilinear', out=None):
     `out` (optional, extension): a preallocated fp16/fp32 tensor view of shape [B,M,C,d,d] with
     arbitrary strides — lets the caller write straight into a channels-last ring buffer.
     """
-    _no_grad_inputs(net)
+    if _needs_grad(net, coords):
+        # training: PatchLayer + the 4-corner blend in torch ops, exactly like correlation.py:51-68 (the blend
+        # weights stay differentiable w.r.t. coords through autograd)
+        patches = _PatchLayer.apply(net, coords, radius)
+        if mode != 'bilinear':
+            return patches
+        offset = (coords - coords.floor()).to(net.device)
+        dx, dy = offset[:, :, None, None, None].unbind(dim=-1)
+        d = 2 * radius + 1
+        res = ((1 - dy) * (1 - dx) * patches[..., :d, :d] + (1 - dy) * dx * patches[..., :d, 1:] +
+               dy * (1 - dx) * patches[..., 1:, :d] + dy * dx * patches[..., 1:, 1:])
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
     if mode != 'bilinear':
         return patchify_forward(net, coords, radius)[0]
     _lib.require_cuda(net, coords)
@@ -80,7 +165,8 @@ def corr(fmap1, fmap2, coords, ii, jj, radius=1, dropout=1):
     [B,E,2R+1,2R+1,P,P] (x-offset dim first) in fmap1's dtype.  fp32 accumulation.  `dropout` only
     affects the reference's backward pass (correlation.py:20-25) and is ignored here.
     """
-    _no_grad_inputs(fmap1, fmap2)
+    if _needs_grad(fmap1, fmap2):
+        return _CorrLayer.apply(fmap1, fmap2, coords, ii, jj, radius, dropout)
     _lib.require_cuda(fmap1, fmap2, coords, ii, jj)
     B, E = coords.shape[0], coords.shape[1]
     P = fmap1.shape[-1]

@@ -17,17 +17,19 @@
 //     ROUNDED outputs reduced with a 31-shuffle warp transpose and accumulated per CTA (extractor.py:30-34: the
 //     statistics pass of nn.InstanceNorm2d costs nothing extra; rvo_in_apply consumes them).
 // Persistent grid: CTA b owns column slice b % n_slices and walks pixel tiles b / n_slices, + n_walkers, ...
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tcgen05.cuh"
 
 namespace rvo {
 
 constexpr int kCvM = 128;
-constexpr int kCvStages = 5;
+constexpr int kCvMaxStages = 8;
 constexpr int kCvAStage = kCvM * 128;          // 16 KB: 128 rows x 64 halves
 constexpr int kCvMaxKB = 13;                   // 7x7x16 = 784 -> 13 K blocks
 constexpr int kCvMaxN = 192;
-constexpr int kCvThreads = 512;                // warp 0 TMA (W), warp 1 MMA, warps 4-11 epilogue, 12-15 A producers
+constexpr int kCvThreads = 640;                // warp 0 TMA (W), warp 1 MMA, warps 4-11 epilogue, 12-19 A producers
 
 struct ConvArgs {
   const __half* src0;
@@ -43,15 +45,32 @@ struct ConvArgs {
   __half* out;             // [Ho*Wo, Cout]
   float* stats;            // [2*Cout] sum / sum of squares, accumulated atomically, or null
   uint32_t tmem_cols;      // power of two >= 2N
+  int stages;              // A ring depth (3..8), as many as fit beside the resident weights
+  uint32_t wo_magic;       // ceil(2^32 / Wo): p / Wo == umulhi(p, wo_magic) for p < 2^32 / Wo
 };
+
+// debugging aid (-DRVO_DEBUG builds): globaltimer stamps of CTA `trace_cta`, read back with rvo_conv_trace
+#ifdef RVO_DEBUG
+__device__ unsigned long long g_cv_trace[8 * 64];
+__device__ int g_cv_trace_cta = 0;
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define CV_TRACE(slot, i) do { if (blockIdx.x == g_cv_trace_cta && (i) < 64) g_cv_trace[(slot) * 64 + (i)] = gtime(); } while (0)
+#else
+#define CV_TRACE(slot, i) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(kCvThreads, 1)
 conv_tc_kernel(const ConvArgs a, const __grid_constant__ TcTmap tmw) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t wfull[kCvMaxKB], xfull[kCvStages], xempty[kCvStages], tfull[2], tempty[2];
+  __shared__ uint64_t wfull[kCvMaxKB], xfull[kCvMaxStages], xempty[kCvMaxStages], tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float bias_s[kCvMaxN];
   __shared__ float stat_s[2 * kCvMaxN];
+  __shared__ int4 kinfo[kCvMaxKB * 8];       // per (K block, 16-byte chunk): where the im2col gather reads from
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slice = blockIdx.x % a.n_slices;
@@ -60,20 +79,32 @@ conv_tc_kernel(const ConvArgs a, const __grid_constant__ TcTmap tmw) {
   const int n_tiles = (P + kCvM - 1) / kCvM;
   const int N = a.N, KB = a.KB, Cout = a.N * a.n_slices;
 
+  if (tid == 0) CV_TRACE(0, 0);
   if (tid == 0) {
     for (int kb = 0; kb < KB; kb++) mbar_init(&wfull[kb], 1);
-    for (int s = 0; s < kCvStages; s++) {
-      mbar_init(&xfull[s], 128);
+    for (int s = 0; s < a.stages; s++) {
+      mbar_init(&xfull[s], 256);
       mbar_init(&xempty[s], 1);
     }
     for (int s = 0; s < 2; s++) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 128);
+      mbar_init(&tempty[s], 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (tid < N) bias_s[tid] = a.bias ? a.bias[slice * N + tid] : 0.f;
   if (tid < 2 * N) stat_s[tid] = 0.f;
+  if (tid >= 512 && tid - 512 < KB * 8) {
+    const int e = tid - 512, Cin = a.C0 + a.C1;
+    const int k0 = e * 8, tap = k0 / Cin, c = k0 - tap * Cin;
+    const int ky = tap / a.ks, kx = tap - ky * a.ks;
+    int4 ki;
+    ki.x = ky * a.W + kx;
+    ki.y = tap < a.ks * a.ks ? (int)((1u << ky) | (1u << (8 + kx))) : -1;    // -1: no row ever qualifies
+    ki.z = c >= a.C0 ? c - a.C0 : c;
+    ki.w = c >= a.C0 ? -a.C1 : a.C0;
+    kinfo[e] = ki;
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)),
                  "r"(a.tmem_cols)
@@ -84,6 +115,7 @@ conv_tc_kernel(const ConvArgs a, const __grid_constant__ TcTmap tmw) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
+  if (tid == 0) CV_TRACE(0, 1);
   const uint32_t wblk = (uint32_t)N * 128;                  // bytes of one resident K block of the weight slice
   const uint32_t W_u = smem_u32(smem);
   const uint32_t X_u = W_u + ((KB * wblk + 1023u) & ~1023u);
@@ -105,85 +137,96 @@ conv_tc_kernel(const ConvArgs a, const __grid_constant__ TcTmap tmw) {
       mbar_wait_spin(&tempty[acc], ((lt >> 1) & 1) ^ 1);
       for (int kb = 0; kb < KB; kb++) {
         if (first) mbar_wait_spin(&wfull[kb], 0);
+        if (lane == 0 && kb == 0) CV_TRACE(1, lt);            // weights (first tile) / accumulator available
         mbar_wait_spin(&xfull[s], ph);
+        // the A block was written by the producers' cp.async (generic proxy) and is read by the tensor core
+        // (async proxy): one proxy fence by the issuing thread after the acquire
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         if (lane == 0) {
+          if (kb == 0) CV_TRACE(2, lt);                       // first A block of the tile has landed
           const uint64_t da0 = umma_desc(X_u + s * kCvAStage), db0 = umma_desc(W_u + kb * wblk);
 #pragma unroll
           for (int k = 0; k < 4; k++)
             umma_f16(tmem_base + acc * N, da0 + (uint64_t)((k * 32) >> 4), db0 + (uint64_t)((k * 32) >> 4), idesc,
                      (kb | k) ? 1u : 0u);
           umma_commit(&xempty[s]);
-          if (kb == KB - 1) umma_commit(&tfull[acc]);
+          if (kb == KB - 1) {
+            umma_commit(&tfull[acc]);
+            CV_TRACE(3, lt);                                  // last MMA of the tile issued
+          }
         }
         __syncwarp();
-        if (++s == kCvStages) { s = 0; ph ^= 1; }
+        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
       first = false;
     }
     if (first)
       for (int kb = 0; kb < KB; kb++) mbar_wait_spin(&wfull[kb], 0);
   } else if (warp >= 12) {
-    // ===== A producers (im2col gather): thread owns 16-byte chunk `ch` of rows r0 + 16 j =====
+    // ===== A producers (im2col gather): 8 warps; thread owns 16-byte chunk `ch` of rows r0 + 32 j.
+    // A lone warp runs its dependent integer chain at ~5 cycles per instruction, so the loop body is kept to a
+    // shared-memory table lookup (what tap / channel run this thread's chunk of K block kb is) plus, per row, a bit
+    // test, an add and one multiply-add; per tile one magic-number division.  (Measured with the straightforward
+    // index arithmetic: 520 ns of producer instructions per K block, 1.9 us of set-up per tile.) =====
     const int ptid = tid - 12 * 32, ch = ptid & 7, r0 = ptid >> 3;
-    const int Cin = a.C0 + a.C1, ntaps = a.ks * a.ks;
-    int it = 0;
+    const int stages = a.stages;
+    int it = 0, s = 0, ph = 1;
     for (int t = walker; t < n_tiles; t += n_walkers) {
-      int iy0[8], ix0[8];
+      int pix0[4];
+      uint32_t okm[4];
+      const uint32_t p0 = (uint32_t)(t * kCvM + r0);
+      int oy = (int)__umulhi(p0, a.wo_magic), ox = (int)p0 - oy * a.Wo;
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int p = t * kCvM + r0 + 16 * j;
-        if (p < P) {
-          const int oy = p / a.Wo, ox = p - oy * a.Wo;
-          iy0[j] = oy * a.stride - a.pad;
-          ix0[j] = ox * a.stride - a.pad;
-        } else {
-          iy0[j] = -(1 << 28);                                // every tap falls outside: zero rows
-          ix0[j] = 0;
-        }
+      for (int j = 0; j < 4; j++) {
+        const int iy0 = oy * a.stride - a.pad, ix0 = ox * a.stride - a.pad;
+        pix0[j] = iy0 * a.W + ix0;
+        // bit k of the low byte: tap row k lies inside the image; bit 8 + k: tap column k does
+        const int ylo = max(0, -iy0), yhi = min(a.ks, a.H - iy0), xlo = max(0, -ix0), xhi = min(a.ks, a.W - ix0);
+        const uint32_t my = yhi > ylo ? (((1u << yhi) - 1u) & ~((1u << ylo) - 1u)) : 0u;
+        const uint32_t mx = xhi > xlo ? (((1u << xhi) - 1u) & ~((1u << xlo) - 1u)) : 0u;
+        okm[j] = ((int)p0 + 32 * j < P) ? (my | (mx << 8)) : 0u;
+        ox += 32;
+        while (ox >= a.Wo) { ox -= a.Wo; oy++; }
       }
+      if (ptid == 0) CV_TRACE(6, 63 - (it < 15 ? it : 15));
       for (int kb = 0; kb < KB; kb++, it++) {
-        const int s = it % kCvStages;
-        mbar_wait(&xempty[s], ((it / kCvStages) & 1) ^ 1);
-        const int k0 = kb * 64 + ch * 8;
-        const int tap = k0 / Cin, c = k0 - tap * Cin;
-        const int ky = tap / a.ks, kx = tap - ky * a.ks;
-        const bool tap_ok = tap < ntaps;
-        const bool second = c >= a.C0;
-        const __half* base = second ? a.src1 + (c - a.C0) : a.src0 + c;
-        const int cs = second ? a.C1 : a.C0;
+        mbar_wait(&xempty[s], ph);
+        if (ptid == 0) CV_TRACE(6, it);                       // stage free
+        const int4 ki = kinfo[kb * 8 + ch];                   // {tap offset in pixels, needed mask bits, element offset, pixel stride}
+        const __half* base = ki.w < 0 ? a.src1 : a.src0;
+        const int cs = ki.w < 0 ? -ki.w : ki.w;
         const uint32_t dst0 = X_u + s * kCvAStage + r0 * 128 + (uint32_t)((ch ^ (r0 & 7)) << 4);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int iy = iy0[j] + ky, ix = ix0[j] + kx;
-          const bool ok = tap_ok && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
-          const int64_t off = ok ? ((int64_t)iy * a.W + ix) * cs : 0;
-          cp_async16(dst0 + j * (16 * 128), base + off, ok ? 16u : 0u);
+        for (int j = 0; j < 4; j++) {
+          const bool ok = (okm[j] & (uint32_t)ki.y) == (uint32_t)ki.y;
+          const int off = ok ? (pix0[j] + ki.x) * cs + ki.z : 0;
+          cp_async16(dst0 + j * (32 * 128), base + off, ok ? 16u : 0u);
         }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-        if (it >= 3) {
-          asm volatile("cp.async.wait_group 3;\n" ::: "memory");
-          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-          mbar_arrive(&xfull[(it - 3) % kCvStages]);
-        }
+        // the barrier arrival is triggered BY THE HARDWARE when this thread's copies have landed: the producer
+        // never waits for its own loads (a wait_group + fence.proxy.async per K block drains every copy in
+        // flight and degrades the ring to one K block per memory round trip: measured 590 ns per K block)
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&xfull[s])) : "memory");
+        if (ptid == 0) CV_TRACE(7, it);                       // K block issued
+        if (++s == stages) { s = 0; ph ^= 1; }
       }
     }
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    for (int d = 3; d >= 1; d--)
-      if (it >= d) mbar_arrive(&xfull[(it - d) % kCvStages]);
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
   } else if (warp >= 4) {
-    // ===== epilogue: group g drains accumulator g; quadrant q; thread = output pixel =====
-    const int g = (warp - 4) >> 2, q = warp & 3;
-    const uint32_t tlane = tmem_base + g * N + ((uint32_t)(q * 32) << 16);
+    // ===== epilogue: all 8 warps drain every tile: lane quadrant q (thread = output pixel), the two warps of a
+    // quadrant take alternate 32-column chunks (one warp runs this dependent LDTM -> add -> pack -> store chain at
+    // ~1.2 us per chunk; a CTA only sees 1-5 tiles, so finishing a tile sooner beats overlapping two of them) =====
+    const int hf = (warp - 4) >> 2, q = warp & 3;
     int lt = 0;
     for (int t = walker; t < n_tiles; t += n_walkers, lt++) {
-      if ((lt & 1) != g) continue;
+      const int g = lt & 1;
+      const uint32_t tlane = tmem_base + g * N + ((uint32_t)(q * 32) << 16);
       const int p = t * kCvM + q * 32 + lane;
       const bool live = p < P;
       mbar_wait(&tfull[g], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      for (int c0 = 0; c0 < N; c0 += 32) {
+      if (q == 0 && hf == 0 && lane == 0) CV_TRACE(4, lt);    // accumulator complete, epilogue starts
+      for (int c0 = 32 * hf; c0 < N; c0 += 64) {
         float v[32];
         if (c0 + 32 <= N) {
           tmem_ld32(tlane + c0, v);
@@ -245,6 +288,7 @@ conv_tc_kernel(const ConvArgs a, const __grid_constant__ TcTmap tmw) {
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      if (q == 0 && hf == 0 && lane == 0) CV_TRACE(5, lt);    // epilogue of the tile done
       mbar_arrive(&tempty[g]);
     }
   }
@@ -258,11 +302,21 @@ conv_tc_kernel(const ConvArgs a, const __grid_constant__ TcTmap tmw) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(a.tmem_cols)
                  : "memory");
   }
+  if (tid == 0) CV_TRACE(0, 2);
 }
 
 }  // namespace rvo
 
 using namespace rvo;
+
+#ifdef RVO_DEBUG
+extern "C" int rvo_conv_trace(unsigned long long* host_out, int next_cta) {
+  RVO_CUDA(cudaDeviceSynchronize());
+  RVO_CUDA(cudaMemcpyFromSymbol(host_out, g_cv_trace, sizeof(unsigned long long) * 8 * 64));
+  RVO_CUDA(cudaMemcpyToSymbol(g_cv_trace_cta, &next_cta, sizeof(int)));
+  return RVO_OK;
+}
+#endif
 
 extern "C" int rvo_conv2d_kpad(int ks, int Cin) {
   if (ks < 1 || Cin < 8 || Cin % 8) return -1;
@@ -291,7 +345,7 @@ extern "C" int rvo_conv2d_nhwc(const void* src0, int C0, const void* src1, int C
   auto fits = [&](int ns) {
     const int N = Cout / ns;
     return Cout % ns == 0 && N % 16 == 0 && N <= kCvMaxN &&
-           (size_t)KB * N * 128 + 1024 + (size_t)kCvStages * kCvAStage + 1024 <= 227 * 1024;
+           (size_t)KB * N * 128 + 1024 + (size_t)4 * kCvAStage + 1024 <= 225 * 1024;
   };
   while (n_slices <= 16 && !fits(n_slices)) n_slices++;
   RVO_CHECK_ARG(n_slices <= 16, "rvo_conv2d_nhwc: Cout = %d with K = %d does not fit", Cout, Kpad);
@@ -309,9 +363,14 @@ extern "C" int rvo_conv2d_nhwc(const void* src0, int C0, const void* src1, int C
   uint32_t cols = 32;
   while (cols < 2u * N) cols <<= 1;
   a.tmem_cols = cols;
+  const size_t wbytes = (((size_t)KB * N * 128 + 1023) & ~(size_t)1023);
+  int stages = (int)((225 * 1024 - 1024 - wbytes) / kCvAStage);
+  a.stages = stages > kCvMaxStages ? kCvMaxStages : stages;
+  a.wo_magic = (uint32_t)((0x100000000ull + (uint64_t)Wo - 1) / (uint64_t)Wo);
+  RVO_CHECK_ARG(P < (int64_t)(0x100000000ull / (uint64_t)Wo) && (int64_t)H * W * (C0 > C1 ? C0 : C1) < 0x7fffffffll,
+                "rvo_conv2d_nhwc: tensor too large for 32-bit index arithmetic");
   cudaStream_t st = (cudaStream_t)stream;
-  if (stats) RVO_CUDA(cudaMemsetAsync(stats, 0, 2 * (size_t)Cout * sizeof(float), st));
-  const size_t smem = (((size_t)KB * N * 128 + 1023) & ~(size_t)1023) + (size_t)kCvStages * kCvAStage + 1024;
+  const size_t smem = wbytes + (size_t)a.stages * kCvAStage + 1024;
   RVO_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   conv_tc_kernel<<<grid, kCvThreads, smem, st>>>(a, tmw);
   RVO_LAUNCH_CHECK("conv_tc_kernel");

@@ -465,16 +465,16 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
         const bool ok = off >= 0;
         if (!(dbg & 4)) cp_async16(dst, gsrc + (ok ? off : 0), ok ? 16u : 0u);
       }
-      asm volatile("cp.async.commit_group;\n" ::: "memory");
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> async proxy
-      mbar_arrive(&afull[s]);
+      // hardware-triggered arrival when this thread's copies have landed: the producer goes on to the next block's
+      // gather instead of sitting out a memory round trip per block (the consumer issues the proxy fence)
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&afull[s])) : "memory");
       if (ptid == 0) TC_TRACE(1, i);
       // the group's next write of rowsrc[pg] comes after its next bar.sync partner has read this one:
       // every thread passes the loop above before any thread can pass the next iteration's barrier
       if (pg == 0) asm volatile("bar.sync 3, 128;\n" ::: "memory");
       else asm volatile("bar.sync 4, 128;\n" ::: "memory");
     }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
   } else if (warp == kTmaTmaWarp) {
     // ===== TMA producer: one thread, one tile load per run of blocks that share the tile =====
     if (lane == 0) {
@@ -523,6 +523,7 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
       const int st = i & 1, sb = ib & 1;
       mbar_wait_spin(&afull[sa], pa);
       mbar_wait_spin(&tempty[st], ((i >> 1) & 1) ^ 1);
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // A rows: cp.async writes -> tensor-core reads
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       if (lane == 0) TC_TRACE(3, i);
       if (lane == 0) {

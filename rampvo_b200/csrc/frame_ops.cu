@@ -296,7 +296,7 @@ struct FrameCommit {
 };
 
 constexpr int kCommitThreads = 1024;
-constexpr int kCommitMaxMedian = 8192;
+constexpr int kCommitMaxMedian = 2048;      // patch depths entering the median (3 frames x 300 patches = 900)
 
 // ramp/Ramp_vo.py:345-372 in one launch: timestamps / intrinsics / index rows, colour conversion, depth
 // initialisation (uniform draw, or the lower median of the last frames' depths like torch.median) and the
@@ -322,16 +322,17 @@ frame_commit_kernel(const FrameCommit a) {
   }
   float med = 0.0f;
   if (a.median_frames > 0) {
-    // torch.median(patches_[n-3:n, :, 2]) (Ramp_vo.py:370-371): lower median of cnt values, exact (sort)
-    const int cnt = a.median_frames * a.M * PP;
+    // torch.median(patches_[n-3:n, :, 2]) (Ramp_vo.py:370-371) = the lower median of F*M*P*P values.  Every pixel
+    // of a patch carries the same inverse depth (BA and the initialisation write all P*P of them, ba_cuda.cu:
+    // 225-227), so the sorted list is the sorted list of the F*M patch depths with each entry repeated P*P times
+    // and its element (cnt-1)/2 is element ((cnt-1)/2) / (P*P) of the short list: sort F*M values, not F*M*P*P.
+    const int cntp = a.median_frames * a.M;
     int cap = 1;
-    while (cap < cnt) cap <<= 1;
+    while (cap < cntp) cap <<= 1;
     for (int t = tid; t < cap; t += kCommitThreads) {
       float v = __int_as_float(0x7f800000);
-      if (t < cnt) {
-        const int f = t / (a.M * PP), r = t % (a.M * PP);
-        v = a.patches[((size_t)(a.n - a.median_frames + f) * a.M + r / PP) * 3 * PP + 2 * PP + r % PP];
-      }
+      if (t < cntp)
+        v = a.patches[((size_t)(a.n - a.median_frames) * a.M + t) * 3 * PP + 2 * PP + (a.P >= 2 ? a.P + 1 : 0)];
       srt[t] = v;
     }
     __syncthreads();
@@ -347,7 +348,7 @@ frame_commit_kernel(const FrameCommit a) {
         }
         __syncthreads();
       }
-    if (tid == 0) s_med = srt[(cnt - 1) / 2];
+    if (tid == 0) s_med = srt[((cntp * PP - 1) / 2) / PP];
     __syncthreads();
     med = s_med;
   }
@@ -372,8 +373,8 @@ extern "C" int rvo_frame_commit(const float* patches_new, const float* clr, cons
   RVO_CHECK_ARG(n >= 0 && n < N && M >= 1 && P >= 1, "rvo_frame_commit: n=%d N=%d M=%d P=%d", n, N, M, P);
   RVO_CHECK_ARG(median_frames >= 0 && median_frames <= n, "rvo_frame_commit: median over %d frames at n=%d",
                 median_frames, n);
-  RVO_CHECK_ARG((int64_t)median_frames * M * P * P <= kCommitMaxMedian,
-                "rvo_frame_commit: median over %d values (max %d)", median_frames * M * P * P, kCommitMaxMedian);
+  RVO_CHECK_ARG((int64_t)median_frames * M <= kCommitMaxMedian,
+                "rvo_frame_commit: median over %d patches (max %d)", median_frames * M, kCommitMaxMedian);
   FrameCommit a;
   a.patches_new = patches_new; a.clr = clr; a.depth_rand = depth_rand; a.patches = patches;
   a.tstamps = tstamps; a.intrinsics = intrinsics; a.index = index; a.index_map = index_map; a.colors = colors;

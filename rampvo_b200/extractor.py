@@ -27,6 +27,30 @@ def _fast(x):
     return x.is_cuda and torch.is_autocast_enabled() and not torch.is_grad_enabled()
 
 
+class _StatArena:
+    """InstanceNorm statistics of every convolution of a forward pass live in one zeroed buffer: the kernels
+    accumulate into their slice, so a frame needs ONE memset (begin()) instead of one per layer.  Outside a
+    begin()/end() bracket each request gets its own zeroed tensor."""
+    _cur = None
+
+    @classmethod
+    def begin(cls, device, floats=8192):
+        cls._cur = [torch.zeros(floats, dtype=torch.float32, device=device), 0]
+
+    @classmethod
+    def end(cls):
+        cls._cur = None
+
+    @classmethod
+    def take(cls, device, n):
+        c = cls._cur
+        if c is None or c[0].device != device or c[1] + n > c[0].numel():
+            return torch.zeros(n, dtype=torch.float32, device=device)
+        out = c[0][c[1]:c[1] + n]
+        c[1] += n
+        return out
+
+
 def _packed_conv(conv, scale, pad_in):
     """fp16 [Cout, Kpad] weight matrix in the K order of rvo_conv2d_nhwc (tap-major, then input channel; the input
     channels optionally zero-padded to `pad_in`) + fp32 bias, both times `scale`; cached on the module and rebuilt
@@ -69,7 +93,7 @@ def _conv_tc(conv, x, x2=None, scale=1.0, stats=False, pad_in=0):
     Cout = conv.out_channels
     Ho, Wo = (H + 2 * pd - ks) // sd + 1, (W + 2 * pd - ks) // sd + 1
     out = torch.empty(1, Cout, Ho, Wo, dtype=torch.float16, device=x.device, memory_format=CL)
-    st = torch.empty(2 * Cout, dtype=torch.float32, device=x.device) if stats else None
+    st = _StatArena.take(x.device, 2 * Cout) if stats else None
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().rvo_conv2d_nhwc(_lib.ptr(x), C0, _lib.ptr(x2), C1, H, W, ks, sd, pd, _lib.ptr(wp),
                                               _lib.ptr(bias), Cout, _lib.ptr(out), _lib.ptr(st),
@@ -271,8 +295,10 @@ class MergerLSTMsceneEncoder(nn.Module):
                 _lib.ptr(self._packed_params(dev)), ev.shape[0], im.shape[0], _lib.ptr(ev), _lib.ptr(im), H, W,
                 _lib.ptr(st[0]), _lib.ptr(st[1]), _lib.ptr(st[2]), _lib.ptr(st[3]), int(first), _lib.ptr(out),
                 _lib.stream_ptr(dev)), "rvo_scene_lstm_forward")
+        _StatArena.begin(dev)
         fmap = self.fmap_encoder.forward_fast(out, out_scale)
         imap = self.imap_encoder.forward_fast(out, out_scale)
+        _StatArena.end()
         return fmap[None], imap[None], None
 
     def forward(self, events, images, reinit_hidden=False, out_scale=1.0):
@@ -421,6 +447,7 @@ class MultiScaleMergerDoubleNet(nn.Module):
             self.super_states[k] = out
             per_scale.append(out)
         side = getattr(self, "branch_stream", None)
+        _StatArena.begin(ev.device)          # zeroed before the branches fork; both CNNs take slices of it
         if side is None:
             fmap = self.fmap_encoder(per_scale[0], per_scale[1], per_scale[2], out_scale)
             imap = self.imap_encoder(per_scale[0], per_scale[1], per_scale[2], out_scale)
@@ -437,6 +464,7 @@ class MultiScaleMergerDoubleNet(nn.Module):
                 imap.record_stream(cur)
                 for t in per_scale:
                     t.record_stream(side)
+        _StatArena.end()
         return fmap[None], imap[None]
 
     def forward(self, events, images, mask, reinit_hidden=False, out_scale=1.0):

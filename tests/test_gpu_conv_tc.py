@@ -42,6 +42,8 @@ def test_conv_tc_matches_fp32_reference(C0, C1, Cout, ks, stride, pad, H, W):
     d = (got.float() - ref).abs()
     tol = 2.0 ** -10 * ref.abs() + 2e-3            # one fp16 rounding of the output + fp32 summation order
     assert bool((d <= tol).all()), "max |d| %.3e" % d.max().item()
+    got2, st2 = _conv_tc(conv, x, x2, stats=True)      # statistics buffers are zeroed by the caller side, per call
+    assert torch.equal(got, got2) and torch.allclose(st, st2, rtol=1e-5)
     # InstanceNorm statistics of the rounded outputs
     s1 = got.float().sum(dim=(0, 2, 3))
     s2 = (got.float() ** 2).sum(dim=(0, 2, 3))
