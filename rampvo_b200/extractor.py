@@ -341,8 +341,15 @@ class LSTMEncoder(nn.Module):
         self.convlstm = nn.LSTM(input_size=in_channels, hidden_size=out_channels, batch_first=True)
 
     def forward(self, x):
-        """x [1,C,H,W] -> h [1,hidden,H/s,W/s]"""
+        """x [T,C,H,W] -> h [T,hidden,H/s,W/s].  The T frames of ONE call form a per-pixel sequence that starts from
+        a zero state (extractor.py:364-381: to_sequence -> nn.LSTM -> from_sequence); online tracking feeds T = 1,
+        where the recurrence collapses to a gated map of the input, training clips feed T = 15."""
         x = self.conv_1(x)
+        T, C, H, W = x.shape
+        if T > 1:
+            seq = x.permute(2, 3, 0, 1).reshape(H * W, T, C)
+            out, _ = self.convlstm(seq.to(self.convlstm.weight_ih_l0.dtype) if not torch.is_autocast_enabled() else seq)
+            return out.reshape(H, W, T, self.hidden).permute(2, 3, 0, 1).to(x.dtype)
         w = self.convlstm.weight_ih_l0                       # [4h, C], gate order i, f, g, o
         b = self.convlstm.bias_ih_l0 + self.convlstm.bias_hh_l0
         gates = F.conv2d(x, w[:, :, None, None].to(x.dtype), b.to(x.dtype))

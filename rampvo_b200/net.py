@@ -19,9 +19,14 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+import numpy as np
+
 from . import _lib, altcorr, fastba
+from . import projective_ops as pops
+from .ba import BA
 from .extractor import MergerLSTMsceneEncoder, MultiScaleMergerDoubleNet
-from .vo_utils import coords_from_topk_events, get_channel_dim
+from .lietorch import SE3
+from .vo_utils import coords_from_topk_events, flatmeshgrid, get_channel_dim, preprocess_input
 
 DIM = 384
 
@@ -233,6 +238,38 @@ class Update(nn.Module):
                                        P(weight), st), "rvo_up_gated_tail")
         return out, (delta, weight, None)
 
+    @staticmethod
+    def _soft_agg_autograd(agg, x, key):
+        """SoftAgg.forward (blocks.py:42-48) with index ops that autograd differentiates"""
+        _, g = torch.unique(key, return_inverse=True)
+        n = int(g.max().item()) + 1
+        gx, fx = agg.g(x)[0], agg.f(x)[0]
+        idx = g[:, None].expand_as(gx)
+        mx = torch.full((n, gx.shape[1]), -float("inf"), dtype=gx.dtype, device=gx.device)
+        mx = mx.scatter_reduce(0, idx, gx.detach(), reduce="amax", include_self=True)
+        ex = (gx - mx[g]).exp()
+        w = ex / torch.zeros(n, gx.shape[1], dtype=gx.dtype, device=gx.device).index_add_(0, g, ex)[g]
+        y = torch.zeros(n, gx.shape[1], dtype=gx.dtype, device=gx.device).index_add_(0, g, fx * w)
+        return agg.h(y)[g][None]
+
+    def _forward_autograd(self, net, inp, corr, ii, jj, kk):
+        """the training path (gradients recorded): the reference's op sequence (net.py:69-90) in tensor ops; only
+        the neighbour lookup, which carries no gradient, runs on the graph-plan kernels"""
+        if isinstance(inp, tuple):
+            table, idx, mod = inp
+            inp = table.reshape(-1, DIM)[(idx % mod) if mod else idx][None]
+        net = net + inp + self.corr(corr)
+        net = self.norm(net)
+        ix, jx = fastba.neighbors(kk, jj)
+        mask_ix = (ix >= 0).float().reshape(1, -1, 1)
+        mask_jx = (jx >= 0).float().reshape(1, -1, 1)
+        net = net + self.c1(mask_ix * net[:, ix])
+        net = net + self.c2(mask_jx * net[:, jx])
+        net = net + self._soft_agg_autograd(self.agg_kk, net, kk)
+        net = net + self._soft_agg_autograd(self.agg_ij, net, ii * 12345 + jj)
+        net = self.gru(net)
+        return net, (self.d(net), self.w(net), None)
+
     def forward(self, net, inp, corr, flow, ii, jj, kk, plans=None, net_out=None):
         """net [1,E,384], inp [1,E,384], corr [1,E,882], ii/jj/kk [E] ->
         (net [1,E,384] fp32, (delta [1,E,2], weight [1,E,2], None)).  Extensions: `plans`, a
@@ -242,6 +279,9 @@ class Update(nn.Module):
         mixed-precision path runs; otherwise the generic path in the tensors' own dtype."""
         _lib.require_cuda(net, corr, ii, jj, kk)
         E = ii.numel()
+        if torch.is_grad_enabled() and (net.requires_grad or corr.requires_grad or
+                                        any(p.requires_grad for p in self.parameters())):
+            return self._forward_autograd(net, inp, corr, ii, jj, kk)
         if plans is None:
             plans = GraphPlans(ii, jj, kk)
         dev = net.device
@@ -302,12 +342,20 @@ class Patchifier(nn.Module):
             with torch.cuda.stream(side):
                 coords = coords_from_topk_events(events, patches_per_image, non_max_supp_rad=11)
         # fmap / 4, imap / 4 (net.py:152-153) are folded into the encoders' last 1x1 convolutions
-        if self.input_mode == "SingleScale":   # net.py:141-145: no mask, the presence tests are data-dependent
-            fmap, imap, _ = self.encoder(events=events, images=images, reinit_hidden=reinit_hidden, out_scale=0.25)
-            mask_l = [True] * fmap.shape[1]
-        else:
-            fmap, imap = self.encoder(events=events, images=images, mask=mask, reinit_hidden=reinit_hidden,
-                                      out_scale=0.25)
+        enc_dtype = getattr(self, "encoder_autocast", None)      # training: run the encoder in bf16 (train.py)
+        import contextlib
+        ctx = (torch.autocast("cuda", dtype=enc_dtype) if (enc_dtype is not None and torch.is_grad_enabled())
+               else contextlib.nullcontext())
+        with ctx:
+            if self.input_mode == "SingleScale":   # net.py:141-145: no mask, the presence tests are data-dependent
+                fmap, imap, _ = self.encoder(events=events, images=images, reinit_hidden=reinit_hidden,
+                                             out_scale=0.25)
+                mask_l = [True] * fmap.shape[1]
+            else:
+                fmap, imap = self.encoder(events=events, images=images, mask=mask, reinit_hidden=reinit_hidden,
+                                          out_scale=0.25)
+        if fmap.dtype == torch.bfloat16:
+            fmap, imap = fmap.float(), imap.float()
         if coords is not None:
             cur.wait_stream(side)
             if not torch.cuda.is_current_stream_capturing():
@@ -343,6 +391,30 @@ class Patchifier(nn.Module):
         return fmap, gmap, imap, patches, index, clr
 
 
+class CorrBlock:
+    """ramp/net.py:206-229: training-time correlation lookup (edge dropout in the backward pass only)"""
+
+    def __init__(self, fmap, gmap, radius=3, dropout=0.2, levels=(1, 4)):
+        self.dropout, self.radius, self.levels = dropout, radius, list(levels)
+        self.gmap = gmap
+        b, n, c, h, w = fmap.shape
+        self.pyramid = [F.avg_pool2d(fmap.view(b * n, c, h, w), l, stride=l).view(b, n, c, h // l, w // l)
+                        for l in self.levels]                                      # utils.py:81-90 pyramidify
+
+    def __call__(self, ii, jj, coords):
+        corrs = [altcorr.corr(self.gmap, self.pyramid[i], coords / self.levels[i], ii, jj, self.radius, self.dropout)
+                 for i in range(len(self.levels))]
+        return torch.stack(corrs, -1).view(1, len(ii), -1)
+
+
+def motion_bootstrap(n, poses, MOTION_MODEL, MOTION_DAMPING):
+    """ramp/pose_prediction/pose_pred_utils.py:189-198: damped-linear extrapolation of the newest pose"""
+    if MOTION_MODEL == 'DAMPED_LINEAR':
+        P1, P2 = SE3(poses[n - 1]), SE3(poses[n - 2])
+        return (SE3.exp(MOTION_DAMPING * (P1 * P2.inv()).log()) * P1).data
+    return poses[n - 1]
+
+
 class VONet(nn.Module):
     """ramp/net.py:232-249 (constructor surface).  `.forward` of the reference is the training
     unroll (net.py:252-378), which belongs to the training row."""
@@ -361,6 +433,71 @@ class VONet(nn.Module):
                                    input_mode=self.input_mode)
         self.update = Update(self.P)
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError("VONet.forward (training unroll, ramp/net.py:252-378) is not built: "
-                                  "this package covers the online tracking path (Ramp_vo)")
+    def forward(self, input_, poses, disps, intrinsics, STEPS=12, structure_only=False):
+        """The training unroll (ramp/net.py:252-378): patchify a whole clip, then STEPS recurrent updates, each
+        followed by two differentiable Gauss-Newton steps (rampvo_b200.ba.BA); frames beyond the first 8 join one
+        per step.  Returns the reference's trajectory list [(valid, coords, coords_gt, Gs[:, :n], Ps[:, :n])].
+        (Upstream unpacks five values from patchify, which returns six — net.py:263 vs :203 — so the reference
+        cannot run this method as shipped; the unpack is the only deviation here.)"""
+        input_ = preprocess_input(input_tensor=input_)
+        if not isinstance(poses, SE3):
+            poses = SE3(poses)
+        intrinsics = intrinsics / 4.0
+        disps = disps[:, :, 1::4, 1::4].float()
+        fmap, gmap, imap, patches, ix, _ = self.patchify(input_=input_, disps=disps, reinit_hidden=True,
+                                                         event_bias=self.EVENT_BIAS)
+        corr_fn = CorrBlock(fmap, gmap)
+        b, N, c, h, w = fmap.shape
+        p = self.P
+        dev = fmap.device
+        patches_gt = patches.clone()
+        Ps = poses
+        d = patches[..., 2, p // 2, p // 2]
+        patches = patches.clone()
+        patches[..., 2, :, :] = torch.rand_like(d)[..., None, None]                  # set_depth, utils.py:99-101
+        kk, jj = flatmeshgrid(torch.where(ix < 8)[0], torch.arange(0, 8, device=dev), indexing="ij")
+        ii = ix[kk]
+        imap = imap.view(b, -1, DIM)
+        net = torch.zeros(b, len(kk), DIM, device=dev, dtype=torch.float)
+        Gs = SE3.IdentityLike(poses)
+        if structure_only:
+            Gs = SE3(poses.data.clone())
+        traj = []
+        bounds = [-64, -64, w + 64, h + 64]
+        n_input = input_[1].shape[1]
+        while len(traj) < STEPS:
+            Gs = Gs.detach()
+            patches = patches.detach()
+            n = int(ii.max().item()) + 1
+            if len(traj) >= 8 and n < n_input:
+                if not structure_only:
+                    data = Gs.data.clone()
+                    data[:, n] = motion_bootstrap(MOTION_DAMPING=self.MOTION_DAMPING, MOTION_MODEL=self.MOTION_MODEL,
+                                                  poses=Gs.data[0, :], n=n)
+                    Gs = SE3(data)
+                kk1, jj1 = flatmeshgrid(torch.where(ix < n)[0], torch.arange(n, n + 1, device=dev), indexing="ij")
+                kk2, jj2 = flatmeshgrid(torch.where(ix == n)[0], torch.arange(0, n + 1, device=dev), indexing="ij")
+                ii = torch.cat([ix[kk1], ix[kk2], ii])
+                jj = torch.cat([jj1, jj2, jj])
+                kk = torch.cat([kk1, kk2, kk])
+                net = torch.cat([torch.zeros(b, len(kk1) + len(kk2), DIM, device=dev), net], dim=1)
+                if np.random.rand() < 0.1:
+                    k = (ii != (n - 4)) & (jj != (n - 4))
+                    ii, jj, kk, net = ii[k], jj[k], kk[k], net[:, k]
+                patches = patches.clone()
+                patches[:, ix == n, 2] = torch.median(patches[:, (ix == n - 1) | (ix == n - 2), 2])
+                n = int(ii.max().item()) + 1
+            coords = pops.transform(Gs, patches, intrinsics, ii, jj, kk)
+            coords1 = coords.permute(0, 1, 4, 2, 3).contiguous()
+            corr = corr_fn(kk, jj, coords1)
+            net, (delta, weight, _) = self.update(net, imap[:, kk], corr, None, ii, jj, kk)
+            target = coords[..., p // 2, p // 2, :] + delta
+            for _ in range(2):
+                Gs, patches = BA(Gs, patches, intrinsics, target, weight, 1e-4, ii, jj, kk, bounds, ep=10,
+                                 fixedp=1, structure_only=structure_only)
+            dij = (ii - jj).abs()
+            k = (dij > 0) & (dij <= 2)
+            coords = pops.transform(Gs, patches, intrinsics, ii[k], jj[k], kk[k])
+            coords_gt, valid, _ = pops.transform(Ps, patches_gt, intrinsics, ii[k], jj[k], kk[k], jacobian=True)
+            traj.append((valid, coords, coords_gt, Gs[:, :n], Ps[:, :n]))
+        return traj

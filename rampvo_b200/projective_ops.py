@@ -37,6 +37,9 @@ def transform(poses, patches, intrinsics, ii, jj, kk, depth=False, valid=False, 
 
     Returns x1 [1,E,P,P,2] (or [...,3] with depth=True); with valid=True also (Z > 0.2) [1,E,P,P];
     with jacobian=True (x1, valid [1,E], (Ji [1,E,2,6], Jj [1,E,2,6], Jz [1,E,2,1]))."""
+    pd = getattr(poses, "data", poses)
+    if torch.is_grad_enabled() and (pd.requires_grad or patches.requires_grad):
+        return _transform_autograd(poses, patches, intrinsics, ii, jj, kk, depth, valid, jacobian, tonly)
     pv, qv, kv, P, (ii, jj, kk) = _prep(poses, patches, intrinsics, ii, jj, kk)
     E = ii.numel()
     dev = pv.device
@@ -63,6 +66,39 @@ def transform(poses, patches, intrinsics, ii, jj, kk, depth=False, valid=False, 
         x1 = torch.cat([x1, d[..., None]], dim=-1)
     if valid:
         return x1, v
+    return x1
+
+
+def _transform_autograd(poses, patches, intrinsics, ii, jj, kk, depth, valid, jacobian, tonly):
+    """The same map as the fused kernel written with tensor ops, used ONLY while gradients are being recorded
+    (training unroll, ramp/net.py:341-371): autograd differentiates it w.r.t. poses and patches."""
+    poses = poses if isinstance(poses, SE3) else SE3(poses)
+    X0 = iproj(patches[:, kk], intrinsics[:, ii])
+    Gij = poses[:, jj] * poses[:, ii].inv()
+    if tonly:
+        ident = torch.zeros_like(Gij.data[..., 3:])
+        ident[..., 3] = 1.0
+        Gij = SE3(torch.cat([Gij.data[..., :3], ident], dim=-1))
+    X1 = Gij[:, :, None, None] * X0
+    x1 = proj(X1, intrinsics[:, jj], depth)
+    if jacobian:
+        p = X1.shape[2]
+        X, Y, Z, H = X1[..., p // 2, p // 2, :].unbind(dim=-1)
+        o = torch.zeros_like(H)
+        fx, fy, cx, cy = intrinsics[:, jj].unbind(dim=-1)
+        d = torch.where(Z.abs() > 0.2, 1.0 / torch.where(Z.abs() > 0.2, Z, torch.ones_like(Z)), o)
+        Ja = torch.stack([H, o, o, o, Z, -Y,
+                          o, H, o, -Z, o, X,
+                          o, o, H, Y, -X, o,
+                          o, o, o, o, o, o], dim=-1).view(1, len(ii), 4, 6)
+        Jp = torch.stack([fx * d, o, -fx * X * d * d, o,
+                          o, fy * d, -fy * Y * d * d, o], dim=-1).view(1, len(ii), 2, 4)
+        Jj = torch.matmul(Jp, Ja)
+        Ji = -Gij[:, :, None].adjT(Jj)
+        Jz = torch.matmul(Jp, Gij.matrix()[..., :, 3:])
+        return x1, (Z > 0.2).float(), (Ji, Jj, Jz)
+    if valid:
+        return x1, (X1[..., 2] > 0.2).float()
     return x1
 
 

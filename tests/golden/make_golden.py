@@ -194,6 +194,16 @@ def main():
     coords = ns["get_coords_from_topk_events"](events=ev, patches_per_image=96, border_suppression_size=0,
                                                non_max_supp_rad=11)
     np.savez_compressed(os.path.join(HERE, "patch_selection.npz"), coords=coords.numpy())
+    # ---- (h) MultiScale encoder on a 4-frame CLIP in one call (per-pixel LSTM sequences of length 4), fp32 CPU
+    torch.manual_seed(GI.ENCODER_SEED)
+    mine = MyEnc(5, 3)
+    ref_enc.load_state_dict(mine.state_dict(), strict=True)
+    ev, im, mask = GI.encoder_clip_inputs()
+    with torch.no_grad():
+        fmap, imap = ref_enc(events=ev, images=im, mask=mask, reinit_hidden=True)
+    np.savez_compressed(os.path.join(HERE, "encoder_clip.npz"), fmap=fmap[0].numpy().astype(np.float32),
+                        imap16=imap[0, :, :16].numpy().astype(np.float32))
+
     # ---- (g) SingleScale encoder (ramp/extractor.py:187-269), three frames with carried LSTM state, fp32 CPU
     from rampvo_b200.extractor import MergerLSTMsceneEncoder as MySS
     torch.manual_seed(GI.ENCODER_SEED)

@@ -91,3 +91,12 @@ def single_scale_inputs(device="cpu", ht=32, wd=48):
             im = torch.zeros_like(im)
         frames.append((ev.to(device), im.to(device)))
     return frames
+
+
+def encoder_clip_inputs(device="cpu", T=4, ht=32, wd=48):
+    """one CALL with T frames: the per-pixel LSTMs then see sequences of length T (training clips)"""
+    g = torch.Generator().manual_seed(82)
+    ev = torch.poisson(torch.full((1, T, 5, ht, wd), 0.3), generator=g)
+    ev = ev * (torch.randint(0, 2, ev.shape, generator=g) * 2 - 1)
+    im = torch.rand(1, T, 3, ht, wd, generator=g) * 2 - 0.5
+    return ev.to(device), im.to(device), torch.ones(1, T, dtype=torch.bool)

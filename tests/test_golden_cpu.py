@@ -154,3 +154,39 @@ def test_single_scale_encoder_matches_reference_on_cpu():
             fmap, imap, _ = enc(events=ev, images=im, reinit_hidden=(f == 0))
             assert rel_err(fmap[0, 0].numpy(), z["fmap_%d" % f]) < 1e-5
             assert rel_err(imap[0, 0].numpy(), z["imap_%d" % f]) < 1e-5
+
+
+def test_differentiable_ba_matches_reference_python_ba():
+    """rampvo_b200.ba.BA (the training-time Gauss-Newton step, tensor algebra) vs the fixture produced by the
+    reference's ramp/ba.py — and gradients reach the confidence weights and targets through both iterations"""
+    from rampvo_b200 import ba as myba
+    from rampvo_b200.lietorch import SE3
+    z = np.load(os.path.join(G, "python_ba.npz"))
+    prob, tgt = GI.ba_problem(O)
+    t = GI.as_torch(prob, torch.float64)
+    poses, patches = SE3(t["poses"].clone().requires_grad_(True)), t["patches"].clone().requires_grad_(True)
+    tg = torch.from_numpy(tgt).double()[None].requires_grad_(True)
+    wg = torch.from_numpy(prob["weight"]).double()[None].requires_grad_(True)
+    for it in (1, 2):
+        poses, patches = myba.BA(poses, patches, t["intrinsics"], tg, wg, 1e-4, t["ii"], t["jj"], t["kk"],
+                                 bounds=[-64, -64, 160 + 64, 120 + 64], ep=1.0, fixedp=prob["t0"])
+        assert np.abs(poses.data[0].detach().numpy() - z["poses_%d" % it]).max() < 1e-12
+        assert np.abs(patches[0, :, 2, 0, 0].detach().numpy() - z["disps_%d" % it]).max() < 1e-12
+    (poses.data[..., :3].sum() + patches[:, :, 2].sum()).backward()
+    assert torch.isfinite(wg.grad).all() and wg.grad.abs().sum() > 0
+    assert torch.isfinite(tg.grad).all() and tg.grad.abs().sum() > 0
+
+
+def test_encoder_clip_matches_reference_on_cpu():
+    """T = 4 frames in ONE call: the reference's per-pixel nn.LSTM runs over the 4-step sequence
+    (ramp/extractor.py:364-381), which only the training unroll exercises"""
+    from rampvo_b200.extractor import MultiScaleMergerDoubleNet
+    z = np.load(os.path.join(G, "encoder_clip.npz"))
+    torch.manual_seed(GI.ENCODER_SEED)
+    enc = MultiScaleMergerDoubleNet(5, 3).eval()
+    ev, im, mask = GI.encoder_clip_inputs()
+    with torch.no_grad():
+        fmap, imap = enc(events=ev, images=im, mask=mask, reinit_hidden=True)
+    assert fmap.shape == (1, 4, 128, 8, 12)
+    assert rel_err(fmap[0].numpy(), z["fmap"]) < 1e-4
+    assert rel_err(imap[0, :, :16].numpy(), z["imap16"]) < 1e-4
