@@ -202,6 +202,23 @@ def run_ours(args):
 
         E_local = int(vo.ii.numel())
         coll = (vo.collective_calls, vo.collective_bytes)
+        replicas = None
+        if sharded and not args.no_replicas:
+            # context for the strong-scaling number: the same box running one INDEPENDENT stream per GPU (weak
+            # scaling, no data-path collective), measured in the same job
+            vo_sh = vo
+            seq_r = synth.SyntheticSequence(seed=rank, device=dev)
+            fr_r = [seq_r.frame(t) for t in range(SETUP_FRAMES + W + K)]
+            torch.cuda.synchronize()
+            vo_r = build_vo(dev, config=args.config)
+            state["vo"] = vo_r
+            for t in range(SETUP_FRAMES):
+                vo_r(t, fr_r[t], intr)
+            ms_r, _, _ = timed(lambda t: vo_r(t, fr_r[t], intr), SETUP_FRAMES)
+            replicas = {"value": world * K / (ms_r * 1e-3), "unit": UNIT, "scaling": "weak", "ms_per_step": ms_r / K,
+                        "parallelism": "one independent stream per GPU, no data-path collective"}
+            state["vo"] = vo = vo_sh
+            del vo_r, fr_r
         if sharded:     # the roofline launch below is measured on the FULL graph: gather nothing, rebuild it
             from rampvo_b200 import synth as _s
             M_, life, rem, _ = _s.CONFIGS[args.config]
@@ -274,6 +291,8 @@ def run_ours(args):
                      "frac": alg / corr_s / 1e9 / peaks["hbm_gbs"], "traffic": traffic,
                      "peak_source": which, "algorithmic_bytes": alg, "launch_us": corr_s * 1e6},
     }
+    if sharded and replicas is not None:
+        line["replicas"] = replicas
     if sharded:
         line["collectives"] = {"calls_total": coll[0], "bytes_total": coll[1], "frames": vo.counter,
                                "note": "per rank, since the start of the stream (setup + warm-up + timed frames)"}
@@ -468,6 +487,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--no-replicas", action="store_true", help="N > 1 sharded mode: skip the replica-throughput leg")
     ap.add_argument("--config", default="default", choices=sorted(WORKLOADS),
                     help="VO preset: default.yaml (the metric's configuration), precise.yaml, fast.yaml")
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"],

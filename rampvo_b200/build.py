@@ -73,11 +73,55 @@ def build_library(force=False, verbose=False, debug=False):
             sys.stderr.write(out.decode(errors="replace"))
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % src)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs
+    cmd = [nvcc, "-arch=sm_100a", "-shared", "-o", LIB] + objs     # no default-arch (sm_52) link stub
     subprocess.check_call(cmd)
     with open(STAMP, "w") as fh:
         fh.write(fp)
     return LIB
+
+
+def sass_summary(out_path=None):
+    """Per-kernel counts of the SASS mnemonics that prove which hardware path a kernel uses (tcgen05 MMA = UTCHMMA /
+    UTCQMMA, TMEM loads = LDTM, TMA = UTMALDG / UBLKCP, Ampere-style tensor cores = HMMA, cp.async = LDGSTS), from
+    `cuobjdump -sass` of the built library.  Written to profiles/sass_summary.txt by __graft_entry__.build()."""
+    import re
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    txt = subprocess.run([cuobjdump, "-sass", LIB], capture_output=True, text=True, check=True).stdout
+    keys = ("UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "HMMA", "LDGSTS", "SYNCS")
+    rows, cur, cnt, arch = [], None, None, set()
+    filt = shutil.which("c++filt")
+    for line in txt.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            if cur:
+                rows.append((cur, cnt))
+            cur, cnt = m.group(1), dict.fromkeys(keys, 0)
+            continue
+        m = re.search(r"arch = (sm_\w+)", line)
+        if m:
+            arch.add(m.group(1))
+        if cur:
+            for k in keys:
+                if re.search(r"\b%s(\.|\b)" % k, line):
+                    cnt[k] += 1
+    if cur:
+        rows.append((cur, cnt))
+    names = [r[0] for r in rows]
+    if filt and names:
+        dem = subprocess.run([filt], input="\n".join(names), capture_output=True, text=True).stdout.splitlines()
+        if len(dem) == len(names):
+            names = [d.split("(")[0][-60:] for d in dem]
+    lines = ["# SASS summary of rampvo_b200/librampvo_b200.so (cuobjdump -sass; code objects: %s)" % ", ".join(sorted(arch)),
+             "# %-58s %s" % ("kernel", " ".join("%8s" % k for k in keys))]
+    for n, (_, c) in sorted(zip(names, rows), key=lambda x: x[0]):
+        if any(c.values()):
+            lines.append("%-60s %s" % (n, " ".join("%8d" % c[k] for k in keys)))
+    out = "\n".join(lines) + "\n"
+    if out_path:
+        os.makedirs(os.path.dirname(out_path), exist_ok=True)
+        with open(out_path, "w") as fh:
+            fh.write(out)
+    return out
 
 
 if __name__ == "__main__":
