@@ -61,9 +61,23 @@ def trace():
                   " ".join("%d/%d" % (rel(t[6][i]), rel(t[7][i])) for i in range(16) if t[7][i] >= t0))
 
 
+def one(idx):
+    """a handful of launches of one layer shape (for `ncu -k regex:conv_tc_kernel`)"""
+    name, C0, C1, Cout, ks, sd, pd, H, W = SHAPES[idx]
+    conv = nn.Conv2d(C0 + C1, Cout, ks, stride=sd, padding=pd).cuda()
+    x = torch.randn(1, C0, H, W, device="cuda").half().contiguous(memory_format=CL)
+    x2 = torch.randn(1, C1, H, W, device="cuda").half().contiguous(memory_format=CL) if C1 else None
+    for _ in range(6):
+        _conv_tc(conv, x, x2, stats=True)
+    torch.cuda.synchronize()
+    print(name)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "trace":
         return trace()
+    if len(sys.argv) > 2 and sys.argv[1] == "one":
+        return one(int(sys.argv[2]))
     torch.backends.cudnn.benchmark = True
     lines = []
     for name, C0, C1, Cout, ks, sd, pd, H, W in SHAPES:
