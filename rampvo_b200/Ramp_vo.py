@@ -203,6 +203,7 @@ class _UpdateGraph:
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             plans = vo._new_plans(self.ii, self.jj, self.kk)
+        self.plans = plans
         _, self.weight = vo._update_body(self.ii, self.jj, self.kk, self.net_in, self.net_out, plans,
                                          0, self.n_free, t0_dev=self.t0,
                                          before_update=lambda: cur.wait_stream(side),
@@ -226,6 +227,7 @@ class Ramp_vo:
         self.cfg = cfg
         self.world_size, self.rank, self.group = int(world_size), int(rank), group
         self._owner = []            # owner rank of every live frame slot (follows frames through keyframe drops)
+        self._owner_dev = None      # the same table on the device (sharded mode)
         self.collective_bytes = 0   # bytes this rank put through collectives (sharded mode)
         self.collective_calls = 0
         self.event_bias = train_cfg["event_bias"]
@@ -576,6 +578,8 @@ class Ramp_vo:
                 self._fmap2_store[dst] = self._fmap2_store[src]
             if len(self._owner) > k:
                 del self._owner[k]
+                if self._owner_dev is not None:
+                    self._owner_dev[k:n - 1] = self._owner_dev[k + 1:n].clone()
             self.n -= 1
             self.m -= self.M
         lim = self.n - self.cfg.REMOVAL_WINDOW
@@ -669,6 +673,7 @@ class Ramp_vo:
         self._ukey_hist = (self._ukey_hist + [self._ukey_prev])[-4:]
         self._ukey_prev = key
         P = self.P
+        plans = None
         if E == 0:      # this rank owns no edge yet: it still takes part in the collectives
             z = torch.zeros(1, 0, 2, device=self.device)
             coords, delta, weight = torch.zeros(1, 0, 2, P, P, device=self.device), z, z
@@ -683,6 +688,7 @@ class Ramp_vo:
             g.run(t0)
             self._net_swap(E)
             coords, delta, weight = g.weight
+            plans = g.plans
         else:
             plans = self._graph_plans()
             other = self._net_other(E)
@@ -696,14 +702,16 @@ class Ramp_vo:
         try:
             sharded.sharded_BA_fused(self.poses, self.patches, self.intrinsics, coords, delta, weight, self.ht // 4,
                                      self.wd // 4, self.lmbda, self.ii, self.jj, self.kk, t0, self.n, iterations=2,
-                                     weight_out=wf, group=self.group)
+                                     weight_out=wf, group=self.group,
+                                     plan=plans.plan_k if plans is not None else None)
         except RuntimeError as e:
             print(f"WARNING: BA failed...{e}")
         self.last_weight = wf
         self.collective_bytes += 2 * n6 * (n6 + 1) * 4
         self.collective_calls += 2
         lo = max(self.n - self.cfg.REMOVAL_WINDOW - 2, 0)
-        sharded.exchange_depths_owned(self.patches_, self._owner, lo, self.n, self.rank, self.group)
+        sharded.exchange_depths_owned(self.patches_, self._owner_dev if self._owner_dev is not None else self._owner,
+                                      lo, self.n, self.rank, self.group)
         self.collective_bytes += (self.n - lo) * self.M * P * P * 4
         self.collective_calls += 1
         pts = pops.point_cloud_centers(SE3(self.poses), self.patches[:, :self.m], self.intrinsics, self.ix[:self.m])
@@ -821,6 +829,10 @@ class Ramp_vo:
                 return
 
         self._owner = self._owner[:self.n] + [(self.counter - 1) % self.world_size]
+        if self.world_size > 1:
+            if self._owner_dev is None:
+                self._owner_dev = torch.full((self.N,), -1, dtype=torch.int32, device=self.device)
+            self._owner_dev[self.n] = self._owner[-1]
         self.n += 1
         self.m += self.M
         self.append_factors(*self._edges_forw())

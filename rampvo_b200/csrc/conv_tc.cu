@@ -29,6 +29,7 @@ constexpr int kCvMaxStages = 8;
 constexpr int kCvAStage = kCvM * 128;          // 16 KB: 128 rows x 64 halves
 constexpr int kCvMaxKB = 13;                   // 7x7x16 = 784 -> 13 K blocks
 constexpr int kCvMaxN = 192;
+constexpr size_t kCvMaxDynSmem = 222 * 1024;   // + ~4 KB of static shared memory <= 227 KB per CTA
 constexpr int kCvThreads = 640;                // warp 0 TMA (W), warp 1 MMA, warps 4-11 epilogue, 12-19 A producers
 
 struct ConvArgs {
@@ -345,7 +346,7 @@ extern "C" int rvo_conv2d_nhwc(const void* src0, int C0, const void* src1, int C
   auto fits = [&](int ns) {
     const int N = Cout / ns;
     return Cout % ns == 0 && N % 16 == 0 && N <= kCvMaxN &&
-           (size_t)KB * N * 128 + 1024 + (size_t)4 * kCvAStage + 1024 <= 225 * 1024;
+           (size_t)KB * N * 128 + 1024 + (size_t)4 * kCvAStage + 1024 <= kCvMaxDynSmem;
   };
   while (n_slices <= 16 && !fits(n_slices)) n_slices++;
   RVO_CHECK_ARG(n_slices <= 16, "rvo_conv2d_nhwc: Cout = %d with K = %d does not fit", Cout, Kpad);
@@ -364,14 +365,16 @@ extern "C" int rvo_conv2d_nhwc(const void* src0, int C0, const void* src1, int C
   while (cols < 2u * N) cols <<= 1;
   a.tmem_cols = cols;
   const size_t wbytes = (((size_t)KB * N * 128 + 1023) & ~(size_t)1023);
-  int stages = (int)((225 * 1024 - 1024 - wbytes) / kCvAStage);
+  int stages = (int)((kCvMaxDynSmem - 1024 - wbytes) / kCvAStage);
   a.stages = stages > kCvMaxStages ? kCvMaxStages : stages;
   a.wo_magic = (uint32_t)((0x100000000ull + (uint64_t)Wo - 1) / (uint64_t)Wo);
   RVO_CHECK_ARG(P < (int64_t)(0x100000000ull / (uint64_t)Wo) && (int64_t)H * W * (C0 > C1 ? C0 : C1) < 0x7fffffffll,
                 "rvo_conv2d_nhwc: tensor too large for 32-bit index arithmetic");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = wbytes + (size_t)a.stages * kCvAStage + 1024;
-  RVO_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // one fixed opt-in for every layer shape: the attribute is per-function state, and a captured graph node must stay
+  // launchable after a later call for a smaller layer (ncu replays graph nodes with the CURRENT attribute)
+  RVO_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCvMaxDynSmem));
   conv_tc_kernel<<<grid, kCvThreads, smem, st>>>(a, tmw);
   RVO_LAUNCH_CHECK("conv_tc_kernel");
   return RVO_OK;

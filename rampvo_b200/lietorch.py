@@ -55,10 +55,12 @@ def _hat(phi):
 def _so3_exp(phi):
     """so3.h:153-170"""
     theta2 = (phi * phi).sum(-1, keepdim=True)
-    theta = theta2.sqrt()
+    small = theta2 < EPS * EPS
+    # the square root is taken of a value bounded away from zero so that autograd never sees d sqrt(0) = inf
+    # (the training unroll differentiates through exp / log of identity-like poses); values are unchanged
+    theta = torch.where(small, torch.ones_like(theta2), theta2).sqrt()
     theta4 = theta2 * theta2
-    small = theta < EPS
-    safe = torch.where(small, torch.ones_like(theta), theta)
+    safe = theta
     imag = torch.where(small, 0.5 - (1.0 / 48.0) * theta2 + (1.0 / 3840.0) * theta4,
                        torch.sin(0.5 * safe) / safe)
     real = torch.where(small, 1.0 - (1.0 / 8.0) * theta2 + (1.0 / 384.0) * theta4,
@@ -70,9 +72,9 @@ def _so3_log(q):
     """so3.h:115-151"""
     qv, w = q[..., :3], q[..., 3:4]
     sq = (qv * qv).sum(-1, keepdim=True)
-    n = sq.sqrt()
     small = sq < EPS * EPS
-    safe_n = torch.where(small, torch.ones_like(n), n)
+    n = torch.where(small, torch.ones_like(sq), sq).sqrt()
+    safe_n = n
     wz = w.abs() < EPS
     safe_w = torch.where(wz, torch.ones_like(w), w)
     f_small = 2.0 / safe_w - (2.0 / 3.0) * sq / (safe_w * safe_w * safe_w)
@@ -88,10 +90,9 @@ def _left_jacobian(phi):
     Phi = _hat(phi)
     Phi2 = Phi @ Phi
     theta2 = (phi * phi).sum(-1, keepdim=True)
-    theta = theta2.sqrt()
-    small = theta < EPS
+    small = theta2 < EPS * EPS
     st2 = torch.where(small, torch.ones_like(theta2), theta2)
-    st = torch.where(small, torch.ones_like(theta), theta)
+    st = st2.sqrt()
     c1 = torch.where(small, 0.5 - (1.0 / 24.0) * theta2, (1.0 - torch.cos(st)) / st2)
     c2 = torch.where(small, 1.0 / 6.0 - (1.0 / 120.0) * theta2, (st - torch.sin(st)) / (st2 * st))
     return I + c1[..., None] * Phi + c2[..., None] * Phi2
@@ -102,11 +103,11 @@ def _left_jacobian_inverse(phi):
     I = torch.eye(3, dtype=phi.dtype, device=phi.device).expand(phi.shape[:-1] + (3, 3))
     Phi = _hat(phi)
     Phi2 = Phi @ Phi
-    theta = (phi * phi).sum(-1, keepdim=True).sqrt()
-    small = theta < EPS
-    st = torch.where(small, torch.ones_like(theta), theta)
+    theta2 = (phi * phi).sum(-1, keepdim=True)
+    small = theta2 < EPS * EPS
+    st = torch.where(small, torch.ones_like(theta2), theta2).sqrt()
     half = 0.5 * st
-    c2 = torch.where(small, torch.full_like(theta, 1.0 / 12.0),
+    c2 = torch.where(small, torch.full_like(theta2, 1.0 / 12.0),
                      (1.0 - st * torch.cos(half) / (2.0 * torch.sin(half))) / (st * st))
     return I - 0.5 * Phi + c2[..., None] * Phi2
 

@@ -91,20 +91,24 @@ def sharded_BA(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0
 
 
 def exchange_depths_owned(patches_, owners, frame_lo, frame_hi, rank, group=None):
-    """exchange_depths for an explicit per-frame owner list (Ramp_vo keeps one: ownership follows a frame through
-    keyframe removals, which renumber the frames).  patches_ [N, M, 3, P, P]."""
+    """exchange_depths for an explicit per-frame owner table (Ramp_vo keeps one: ownership follows a frame through
+    keyframe removals, which renumber the frames).  patches_ [N, M, 3, P, P]; owners: a list of ranks or a DEVICE
+    int tensor [N] (no host->device copy on the per-update path)."""
     if frame_hi <= frame_lo or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
     sl = patches_[frame_lo:frame_hi, :, 2]                                   # [F, M, P, P] view
-    mine = torch.tensor([1.0 if o == rank else 0.0 for o in owners[frame_lo:frame_hi]], device=patches_.device,
-                        dtype=sl.dtype).view(-1, 1, 1, 1)
+    if torch.is_tensor(owners):
+        mine = (owners[frame_lo:frame_hi] == rank).to(sl.dtype).view(-1, 1, 1, 1)
+    else:
+        mine = torch.tensor([1.0 if o == rank else 0.0 for o in owners[frame_lo:frame_hi]], device=patches_.device,
+                            dtype=sl.dtype).view(-1, 1, 1, 1)
     buf = (sl * mine).contiguous()
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     sl.copy_(buf)
 
 
 def sharded_BA_fused(poses, patches, intrinsics, coords, delta, weight, ht, wd, lmbda, ii, jj, kk, t0, t1,
-                     iterations=2, weight_out=None, group=None):
+                     iterations=2, weight_out=None, group=None, plan=None):
     """sharded_BA with the target formation / filter_features folded into the assembly (rvo_ba_assemble_fused):
     coords [1,E,2,P,P], delta / weight [1,E,2] of THIS rank's edges.  Collective per iteration: one all-reduce of
     [S | y] (6N x (6N+1) fp32)."""
@@ -124,7 +128,12 @@ def sharded_BA_fused(poses, patches, intrinsics, coords, delta, weight, ht, wd, 
     Sy = torch.zeros(max(n6, 1), n6 + 1, dtype=torch.float32, device=dev)
     st = _lib.stream_ptr(dev)
     with torch.cuda.device(dev):
-        if E:
+        if E and plan is not None:
+            # the update operator already grouped these edges by (kk, jj): the workspace starts with a plan of the
+            # same layout (rvo_plan_bytes), so the sort is replaced by one device copy
+            nb = L.rvo_plan_bytes(E)
+            ws[:nb].copy_(plan.view(torch.uint8).reshape(-1)[:nb])
+        elif E:
             _lib.check(L.rvo_ba_plan(_lib.ptr(kk), _lib.ptr(jj), E, pv.shape[0], qv.shape[0], N,
                                      _lib.ptr(ws), ws.numel(), st), "rvo_ba_plan")
         for it in range(iterations):
