@@ -296,6 +296,146 @@ stem_kernel(StemParams sp, const float* __restrict__ params, const float* __rest
 }  // namespace rvo
 
 namespace rvo {
+
+// ------------------------------------------------------------------ recurrent stem, thread-per-pixel variant ----
+//
+// Scales 1 and 2 (hidden 16 / 32, 307 200 / 76 800 output pixels): ONE thread owns ONE output pixel end to end —
+// conv_1 taps, both one-step LSTM cells and the two super-state matrix-vector products — with every intermediate in
+// registers and the weights read from shared memory as warp-wide broadcasts (float4 = 4 FMAs per load).  No
+// block-level synchronisation after the parameter load, inputs planar (coalesced across the warp), state in / out
+// as 32 / 64 contiguous bytes per thread.  The tiled mma.sync kernel above spends ~2.7 us per 64-pixel tile on
+// shared-memory round trips and barriers (89 / 57 us per launch); this one is bound by its ~1.5 k / 5 k FMAs per
+// pixel.  fp32 arithmetic; the intermediate super state is rounded to fp16 like the reference under autocast.
+template <int HID, int KS>
+__global__ void __launch_bounds__(128)
+stem_px_kernel(StemParams sp, const float* __restrict__ params, const float* __restrict__ events,
+               const float* __restrict__ image, const __half* __restrict__ ss_prev, int use_image,
+               __half* __restrict__ ss_out) {
+  extern __shared__ float P[];
+  for (int i = threadIdx.x; i < sp.n_params; i += blockDim.x) P[i] = params[i];
+  __syncthreads();
+  constexpr int S = KS == 1 ? 1 : KS - 1, PAD = KS == 1 ? 0 : 1;
+  const int npix = sp.Ho * sp.Wo;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const int oy = p / sp.Wo, ox = p - oy * sp.Wo;
+  // ---- conv_1 of both modalities (extractor.py:326-345)
+  float xe[5], xi[3];
+#pragma unroll
+  for (int c = 0; c < 5; c++) xe[c] = c < sp.Ce ? P[sp.o_bce + c] : 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; c++) xi[c] = c < sp.Ci ? P[sp.o_bci + c] : 0.f;
+#pragma unroll
+  for (int ky = 0; ky < KS; ky++) {
+    const int iy = oy * S - PAD + ky;
+    const bool oky = (unsigned)iy < (unsigned)sp.H;
+#pragma unroll
+    for (int kx = 0; kx < KS; kx++) {
+      const int ix = ox * S - PAD + kx;
+      const bool ok = oky && (unsigned)ix < (unsigned)sp.W;
+      const size_t off = ok ? (size_t)iy * sp.W + ix : 0;
+#pragma unroll
+      for (int ci = 0; ci < 5; ci++) {
+        if (ci < sp.Ce) {
+          const float v = ok ? events[(size_t)ci * sp.H * sp.W + off] : 0.f;
+#pragma unroll
+          for (int co = 0; co < 5; co++)
+            if (co < sp.Ce) xe[co] = fmaf(P[sp.o_wce + ((co * sp.Ce + ci) * KS + ky) * KS + kx], v, xe[co]);
+        }
+      }
+#pragma unroll
+      for (int ci = 0; ci < 3; ci++) {
+        if (ci < sp.Ci) {
+          const float v = ok ? image[(size_t)ci * sp.H * sp.W + off] : 0.f;
+#pragma unroll
+          for (int co = 0; co < 3; co++)
+            if (co < sp.Ci) xi[co] = fmaf(P[sp.o_wci + ((co * sp.Ci + ci) * KS + ky) * KS + kx], v, xi[co]);
+        }
+      }
+    }
+  }
+  // ---- one LSTM step from a zero state per modality (gates i, g, o; extractor.py:351-381)
+  float in[2 * HID];                               // [ss_prev | h_ev], later [ss_1 | h_im]
+  float him[HID];
+#pragma unroll
+  for (int j = 0; j < HID; j++) {
+    float gi = P[sp.o_bge + j], gg = P[sp.o_bge + HID + j], go = P[sp.o_bge + 2 * HID + j];
+#pragma unroll
+    for (int c = 0; c < 5; c++)
+      if (c < sp.Ce) {
+        gi = fmaf(P[sp.o_wge + j * sp.Ce + c], xe[c], gi);
+        gg = fmaf(P[sp.o_wge + (HID + j) * sp.Ce + c], xe[c], gg);
+        go = fmaf(P[sp.o_wge + (2 * HID + j) * sp.Ce + c], xe[c], go);
+      }
+    in[HID + j] = sigmoidf_(go) * tanhf_(sigmoidf_(gi) * tanhf_(gg));
+    gi = P[sp.o_bgi + j]; gg = P[sp.o_bgi + HID + j]; go = P[sp.o_bgi + 2 * HID + j];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      if (c < sp.Ci) {
+        gi = fmaf(P[sp.o_wgi + j * sp.Ci + c], xi[c], gi);
+        gg = fmaf(P[sp.o_wgi + (HID + j) * sp.Ci + c], xi[c], gg);
+        go = fmaf(P[sp.o_wgi + (2 * HID + j) * sp.Ci + c], xi[c], go);
+      }
+    him[j] = sigmoidf_(go) * tanhf_(sigmoidf_(gi) * tanhf_(gg));
+  }
+  // ---- previous super state (fp16 channels-last)
+  if (ss_prev) {
+    const uint4* sp4 = reinterpret_cast<const uint4*>(ss_prev + (size_t)p * HID);
+#pragma unroll
+    for (int q = 0; q < HID / 8; q++) {
+      const uint4 u = sp4[q];
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const float2 f = __half22float2(h2[e]);
+        in[q * 8 + 2 * e] = f.x;
+        in[q * 8 + 2 * e + 1] = f.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < HID; c++) in[c] = 0.f;
+  }
+  // ---- ss <- W_ev [ss ; h_ev] + b ; ss <- W_im [ss ; h_im] + b (extractor.py:404-411,446-452)
+  float acc[HID];
+#pragma unroll
+  for (int stage = 0; stage < 2; stage++) {
+    if (stage == 1 && !use_image) break;
+    const float* Wt = P + (stage ? sp.o_wsi : sp.o_wse);            // [2h][h], output channel contiguous
+    const float* bs = P + (stage ? sp.o_bsi : sp.o_bse);
+#pragma unroll
+    for (int c = 0; c < HID; c++) acc[c] = bs[c];
+#pragma unroll
+    for (int k = 0; k < 2 * HID; k++) {
+      const float a = in[k];
+#pragma unroll
+      for (int q = 0; q < HID / 4; q++) {
+        const float4 w = *reinterpret_cast<const float4*>(Wt + k * HID + 4 * q);
+        acc[4 * q] = fmaf(a, w.x, acc[4 * q]);
+        acc[4 * q + 1] = fmaf(a, w.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(a, w.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(a, w.w, acc[4 * q + 3]);
+      }
+    }
+    if (stage == 0 && use_image) {
+#pragma unroll
+      for (int c = 0; c < HID; c++) {
+        in[c] = __half2float(__float2half_rn(acc[c]));               // fp16 intermediate state (autocast)
+        in[HID + c] = him[c];
+      }
+    }
+  }
+  uint4* o4 = reinterpret_cast<uint4*>(ss_out + (size_t)p * HID);
+#pragma unroll
+  for (int q = 0; q < HID / 8; q++) {
+    uint4 u;
+    __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; e++) h2[e] = __floats2half2_rn(acc[q * 8 + 2 * e], acc[q * 8 + 2 * e + 1]);
+    o4[q] = u;
+  }
+}
+
 template <int HID, int K>
 __global__ void stem_mma_kernel(StemParams sp, const float* __restrict__ params, const float* __restrict__ events,
                                 const float* __restrict__ image, const __half* __restrict__ ss_prev,
@@ -327,9 +467,31 @@ extern "C" int rvo_stem_forward(const float* params, int Ce, int Ci, int k, int 
   sp.n_params = (o + 3) & ~3;
   const int grid = (sp.Ho * sp.Wo + kStemPix - 1) / kStemPix;
   cudaStream_t st = (cudaStream_t)stream;
-  static const int variant = getenv("RVO_STEM_VARIANT") ? atoi(getenv("RVO_STEM_VARIANT")) : 1;
+#ifdef RVO_DEBUG
+  static const int variant = getenv("RVO_STEM_VARIANT") ? atoi(getenv("RVO_STEM_VARIANT")) : 2;
+#else
+  constexpr int variant = 2;                     // the release library never reads the environment
+#endif
   const bool std_geom = (k == 1 && stride == 1 && pad == 0) || ((k == 3 || k == 5) && stride == k - 1 && pad == 1);
-  if (variant == 1 && Ce <= 5 && Ci <= 3 && std_geom) {   // tensor-core variant
+  if (variant == 2 && std_geom && (h == 16 || h == 32) && (k == 1 || k == 3)) {   // thread-per-pixel variant
+    const size_t smp = (size_t)sp.n_params * sizeof(float);
+    const int gridp = (sp.Ho * sp.Wo + 127) / 128;
+#define RVO_STEMP(HID, KK)                                                                          \
+  do {                                                                                              \
+    RVO_CUDA(cudaFuncSetAttribute(stem_px_kernel<HID, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)smp));                                                       \
+    stem_px_kernel<HID, KK><<<gridp, 128, smp, st>>>(sp, params, events, image, (const __half*)ss_prev16, \
+                                                     use_image, (__half*)ss_out16);                 \
+  } while (0)
+    if (h == 16 && k == 1) RVO_STEMP(16, 1);
+    else if (h == 16) RVO_STEMP(16, 3);
+    else if (k == 1) RVO_STEMP(32, 1);
+    else RVO_STEMP(32, 3);
+#undef RVO_STEMP
+    RVO_LAUNCH_CHECK("stem_px_kernel");
+    return RVO_OK;
+  }
+  if (variant >= 1 && Ce <= 5 && Ci <= 3 && std_geom) {   // tensor-core variant
     const size_t sm2 = stem_mma_smem(sp, h);
     int per_sm = (int)((220 * 1024) / (sm2 + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
