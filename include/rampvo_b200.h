@@ -390,6 +390,73 @@ int rvo_up_gated_tail(const float* x32, const void* a16, const void* r16, int E,
                       const float* Wd, const float* bd, const float* Ww, const float* bw, float* delta,
                       float* weight, void* stream);
 
+/* ---- fused Linear chains of the update operator (csrc/up_chain.cu) ------------------------------- */
+
+/* Update.forward (ramp/net.py:69-90) is five row-local stretches separated by four cross-row exchanges (the two
+ * neighbour gathers of net.py:78-82 and the two SoftAgg reductions of net.py:84-85).  rvo_up_chain runs ONE such
+ * stretch — up to 6 nn.Linear layers with everything between them — as one persistent tcgen05 kernel: a tile of
+ * 128 edge rows stays in shared memory (fp16, the dtype Linear sees under autocast) from layer to layer, the
+ * weights stream through a TMA ring, accumulators live in TMEM, and the element-wise / LayerNorm / residual /
+ * gate / head arithmetic of the reference runs in the epilogues with its rounding points (fp16 Linear outputs,
+ * fp32 residual stream and LayerNorm, eps 1e-3).
+ *
+ * prologue (how the A tile of layer 0 is formed)
+ *   RVO_CHAIN_PRO_ROWS       rows of a16 [*, K0] fp16 (row pitch lda), row e or gather[e] (< 0: a zero row — the
+ *                            mask_ix * net[:, ix] of net.py:78-82); K0 = layer[0].K may exceed 384 (streamed)
+ *   RVO_CHAIN_PRO_EXPAND     half(x32[e] + hy_a[grp_a[e]])                      (blocks.py:47-48, net.py:84)
+ *   RVO_CHAIN_PRO_EXPAND_LN  n = LN((x32[e] + hy_a[grp_a[e]]) + hy_b[grp_b[e]]); A = half(n); n is the residual of
+ *                            the first GATED epilogue                           (net.py:84-85, gru[0] net.py:47)
+ * epilogue of a layer, t = half(acc + bias)
+ *   RVO_CHAIN_EPI_RELU        next A = relu(t)                                   (Linear + ReLU)
+ *   RVO_CHAIN_EPI_LN_RELU     next A = half(relu(LN(t)))                         (corr[2:5], net.py:54-56)
+ *   RVO_CHAIN_EPI_ADD3_LN     out32[e] = LN((net_in[e] + imap16[imap_idx[e] % imap_mod]) + t); out16 = half(out32)
+ *                                                                                (net.py:74-75, Ramp_vo.py:282)
+ *   RVO_CHAIN_EPI_RES         v = res32[e] + t; out32[e] = v; out16[e] = half(v) (if given); next A = half(v)
+ *                                                                                (net.py:81-82)
+ *   RVO_CHAIN_EPI_STORE16     layer.y16[e * ldy + c] = t; A unchanged            (SoftAgg f, g, h: blocks.py:36-38)
+ *   RVO_CHAIN_EPI_GATE        gate = half(sigmoid(t)) kept for the next GATED epilogue; A unchanged (blocks.py:23)
+ *   RVO_CHAIN_EPI_GATED_LN    y = residual + half(gate * t); m = LN(y); residual = m; next A = half(m)
+ *                                                                                (blocks.py:30-31, net.py:49)
+ *   RVO_CHAIN_EPI_GATED_HEADS y as above -> out32[e]; delta[e] = Wd relu(y) + bd; weight[e] = sigmoid(Ww relu(y) + bw)
+ *                                                                                (net.py:63-67,90)
+ * Every layer has N = 384 outputs; layers after the first have K = 384.  scratch32 / scratch16: per-CTA residual
+ * and gate rows, rvo_up_chain_scratch_rows() rows of 384 floats / halves each (only for the GATED epilogues and
+ * PRO_EXPAND_LN).  out32 may alias x32 / res32 only when no other row is read (i.e. not in a gathering stretch). */
+enum { RVO_CHAIN_PRO_ROWS = 0, RVO_CHAIN_PRO_EXPAND = 1, RVO_CHAIN_PRO_EXPAND_LN = 2 };
+enum {
+  RVO_CHAIN_EPI_RELU = 0, RVO_CHAIN_EPI_LN_RELU = 1, RVO_CHAIN_EPI_ADD3_LN = 2, RVO_CHAIN_EPI_RES = 3,
+  RVO_CHAIN_EPI_STORE16 = 4, RVO_CHAIN_EPI_GATE = 5, RVO_CHAIN_EPI_GATED_LN = 6, RVO_CHAIN_EPI_GATED_HEADS = 7
+};
+#define RVO_CHAIN_MAX_LAYERS 6
+typedef struct {
+  const void* w16;      /* [384, K] fp16, nn.Linear layout (row pitch K halves, K % 8 == 0) */
+  const void* bias16;   /* [384] fp16 */
+  const float* gamma;   /* LayerNorm weight / bias of the epilogue (LN_RELU, ADD3_LN, GATED_LN) */
+  const float* beta;
+  void* y16;            /* STORE16 destination, already offset to its first column */
+  int64_t ldy;          /* row pitch of y16 in halves (multiple of 8) */
+  int32_t K;
+  int32_t epilogue;
+} rvo_chain_layer_t;
+typedef struct {
+  int32_t M, n_layers, prologue, reserved;
+  const void* a16; int64_t lda; const int64_t* gather;                                   /* PRO_ROWS */
+  const float* x32; const void* hy_a; const int32_t* grp_a; const void* hy_b; const int32_t* grp_b;
+  const float* pro_gamma; const float* pro_beta;                                         /* PRO_EXPAND(_LN) */
+  const float* net_in; const void* imap16; const int64_t* imap_idx; int64_t imap_mod;    /* EPI_ADD3_LN */
+  const float* res32;                                                                    /* EPI_RES */
+  float* out32; void* out16;
+  const float* Wd; const float* bd; const float* Ww; const float* bw; float* delta; float* weight;  /* heads */
+  float* scratch32; void* scratch16;
+  rvo_chain_layer_t layer[RVO_CHAIN_MAX_LAYERS];
+} rvo_chain_t;
+int64_t rvo_up_chain_scratch_rows(void);
+int rvo_up_chain(const rvo_chain_t* chain, void* stream);
+
+/* group id of every EDGE (not sorted position) of a plan: grp[e] = seg_of[s] with perm[s] = e — the index the
+ * expand prologues of rvo_up_chain take. */
+int rvo_plan_edge_groups(const void* plan, int E, const int32_t** grp);
+
 /* ---- encoder convolutions on the tensor cores (csrc/conv_tc.cu) --------------------------------- */
 
 /* nn.Conv2d of the RAMP encoder CNNs (ramp/extractor.py:12-13,47,79,88,286: 7x7 s2, 3x3 s1/s2, 1x1 s1/s2) as a

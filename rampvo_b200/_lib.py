@@ -24,9 +24,35 @@ class FMap(Structure):
                 ("sH", c_int64), ("sW", c_int64)]
 
 
+class ChainLayer(Structure):
+    """rvo_chain_layer_t"""
+    _fields_ = [("w16", c_void_p), ("bias16", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
+                ("y16", c_void_p), ("ldy", c_int64), ("K", c_int32), ("epilogue", c_int32)]
+
+
+class Chain(Structure):
+    """rvo_chain_t (include/rampvo_b200.h): one row-local stretch of the update operator"""
+    _fields_ = [("M", c_int32), ("n_layers", c_int32), ("prologue", c_int32), ("reserved", c_int32),
+                ("a16", c_void_p), ("lda", c_int64), ("gather", c_void_p),
+                ("x32", c_void_p), ("hy_a", c_void_p), ("grp_a", c_void_p), ("hy_b", c_void_p), ("grp_b", c_void_p),
+                ("pro_gamma", c_void_p), ("pro_beta", c_void_p),
+                ("net_in", c_void_p), ("imap16", c_void_p), ("imap_idx", c_void_p), ("imap_mod", c_int64),
+                ("res32", c_void_p), ("out32", c_void_p), ("out16", c_void_p),
+                ("Wd", c_void_p), ("bd", c_void_p), ("Ww", c_void_p), ("bw", c_void_p),
+                ("delta", c_void_p), ("weight", c_void_p),
+                ("scratch32", c_void_p), ("scratch16", c_void_p),
+                ("layer", ChainLayer * 6)]
+
+
+PRO_ROWS, PRO_EXPAND, PRO_EXPAND_LN = 0, 1, 2
+(EPI_RELU, EPI_LN_RELU, EPI_ADD3_LN, EPI_RES, EPI_STORE16, EPI_GATE, EPI_GATED_LN, EPI_GATED_HEADS) = range(8)
+
 _P = c_void_p
 _I64 = c_int64
 _SIGNATURES = {
+    "rvo_up_chain_scratch_rows": (c_int64, []),
+    "rvo_up_chain": (c_int, [POINTER(Chain), c_void_p]),
+    "rvo_plan_edge_groups": (c_int, [c_void_p, c_int, POINTER(c_void_p)]),
     "rvo_abi_version": (c_int, []),
     "rvo_last_error": (c_char_p, []),
     "rvo_device_cc": (c_int, []),

@@ -473,7 +473,10 @@ extern "C" int rvo_stem_forward(const float* params, int Ce, int Ci, int k, int 
   constexpr int variant = 2;                     // the release library never reads the environment
 #endif
   const bool std_geom = (k == 1 && stride == 1 && pad == 0) || ((k == 3 || k == 5) && stride == k - 1 && pad == 1);
-  if (variant == 2 && std_geom && (h == 16 || h == 32) && (k == 1 || k == 3)) {   // thread-per-pixel variant
+  // thread-per-pixel variant: measured in the frame (profiles/r02_step_profile_torchprof_v9.txt) it wins only for the
+  // 16-channel scale (83 vs 89 us); at hidden 32 its 128 live accumulators spill (234 vs 57 us), so that scale and
+  // hidden 64 stay on the mma.sync kernel.  The env hook of debug builds can still force it (variant 3).
+  if (((variant == 2 && h == 16) || variant == 3) && std_geom && (h == 16 || h == 32) && (k == 1 || k == 3)) {
     const size_t smp = (size_t)sp.n_params * sizeof(float);
     const int gridp = (sp.Ho * sp.Wo + 127) / 128;
 #define RVO_STEMP(HID, KK)                                                                          \

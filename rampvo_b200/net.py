@@ -31,6 +31,29 @@ from .vo_utils import coords_from_topk_events, flatmeshgrid, get_channel_dim, pr
 DIM = 384
 
 
+def _addr(t, off=0):
+    """tensor (+ byte offset) -> ctypes pointer; None and ready-made pointers pass through"""
+    if t is None or isinstance(t, ctypes.c_void_p):
+        return t
+    return ctypes.c_void_p(t.data_ptr() + off)
+
+
+def run_chain(M, prologue, layers, stream, **kw):
+    """rvo_up_chain (include/rampvo_b200.h): `layers` = [(w16, bias16, epilogue, {K, gamma, beta, y16, ldy})],
+    keyword arguments = the other fields of rvo_chain_t (tensors, ctypes pointers or ints)."""
+    c = _lib.Chain()
+    c.M, c.n_layers, c.prologue = M, len(layers), prologue
+    for k, v in kw.items():
+        setattr(c, k, v if isinstance(v, int) else _addr(v))
+    for i, (w, b, epi, extra) in enumerate(layers):
+        ly = c.layer[i]
+        extra = dict(extra)
+        ly.w16, ly.bias16, ly.K, ly.epilogue = _addr(w), _addr(b), extra.pop("K", DIM), epi
+        for k, v in extra.items():
+            setattr(ly, k, v if isinstance(v, int) else _addr(v))
+    _lib.check(_lib.lib().rvo_up_chain(ctypes.byref(c), stream), "rvo_up_chain")
+
+
 class GatedResidual(nn.Module):
     """ramp/blocks.py:15-31: x + sigmoid(W_g x) * W_2 relu(W_1 x)"""
 
@@ -82,6 +105,16 @@ class GraphPlans:
                                             _lib.ptr(self.jx), st), "rvo_plan_neighbors")
             _lib.check(L.rvo_graph_plan(_lib.ptr(key_ij), _lib.ptr(jj), E, (jmax * 12345 + jmax) if jmax else 0,
                                         jmax, _lib.ptr(self.plan_ij), nb, st), "rvo_graph_plan")
+
+    def edge_groups(self):
+        """device pointers (ctypes) to the group id of every edge in the kk plan and in the (ii, jj) plan"""
+        L = _lib.lib()
+        out = []
+        for plan in (self.plan_k, self.plan_ij):
+            p = ctypes.c_void_p()
+            _lib.check(L.rvo_plan_edge_groups(_lib.ptr(plan), self.E, ctypes.byref(p)), "rvo_plan_edge_groups")
+            out.append(p)
+        return out
 
 
 class Update(nn.Module):
@@ -158,8 +191,96 @@ class Update(nn.Module):
         return self.norm.weight.is_cuda
 
     def _forward_fused(self, net, inp, corr, ii, jj, kk, plans, net_out=None):
-        """Same arithmetic and dtypes as the reference under autocast, 17 fp16 GEMMs + 13 fused
-        kernels instead of ~250 launches.  inp: [1,E,384] tensor or (imap_table [N,384] fp16, idx, mod)."""
+        """Same arithmetic and dtypes as the reference under autocast in 9 launches: the five row-local stretches of
+        net.py:69-90 are one rvo_up_chain each (csrc/up_chain.cu: the 128-row activation tile stays in shared memory
+        from Linear to Linear, LayerNorm / residual / gate / heads in the epilogues), separated by the two neighbour
+        gathers (folded into the next stretch's operand load) and the two SoftAgg reductions (rvo_up_softagg_fg +
+        the small per-group Linear h).  inp: [1,E,384] tensor or (imap_table [N,384] fp16, idx, mod)."""
+        L = _lib.lib()
+        W = self._fused_weights()
+        E = ii.numel()
+        dev = net.device
+        st = _lib.stream_ptr(dev)
+        P = _lib.ptr
+        f16 = lambda *shape: torch.empty(*(shape or (E, DIM)), dtype=torch.float16, device=dev)
+        f32 = lambda: torch.empty(E, DIM, dtype=torch.float32, device=dev)
+        addr = _addr
+        chain = lambda prologue, layers, **kw: run_chain(E, prologue, layers, st, **kw)
+
+        lay = lambda key, epi, **extra: (addr(W[key][0]), addr(W[key][1]), epi, extra)
+        def lay_half(key, half, epi, **extra):          # f (rows 0..383) or g (rows 384..767) of a fused [768, 384] weight
+            w, b = W[key]
+            return (addr(w, half * DIM * DIM * 2), addr(b, half * DIM * 2), epi, extra)
+        rows = int(L.rvo_up_chain_scratch_rows())
+        scr = _lib.Workspace.get(dev, rows * DIM * 6 + 512, "up_chain")
+        scr32 = ctypes.c_void_p(scr.data_ptr())
+        scr16 = ctypes.c_void_p(scr.data_ptr() + rows * DIM * 4)
+
+        # ---- stretch 1: net = norm(net + inp + corr-MLP(corr))                                 net.py:74-75
+        K0 = corr.shape[-1]
+        if K0 == 18 * altcorr.TILE_GROUP and corr.dtype == torch.float16:
+            c0, w0 = corr.reshape(E, K0), W["corr0t"]          # tile layout of altcorr.corr_tiles, permuted weight columns
+        elif corr.dtype == torch.float16 and corr.stride(-1) == 1 and corr.stride(-2) == 896 and K0 == 882:
+            c0, w0 = torch.as_strided(corr, (E, 896), (896, 1), corr.storage_offset()), W["corr0p"]   # zero-padded rows
+        else:
+            c0, w0 = F.pad(corr.reshape(E, -1).to(torch.float16), (0, 896 - K0)).contiguous(), W["corr0p"]
+        if isinstance(inp, tuple):
+            table, idx, mod = inp
+            table = table.reshape(-1, DIM)
+        else:
+            table, idx, mod = inp.reshape(E, DIM).to(torch.float16).contiguous(), torch.arange(E, device=dev), 0
+        net_in = net.reshape(E, DIM).float().contiguous()
+        xa32, xa16, xb32, xb16 = f32(), f16(), f32(), f16()
+        chain(_lib.PRO_ROWS,
+              [(addr(w0), addr(W["corr0"][1]), _lib.EPI_RELU, {"K": w0.shape[1]}),
+               lay("corr2", _lib.EPI_LN_RELU, gamma=W["ln_corr"][0], beta=W["ln_corr"][1]),
+               lay("corr5", _lib.EPI_ADD3_LN, gamma=W["ln_norm"][0], beta=W["ln_norm"][1])],
+              a16=c0, lda=c0.stride(0), net_in=net_in, imap16=table, imap_idx=idx, imap_mod=int(mod),
+              out32=xa32, out16=xa16)
+        # ---- stretch 2: net += c1(mask_ix * net[:, ix])                                        net.py:78-81
+        chain(_lib.PRO_ROWS, [lay("c1a", _lib.EPI_RELU), lay("c1b", _lib.EPI_RES)],
+              a16=xa16, lda=DIM, gather=plans.ix, res32=xa32, out32=xb32, out16=xb16)
+        # ---- stretch 3: net += c2(mask_jx * net[:, jx]); f(net), g(net) of agg_kk              net.py:82,84
+        fg = f16(E, 2 * DIM)
+        chain(_lib.PRO_ROWS,
+              [lay("c2a", _lib.EPI_RELU), lay("c2b", _lib.EPI_RES),
+               lay_half("kk_fg", 0, _lib.EPI_STORE16, y16=fg, ldy=2 * DIM),
+               lay_half("kk_fg", 1, _lib.EPI_STORE16, y16=addr(fg, DIM * 2), ldy=2 * DIM)],
+              a16=xb16, lda=DIM, gather=plans.jx, res32=xb32, out32=xa32)
+        x32 = xa32                                           # the hidden state after both neighbour MLPs
+        def soft_agg(plan, cap, kh):
+            y = f16(cap, DIM)
+            _lib.check(L.rvo_up_softagg_fg(P(fg), P(plan), E, DIM, cap, P(y), st), "rvo_up_softagg_fg")
+            w, b = W[kh]
+            hy = f16(cap, DIM)
+            _lib.check(L.rvo_up_linear(P(y), DIM, P(w), P(b), cap, DIM, DIM, 0, P(hy), DIM, st), "rvo_up_linear")
+            return hy
+        hy_k = soft_agg(plans.plan_k, plans.cap_k, "kk_h")
+        grp_k, grp_ij = plans.edge_groups()
+        # ---- stretch 4: f, g of agg_ij on net + agg_kk(net)                                    net.py:84-85
+        chain(_lib.PRO_EXPAND,
+              [lay_half("ij_fg", 0, _lib.EPI_STORE16, y16=fg, ldy=2 * DIM),
+               lay_half("ij_fg", 1, _lib.EPI_STORE16, y16=addr(fg, DIM * 2), ldy=2 * DIM)],
+              x32=x32, hy_a=hy_k, grp_a=grp_k)
+        hy_ij = soft_agg(plans.plan_ij, plans.cap_ij, "ij_h")
+        # ---- stretch 5: net = gru(net + agg_kk + agg_ij); heads                                net.py:86-90
+        out = net_out if net_out is not None else torch.empty(1, E, DIM, dtype=torch.float32, device=dev)
+        delta = torch.empty(1, E, 2, dtype=torch.float32, device=dev)
+        weight = torch.empty(1, E, 2, dtype=torch.float32, device=dev)
+        chain(_lib.PRO_EXPAND_LN,
+              [lay("g1_gate", _lib.EPI_GATE), lay("g1_a", _lib.EPI_RELU),
+               lay("g1_b", _lib.EPI_GATED_LN, gamma=W["ln_g2"][0], beta=W["ln_g2"][1]),
+               lay("g3_gate", _lib.EPI_GATE), lay("g3_a", _lib.EPI_RELU), lay("g3_b", _lib.EPI_GATED_HEADS)],
+              x32=x32, hy_a=hy_k, grp_a=grp_k, hy_b=hy_ij, grp_b=grp_ij,
+              pro_gamma=W["ln_g0"][0], pro_beta=W["ln_g0"][1], out32=out,
+              Wd=W["d"][0], bd=W["d"][1], Ww=W["w"][0], bw=W["w"][1], delta=delta, weight=weight,
+              scratch32=scr32, scratch16=scr16)
+        return out, (delta, weight, None)
+
+    def _forward_layers(self, net, inp, corr, ii, jj, kk, plans, net_out=None):
+        """The layer-by-layer form of _forward_fused (one rvo_up_linear per nn.Linear + the row kernels of
+        update_ops.cu): kept as the differential-test reference of the chain kernel (tests/test_gpu_up_chain.py);
+        Update.forward never calls it."""
         L = _lib.lib()
         W = self._fused_weights()
         E = ii.numel()
