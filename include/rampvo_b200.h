@@ -421,7 +421,11 @@ int rvo_up_gated_tail(const float* x32, const void* a16, const void* r16, int E,
  *                                                                                (net.py:63-67,90)
  * Every layer has N = 384 outputs; layers after the first have K = 384.  scratch32 / scratch16: per-CTA residual
  * and gate rows, rvo_up_chain_scratch_rows() rows of 384 floats / halves each (only for the GATED epilogues and
- * PRO_EXPAND_LN).  out32 may alias x32 / res32 only when no other row is read (i.e. not in a gathering stretch). */
+ * PRO_EXPAND_LN).
+ * Layouts.  Row-major [M, 384]: a16, net_in, imap16, hy_a / hy_b, out16, y16 and the out32 of GATED_HEADS (the
+ * arrays other code reads).  TILE-BLOCKED fp32, private to the chains: x32, res32 and the out32 of RES / ADD3_LN —
+ * ceil(M / 128) * 128 rows, element (e, c) at ((e / 128 * 96 + c / 4) * 128 + e % 128) * 4 + c % 4 floats, so that
+ * the 32 rows a warp owns in an epilogue are one contiguous 512-byte access.  out32 may alias res32. */
 enum { RVO_CHAIN_PRO_ROWS = 0, RVO_CHAIN_PRO_EXPAND = 1, RVO_CHAIN_PRO_EXPAND_LN = 2 };
 enum {
   RVO_CHAIN_EPI_RELU = 0, RVO_CHAIN_EPI_LN_RELU = 1, RVO_CHAIN_EPI_ADD3_LN = 2, RVO_CHAIN_EPI_RES = 3,
@@ -452,6 +456,12 @@ typedef struct {
 } rvo_chain_t;
 int64_t rvo_up_chain_scratch_rows(void);
 int rvo_up_chain(const rvo_chain_t* chain, void* stream);
+/* The chain kernel runs as thread-block clusters whose CTAs share every weight stage by TMA multicast (the L2 is read
+ * once per cluster).  rvo_up_chain_info reports the cluster size picked for this device (the largest of 4 / 2 / 1
+ * whose first wave covers the GPU) and the CTAs of one wave; rvo_up_chain_set_cluster forces 1, 2 or 4 (0 = automatic
+ * again) — a benchmarking knob, results do not depend on it. */
+int rvo_up_chain_info(int* cluster_size, int* ctas);
+int rvo_up_chain_set_cluster(int cluster_size);
 
 /* group id of every EDGE (not sorted position) of a plan: grp[e] = seg_of[s] with perm[s] = e — the index the
  * expand prologues of rvo_up_chain take. */

@@ -52,6 +52,8 @@ _I64 = c_int64
 _SIGNATURES = {
     "rvo_up_chain_scratch_rows": (c_int64, []),
     "rvo_up_chain": (c_int, [POINTER(Chain), c_void_p]),
+    "rvo_up_chain_info": (c_int, [POINTER(c_int), POINTER(c_int)]),
+    "rvo_up_chain_set_cluster": (c_int, [c_int]),
     "rvo_plan_edge_groups": (c_int, [c_void_p, c_int, POINTER(c_void_p)]),
     "rvo_abi_version": (c_int, []),
     "rvo_last_error": (c_char_p, []),

@@ -19,6 +19,8 @@
 // MMA and epilogue of one tile do not overlap (the accumulator fills 384 of the 512 TMEM columns and the A tile is
 // rewritten in place), but the weight ring keeps prefetching during the epilogue and the 148 CTAs are not in
 // lockstep; the win is the traffic: per stretch the hidden state is read once and written once.
+#include <type_traits>
+
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -31,58 +33,55 @@ constexpr int kCcSlots = 6;                        // A-tile K blocks resident i
 constexpr int kCcSlotBytes = kCcM * 128;           // 16 384
 constexpr int kCcWStage = kCcNH * 128;             // 24 576
 constexpr int kCcWStages = 5;
-constexpr int kCcWorkers = 512;                    // 16 warps
-constexpr int kCcThreads = 64 + kCcWorkers;        // warp 0: weight TMA, warp 1: MMA issuer
+constexpr int kCcWorkers = 384;                    // 12 warps (warps 4..15); 512 threads in all = 128 registers each
+constexpr int kCcThreads = 128 + kCcWorkers;       // warp 0: weight TMA, warp 1: MMA issuer, warps 2-3 idle
 constexpr int kCcSmemBytes = kCcSlots * kCcSlotBytes + kCcWStages * kCcWStage + 1024;
-constexpr int kCcParts = 4;                        // column parts per row (96 columns each)
-constexpr int kCcPartCols = kCcC / kCcParts;       // 96
+constexpr int kCcParts = 3;                        // column parts per row (128 columns each)
+constexpr int kCcPartCols = kCcC / kCcParts;       // 128
+constexpr int kCcChunks = kCcPartCols / 16;        // 16-column chunks per thread
 
 struct ChainMaps {
   TcTmap m[RVO_CHAIN_MAX_LAYERS];
+  TcTmap out16;                                    // row-major fp16 [M, 384] output that equals the activation tile
 };
 
 __device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
 
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
   asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
       "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
       "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
       "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
-      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
-      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
-      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
-      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
 }
 
-// 8 halves (one 16-byte chunk) -> 8 floats
-__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
-  const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const float2 t = __half22float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
+// 8 halves (one 16-byte chunk) <-> 8 floats, by value (no pointer punning: the chunks live in registers)
+__device__ __forceinline__ void unpack2(uint32_t u, float& lo, float& hi) {
+  lo = __half2float(__ushort_as_half((unsigned short)(u & 0xffffu)));
+  hi = __half2float(__ushort_as_half((unsigned short)(u >> 16)));
+}
+__device__ __forceinline__ void unpack8(uint4 u, float* f) {
+  unpack2(u.x, f[0], f[1]);
+  unpack2(u.y, f[2], f[3]);
+  unpack2(u.z, f[4], f[5]);
+  unpack2(u.w, f[6], f[7]);
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  return (uint32_t)__half_as_ushort(__float2half_rn(lo)) | ((uint32_t)__half_as_ushort(__float2half_rn(hi)) << 16);
 }
 __device__ __forceinline__ uint4 pack8(const float* f) {
-  uint4 u;
-  __half2* h = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-  return u;
+  return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
 }
 
-// v[0..32) += bias16[c0 .. c0+32)   (uniform address across the warp: one broadcast transaction per 16 bytes)
-__device__ __forceinline__ void add_bias32(const __half* __restrict__ bias, int c0, float* v) {
+// v[0..16) += bias16[c0 .. c0+16)   (uniform address across the warp: one broadcast transaction per 16 bytes)
+__device__ __forceinline__ void add_bias16(const __half* __restrict__ bias, int c0, float* v) {
   const uint4* p = reinterpret_cast<const uint4*>(bias + c0);
 #pragma unroll
-  for (int g = 0; g < 4; g++) {
+  for (int g = 0; g < 2; g++) {
     float b[8];
     unpack8(__ldg(p + g), b);
 #pragma unroll
@@ -90,30 +89,81 @@ __device__ __forceinline__ void add_bias32(const __half* __restrict__ bias, int 
   }
 }
 
-// 32 fp32 values of row `p` (already offset to the first column) — 128 contiguous bytes
-__device__ __forceinline__ void load32_f32(const float* __restrict__ p, float* v) {
-  const float4* q = reinterpret_cast<const float4*>(p);
+// v = (v - mean) * rstd * gamma + beta over 16 columns (gamma / beta already offset; uniform addresses)
+__device__ __forceinline__ void layer_norm16(float* v, float mean, float rstd, const float* __restrict__ gamma,
+                                             const float* __restrict__ beta) {
 #pragma unroll
-  for (int g = 0; g < 8; g++) {
-    const float4 t = q[g];
+  for (int g = 0; g < 4; g++) {
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + g);
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + g);
+    v[4 * g] = (v[4 * g] - mean) * rstd * ga.x + be.x;
+    v[4 * g + 1] = (v[4 * g + 1] - mean) * rstd * ga.y + be.y;
+    v[4 * g + 2] = (v[4 * g + 2] - mean) * rstd * ga.z + be.z;
+    v[4 * g + 3] = (v[4 * g + 3] - mean) * rstd * ga.w + be.w;
+  }
+}
+
+// ---- tile-blocked private layouts.  In the epilogues a thread owns a ROW, so a row-major [E, 384] array makes every
+// warp access touch 32 different lines.  Arrays that only the chains themselves read (the hidden state between
+// stretches, the per-CTA residual and gate scratch) are therefore stored as [block][16-byte chunk][row 0..127]:
+// the 32 rows of a warp are 32 consecutive 16-byte pieces — one fully coalesced 512-byte access.
+__device__ __forceinline__ size_t blk32_off(int blk, int row, int c) {   // fp32, c % 4 == 0, in floats
+  return (((size_t)blk * (kCcC / 4) + (size_t)(c >> 2)) * kCcM + (size_t)row) << 2;
+}
+__device__ __forceinline__ size_t blk16_off(int blk, int row, int c) {   // fp16, c % 8 == 0, in halves
+  return (((size_t)blk * (kCcC / 8) + (size_t)(c >> 3)) * kCcM + (size_t)row) << 3;
+}
+__device__ __forceinline__ void load16_blk32(const float* __restrict__ base, int blk, int row, int c0, float* v) {
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    const float4 t = *reinterpret_cast<const float4*>(base + blk32_off(blk, row, c0 + 4 * g));
     v[4 * g] = t.x; v[4 * g + 1] = t.y; v[4 * g + 2] = t.z; v[4 * g + 3] = t.w;
   }
 }
-__device__ __forceinline__ void store32_f32(float* __restrict__ p, const float* v) {
-  float4* q = reinterpret_cast<float4*>(p);
+__device__ __forceinline__ void store16_blk32(float* __restrict__ base, int blk, int row, int c0, const float* v) {
 #pragma unroll
-  for (int g = 0; g < 8; g++) q[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  for (int g = 0; g < 4; g++)
+    *reinterpret_cast<float4*>(base + blk32_off(blk, row, c0 + 4 * g)) =
+        make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
 }
-__device__ __forceinline__ void store32_f16(__half* __restrict__ p, const float* v) {
-  uint4* q = reinterpret_cast<uint4*>(p);
-#pragma unroll
-  for (int g = 0; g < 4; g++) q[g] = pack8(v + 8 * g);
+__device__ __forceinline__ void load16_blk16(const __half* __restrict__ base, int blk, int row, int c0, uint4* g) {
+  g[0] = *reinterpret_cast<const uint4*>(base + blk16_off(blk, row, c0));
+  g[1] = *reinterpret_cast<const uint4*>(base + blk16_off(blk, row, c0 + 8));
+}
+__device__ __forceinline__ void store16_blk16(__half* __restrict__ base, int blk, int row, int c0, const float* v) {
+  *reinterpret_cast<uint4*>(base + blk16_off(blk, row, c0)) = pack8(v);
+  *reinterpret_cast<uint4*>(base + blk16_off(blk, row, c0 + 8)) = pack8(v + 8);
 }
 
-// the 32 columns [c0, c0+32) of row r of the activation tile (fp16, K-major SWIZZLE_128B K blocks)
-__device__ __forceinline__ void store32_tile(uint32_t A_u, int r, int c0, const float* v) {
+// ---- row-major arrays of the interface (the incoming / outgoing hidden state, the SoftAgg f | g rows): 32-byte
+// (full sector) accesses per thread
+__device__ __forceinline__ void load16_row32(const float* __restrict__ p, float* v) {
 #pragma unroll
-  for (int g = 0; g < 4; g++) {
+  for (int g = 0; g < 2; g++)
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=f"(v[8 * g]), "=f"(v[8 * g + 1]), "=f"(v[8 * g + 2]), "=f"(v[8 * g + 3]), "=f"(v[8 * g + 4]),
+                   "=f"(v[8 * g + 5]), "=f"(v[8 * g + 6]), "=f"(v[8 * g + 7])
+                 : "l"(p + 8 * g));
+}
+__device__ __forceinline__ void store16_row32(float* __restrict__ p, const float* v) {
+#pragma unroll
+  for (int g = 0; g < 2; g++)
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(p + 8 * g), "f"(v[8 * g]),
+                 "f"(v[8 * g + 1]), "f"(v[8 * g + 2]), "f"(v[8 * g + 3]), "f"(v[8 * g + 4]), "f"(v[8 * g + 5]),
+                 "f"(v[8 * g + 6]), "f"(v[8 * g + 7])
+                 : "memory");
+}
+__device__ __forceinline__ void store16_row16(__half* __restrict__ p, const float* v) {
+  const uint4 lo = pack8(v), hi = pack8(v + 8);
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(p), "r"(lo.x), "r"(lo.y),
+               "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
+
+// the 16 columns [c0, c0+16) of row r of the activation tile (fp16, K-major SWIZZLE_128B K blocks)
+__device__ __forceinline__ void store16_tile(uint32_t A_u, int r, int c0, const float* v) {
+#pragma unroll
+  for (int g = 0; g < 2; g++) {
     const int col = c0 + 8 * g;
     const uint32_t addr = A_u + (uint32_t)(col >> 6) * kCcSlotBytes + (uint32_t)r * 128u +
                           (uint32_t)((((col & 63) >> 3) ^ (r & 7)) << 4);
@@ -123,32 +173,112 @@ __device__ __forceinline__ void store32_tile(uint32_t A_u, int r, int c0, const 
   }
 }
 
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// the CTAs of a cluster run the same tiles-per-CTA count and the same layer program, so every weight stage is needed
+// by all of them at (nearly) the same time: each CTA fetches 1/csize of the stage and multicasts it to every CTA of
+// the cluster — the L2 is read once per cluster instead of once per CTA (measured: a Linear layer's time follows the
+// number of CTAs that stream the same 288 KB from L2, 1.9 / 3.9 / 6.0 us per tile at 37 / 74 / 148 readers)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* tmap, int c0, int c1, uint64_t* bar,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4}], [%2], %5;\n" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* b, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+                   smem_u32(b)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
 __device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(kCcWorkers) : "memory"); }
 
-__device__ __forceinline__ float warp_sum(float v) {
+// one 16-column chunk of global operands, prefetched one chunk ahead of its use: x = 16 fp32, g / h = 16 fp16 each
+struct Pre {
+  float4 x[4];
+  uint4 g[2], h[2];
+};
+__device__ __forceinline__ void pre_x(const Pre& p, float* v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+  for (int i = 0; i < 4; i++) { v[4 * i] = p.x[i].x; v[4 * i + 1] = p.x[i].y; v[4 * i + 2] = p.x[i].z; v[4 * i + 3] = p.x[i].w; }
+}
+__device__ __forceinline__ void pre_blk32(Pre& p, const float* __restrict__ base, int blk, int row, int c0) {
+#pragma unroll
+  for (int g = 0; g < 4; g++) p.x[g] = *reinterpret_cast<const float4*>(base + blk32_off(blk, row, c0 + 4 * g));
+}
+__device__ __forceinline__ void pre_row32(Pre& p, const float* __restrict__ q) {   // row-major: two 32-byte loads
+#pragma unroll
+  for (int g = 0; g < 2; g++) {
+    float r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(r3), "=f"(r4), "=f"(r5), "=f"(r6), "=f"(r7)
+                 : "l"(q + 8 * g));
+    p.x[2 * g] = make_float4(r0, r1, r2, r3);
+    p.x[2 * g + 1] = make_float4(r4, r5, r6, r7);
+  }
+}
+
+// chunks 0..kCcChunks-1 of this thread's part, chunk i+1 fetched while chunk i is processed; `first` = chunk 0,
+// fetched by the caller before it waited for the accumulator
+template <class Fetch, class Chunk>
+__device__ __forceinline__ void pipelined_chunks(int cbase, Pre first, Fetch fetch, Chunk chunk) {
+  Pre p0 = first, p1;
+#pragma unroll 1
+  for (int ci = 0; ci < kCcChunks; ci += 2) {
+    const int c0 = cbase + 16 * ci;
+    p1 = fetch(c0 + 16);
+    chunk(c0, p0);
+    if (ci + 2 < kCcChunks) p0 = fetch(c0 + 32);
+    chunk(c0 + 16, p1);
+  }
 }
 
 // TMEM column of output column c: the two N = 192 halves sit at columns 0 and 256
 __device__ __forceinline__ uint32_t acc_col(int c) { return (uint32_t)(c + (c >= kCcNH ? 256 - kCcNH : 0)); }
+
+// -DRVO_DEBUG builds: clock64 stamps of CTA 0 (MMA issuer: operands ready / last MMA issued; worker warp 4: accumulator
+// ready / epilogue done), read back with rvo_up_chain_trace (tools/chain_bench.py --trace)
+#ifdef RVO_DEBUG
+__device__ long long g_cc_trace[4 * 64];
+#define CC_TRACE(slot, i) do { if (blockIdx.x == 0 && (i) < 64) g_cc_trace[(slot) * 64 + (i)] = clock64(); } while (0)
+#else
+#define CC_TRACE(slot, i) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(kCcThreads, 1)
 up_chain_kernel(const rvo_chain_t a, const __grid_constant__ ChainMaps maps) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t wfull[kCcWStages], wempty[kCcWStages], afull[kCcSlots], aempty[kCcSlots], hfull, tfull;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float4 xch[kCcM][kCcParts];             // row statistics / head partial sums of the four column parts
+  __shared__ float4 xch[kCcM][4];             // row statistics / head partial sums of the four column parts
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = a.M, n_layers = a.n_layers;
   const int n_tiles = (M + kCcM - 1) / kCcM;
+  // every CTA of a cluster must consume the same weight stages: the same number of tiles for all (a tile index past
+  // the last one is a phantom tile: zero rows in, nothing stored)
+  const int n_iter = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  uint32_t csize, crank;
+  asm volatile("mov.u32 %0, %%cluster_nctaid.x;\n" : "=r"(csize));
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(crank));
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
   if (tid == 0) {
     for (int s = 0; s < kCcWStages; s++) {
       mbar_init(&wfull[s], 1);
-      mbar_init(&wempty[s], 1);
+      mbar_init(&wempty[s], csize);                      // the MMA issuer of every CTA of the cluster releases a stage
     }
     for (int s = 0; s < kCcSlots; s++) {
       mbar_init(&afull[s], kCcWorkers);
@@ -165,6 +295,7 @@ up_chain_kernel(const rvo_chain_t a, const __grid_constant__ ChainMaps maps) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  cluster_sync_all();                                     // remote barriers are initialised before anyone signals them
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t A_u = smem_u32(smem), W_u = A_u + kCcSlots * kCcSlotBytes;
@@ -174,15 +305,21 @@ up_chain_kernel(const rvo_chain_t a, const __grid_constant__ ChainMaps maps) {
     // ===== weight producer: (tile, layer, K block, N half) in the order the MMA issuer consumes them =====
     if (lane == 0) {
       int s = 0, ph = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+      const int slice_rows = kCcNH / (int)csize;           // this CTA's share of a [192 x 64] stage
+      const uint32_t slice_off = crank * (uint32_t)(slice_rows * 128);
+      for (int it = 0; it < n_iter; it++)
         for (int l = 0; l < n_layers; l++) {
           const int nkb = (a.layer[l].K + 63) >> 6;
           for (int kb = 0; kb < nkb; kb++)
 #pragma unroll
             for (int nh = 0; nh < 2; nh++) {
-              mbar_wait(&wempty[s], ph ^ 1);
+              mbar_wait(&wempty[s], ph ^ 1);               // every CTA of the cluster has consumed this stage
               mbar_expect_tx(&wfull[s], (uint32_t)kCcWStage);
-              tma_load_2d(W_u + s * kCcWStage, &maps.m[l], kb * 64, nh * kCcNH, &wfull[s]);
+              if (csize == 1)
+                tma_load_2d(W_u + s * kCcWStage, &maps.m[l], kb * 64, nh * kCcNH, &wfull[s]);
+              else
+                tma_load_2d_mc(W_u + s * kCcWStage + slice_off, &maps.m[l], kb * 64,
+                               nh * kCcNH + (int)crank * slice_rows, &wfull[s], cmask);
               if (++s == kCcWStages) { s = 0; ph ^= 1; }
             }
         }
@@ -192,8 +329,9 @@ up_chain_kernel(const rvo_chain_t a, const __grid_constant__ ChainMaps maps) {
     int s = 0, ph = 0;
     uint32_t a_par = 0, h_ph = 0;
     constexpr uint32_t idesc = umma_idesc_f16(kCcM, kCcNH);
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
-      for (int l = 0; l < n_layers; l++) {
+    int tr = 0;
+    for (int it = 0; it < n_iter; it++)
+      for (int l = 0; l < n_layers; l++, tr++) {
         const int nkb = (a.layer[l].K + 63) >> 6;
         const bool stream = stream0 && l == 0;
         if (!stream) {                                   // whole A tile written by the workers (prologue / epilogue)
@@ -202,6 +340,7 @@ up_chain_kernel(const rvo_chain_t a, const __grid_constant__ ChainMaps maps) {
           asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         }
+        if (lane == 0) CC_TRACE(0, tr);
         for (int kb = 0; kb < nkb; kb++) {
           const int slot = stream ? kb % kCcSlots : kb;
           if (stream) {
@@ -220,7 +359,8 @@ up_chain_kernel(const rvo_chain_t a, const __grid_constant__ ChainMaps maps) {
               for (int k = 0; k < 4; k++)
                 umma_f16(tmem_base + nh * 256, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc,
                          (kb | k) ? 1u : 0u);
-              umma_commit(&wempty[s]);
+              if (csize == 1) umma_commit(&wempty[s]);
+              else umma_commit_mc(&wempty[s], cmask);
             }
             __syncwarp();
             if (++s == kCcWStages) { s = 0; ph ^= 1; }
@@ -228,36 +368,42 @@ up_chain_kernel(const rvo_chain_t a, const __grid_constant__ ChainMaps maps) {
           if (stream && lane == 0) umma_commit(&aempty[slot]);
           __syncwarp();
         }
-        if (lane == 0) umma_commit(&tfull);
+        if (lane == 0) {
+          umma_commit(&tfull);
+          CC_TRACE(1, tr);
+        }
         __syncwarp();
       }
-  } else {
-    // ===== workers: thread = (row, 96-column part) in the epilogues =====
-    const int wtid = tid - 64, wwarp = wtid >> 5;
-    const int q = warp & 3, part = wwarp >> 2;             // warps 2..17: every quadrant gets parts 0..3
+  } else if (warp >= 4) {
+    // ===== workers: thread = (row, 128-column part), eight chunks of 16 columns each =====
+    const int wtid = tid - 128, wwarp = wtid >> 5;
+    const int q = warp & 3, part = wwarp >> 2;             // warps 4..15: every quadrant gets parts 0..2
     const int row = q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const int cbase = part * kCcPartCols;
     uint32_t e_par = (1u << kCcSlots) - 1u, t_ph = 0;
     const __half* a16 = reinterpret_cast<const __half*>(a.a16);
-    float* scr32 = a.scratch32 ? a.scratch32 + ((size_t)blockIdx.x * kCcM + row) * kCcC : nullptr;
-    __half* scr16 = a.scratch16 ? reinterpret_cast<__half*>(a.scratch16) + ((size_t)blockIdx.x * kCcM + row) * kCcC
-                                : nullptr;
+    const __half* hya = reinterpret_cast<const __half*>(a.hy_a);
+    const __half* hyb = reinterpret_cast<const __half*>(a.hy_b);
+    __half* scr16 = reinterpret_cast<__half*>(a.scratch16);
+    const int cta = blockIdx.x;
+    bool tile_store_pending = false;                       // a TMA store still reads the activation tile
 
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    for (int it = 0; it < n_iter; it++) {
+      const int t = blockIdx.x + it * gridDim.x;           // >= n_tiles: phantom tile
       const int e = t * kCcM + row;
       const bool valid = e < M;
 
       // ---------------- prologue ----------------
       if (stream0) {
-        // thread owns 16-byte chunk `ch` of rows r0 and r0 + 64 of every K block
+        // thread owns 16-byte chunk `ch` of rows r0, r0 + 48 (and r0 + 96 when r0 < 32) of every K block
         const int ch = wtid & 7, r0 = wtid >> 3;
-        int64_t src[2];
+        const int nj = r0 < 32 ? 3 : 2;
+        int64_t src[3];
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-          const int ee = t * kCcM + r0 + 64 * j;
-          int64_t g = ee < M ? (a.gather ? a.gather[ee] : (int64_t)ee) : -1;
-          src[j] = g;
+        for (int j = 0; j < 3; j++) {
+          const int ee = t * kCcM + r0 + 48 * j;
+          src[j] = (j < nj && ee < M) ? (a.gather ? a.gather[ee] : (int64_t)ee) : -1;
         }
         const int K0 = a.layer[0].K, nkb = (K0 + 63) >> 6;
         for (int kb = 0; kb < nkb; kb++) {
@@ -267,244 +413,64 @@ up_chain_kernel(const rvo_chain_t a, const __grid_constant__ ChainMaps maps) {
           const int col = kb * 64 + ch * 8;
           const uint32_t dst0 = A_u + slot * kCcSlotBytes + r0 * 128 + (uint32_t)((ch ^ (r0 & 7)) << 4);
 #pragma unroll
-          for (int j = 0; j < 2; j++) {                     // (r0 + 64) & 7 == r0 & 7
-            const bool ok = src[j] >= 0 && col < K0;
-            cp_async16(dst0 + j * (64 * 128), a16 + (ok ? src[j] * a.lda + col : 0), ok ? 16u : 0u);
+          for (int j = 0; j < 3; j++) {                     // (r0 + 48 j) & 7 == r0 & 7
+            if (j < nj) {
+              const bool ok = src[j] >= 0 && col < K0;
+              cp_async16(dst0 + j * (48 * 128), a16 + (ok ? src[j] * a.lda + col : 0), ok ? 16u : 0u);
+            }
           }
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&afull[slot]))
                        : "memory");
         }
       } else {
-        // SoftAgg expand (+ the first LayerNorm of Update.gru): warp per row, lane owns 4 columns of each 128
-        const __half* hya = reinterpret_cast<const __half*>(a.hy_a);
-        const __half* hyb = reinterpret_cast<const __half*>(a.hy_b);
+        // SoftAgg expand (blocks.py:47-48, net.py:84-85) [+ the first LayerNorm of Update.gru, net.py:47]
         const bool with_ln = a.prologue == RVO_CHAIN_PRO_EXPAND_LN;
-        for (int r = wwarp; r < kCcM; r += kCcWorkers / 32) {
-          const int ee = t * kCcM + r;
-          float v[3][4];
-          if (ee < M) {
-            const int ga = a.grp_a[ee];
-            const int gb = hyb ? a.grp_b[ee] : 0;
+        const __half* ra = valid ? hya + (size_t)a.grp_a[e] * kCcC : nullptr;
+        const __half* rb = (valid && hyb) ? hyb + (size_t)a.grp_b[e] * kCcC : nullptr;
+        float s1 = 0.f, s2 = 0.f;
+        auto fetch = [&](int c0) {
+          Pre p;
+          if (valid) {
+            pre_blk32(p, a.x32, t, row, c0);
+            p.g[0] = __ldg(reinterpret_cast<const uint4*>(ra + c0));
+            p.g[1] = __ldg(reinterpret_cast<const uint4*>(ra + c0) + 1);
+            if (rb) {
+              p.h[0] = __ldg(reinterpret_cast<const uint4*>(rb + c0));
+              p.h[1] = __ldg(reinterpret_cast<const uint4*>(rb + c0) + 1);
+            }
+          }
+          return p;
+        };
+        auto chunk = [&](int c0, const Pre& p) {
+          float v[16];
+          if (valid) {
+            pre_x(p, v);
 #pragma unroll
-            for (int j = 0; j < 3; j++) {
-              const float4 x = reinterpret_cast<const float4*>(a.x32 + (size_t)ee * kCcC + 128 * j)[lane];
-              const uint2 ha = reinterpret_cast<const uint2*>(hya + (size_t)ga * kCcC + 128 * j)[lane];
-              const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&ha.x));
-              const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&ha.y));
-              v[j][0] = x.x + a0.x; v[j][1] = x.y + a0.y; v[j][2] = x.z + a1.x; v[j][3] = x.w + a1.y;
-              if (hyb) {
-                const uint2 hb = reinterpret_cast<const uint2*>(hyb + (size_t)gb * kCcC + 128 * j)[lane];
-                const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&hb.x));
-                const float2 b1 = __half22float2(*reinterpret_cast<const __half2*>(&hb.y));
-                v[j][0] += b0.x; v[j][1] += b0.y; v[j][2] += b1.x; v[j][3] += b1.y;
+            for (int hf = 0; hf < 2; hf++) {
+              float h8[8];
+              unpack8(p.g[hf], h8);
+#pragma unroll
+              for (int i = 0; i < 8; i++) v[8 * hf + i] += h8[i];
+              if (rb) {
+                unpack8(p.h[hf], h8);
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[8 * hf + i] += h8[i];
               }
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 3; j++)
-#pragma unroll
-              for (int i = 0; i < 4; i++) v[j][i] = 0.f;
+            for (int i = 0; i < 16; i++) v[i] = 0.f;
           }
-          if (with_ln) {                                   // two-pass LayerNorm in registers, eps 1e-3
-            float s = 0.f;
+          if (with_ln) {
 #pragma unroll
-            for (int j = 0; j < 3; j++)
-#pragma unroll
-              for (int i = 0; i < 4; i++) s += v[j][i];
-            const float mean = warp_sum(s) * (1.0f / kCcC);
-            float ss = 0.f;
-#pragma unroll
-            for (int j = 0; j < 3; j++)
-#pragma unroll
-              for (int i = 0; i < 4; i++) { const float d = v[j][i] - mean; ss += d * d; }
-            const float rstd = rsqrtf(warp_sum(ss) * (1.0f / kCcC) + 1e-3f);
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-              const float4 g = reinterpret_cast<const float4*>(a.pro_gamma + 128 * j)[lane];
-              const float4 b = reinterpret_cast<const float4*>(a.pro_beta + 128 * j)[lane];
-              v[j][0] = (v[j][0] - mean) * rstd * g.x + b.x;
-              v[j][1] = (v[j][1] - mean) * rstd * g.y + b.y;
-              v[j][2] = (v[j][2] - mean) * rstd * g.z + b.z;
-              v[j][3] = (v[j][3] - mean) * rstd * g.w + b.w;
-            }
-            float* sr = a.scratch32 + ((size_t)blockIdx.x * kCcM + r) * kCcC;
-#pragma unroll
-            for (int j = 0; j < 3; j++)
-              reinterpret_cast<float4*>(sr + 128 * j)[lane] = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+            for (int i = 0; i < 16; i++) { s1 += v[i]; s2 += v[i] * v[i]; }
+            tmem_st16(trow + acc_col(c0), v);
+          } else {
+            store16_tile(A_u, row, c0, v);
           }
-#pragma unroll
-          for (int j = 0; j < 3; j++) {
-            const int col = 128 * j + 4 * lane;
-            const uint32_t addr = A_u + (uint32_t)(col >> 6) * kCcSlotBytes + (uint32_t)r * 128u +
-                                  (uint32_t)((((col & 63) >> 3) ^ (r & 7)) << 4) + (uint32_t)((col & 7) * 2);
-            const __half2 p0 = __floats2half2_rn(v[j][0], v[j][1]), p1 = __floats2half2_rn(v[j][2], v[j][3]);
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};\n" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&p0)),
-                         "r"(*reinterpret_cast<const uint32_t*>(&p1))
-                         : "memory");
-          }
-        }
-        // the scratch rows written above are read back by OTHER threads in the GATED epilogues
-        if (with_ln) __threadfence_block();
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        mbar_arrive(&hfull);
-      }
-
-      // ---------------- layers ----------------
-      for (int l = 0; l < n_layers; l++) {
-        const rvo_chain_layer_t& L = a.layer[l];
-        const __half* bias = reinterpret_cast<const __half*>(L.bias16);
-        const bool has_next = l + 1 < n_layers;
-        mbar_wait(&tfull, t_ph);
-        t_ph ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const int epi = L.epilogue;
-
-        if (epi == RVO_CHAIN_EPI_RELU) {
-#pragma unroll 1
-          for (int ci = 0; ci < 3; ci++) {
-            const int c0 = cbase + 32 * ci;
-            float v[32];
-            tmem_ld32(trow + acc_col(c0), v);
-            add_bias32(bias, c0, v);
-#pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.f);
-            store32_tile(A_u, row, c0, v);
-          }
-        } else if (epi == RVO_CHAIN_EPI_STORE16) {
-          __half* y = reinterpret_cast<__half*>(L.y16) + (size_t)e * L.ldy;
-#pragma unroll 1
-          for (int ci = 0; ci < 3; ci++) {
-            const int c0 = cbase + 32 * ci;
-            float v[32];
-            tmem_ld32(trow + acc_col(c0), v);
-            add_bias32(bias, c0, v);
-            if (valid) store32_f16(y + c0, v);
-          }
-        } else if (epi == RVO_CHAIN_EPI_GATE) {
-#pragma unroll 1
-          for (int ci = 0; ci < 3; ci++) {
-            const int c0 = cbase + 32 * ci;
-            float v[32];
-            tmem_ld32(trow + acc_col(c0), v);
-            add_bias32(bias, c0, v);
-#pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = 1.0f / (1.0f + __expf(-round_h(v[i])));
-            store32_f16(scr16 + c0, v);
-          }
-        } else if (epi == RVO_CHAIN_EPI_RES) {
-          const float* res = a.res32 + (size_t)e * kCcC;
-          float* o32 = a.out32 + (size_t)e * kCcC;
-          __half* o16 = a.out16 ? reinterpret_cast<__half*>(a.out16) + (size_t)e * kCcC : nullptr;
-#pragma unroll 1
-          for (int ci = 0; ci < 3; ci++) {
-            const int c0 = cbase + 32 * ci;
-            float v[32], x[32];
-            tmem_ld32(trow + acc_col(c0), v);
-            add_bias32(bias, c0, v);
-            if (valid) {
-              load32_f32(res + c0, x);
-#pragma unroll
-              for (int i = 0; i < 32; i++) v[i] = x[i] + round_h(v[i]);
-              store32_f32(o32 + c0, v);
-              if (o16) store32_f16(o16 + c0, v);
-            }
-            if (has_next) store32_tile(A_u, row, c0, v);
-          }
-        } else if (epi == RVO_CHAIN_EPI_GATED_HEADS) {
-          float* o32 = a.out32 + (size_t)e * kCcC;
-          float acc4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-          for (int ci = 0; ci < 3; ci++) {
-            const int c0 = cbase + 32 * ci;
-            float v[32], x[32];
-            tmem_ld32(trow + acc_col(c0), v);
-            add_bias32(bias, c0, v);
-            load32_f32(scr32 + c0, x);
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-              float gt[8];
-              unpack8(reinterpret_cast<const uint4*>(scr16 + c0)[g], gt);
-#pragma unroll
-              for (int i = 0; i < 8; i++) v[8 * g + i] = x[8 * g + i] + round_h(gt[i] * round_h(v[8 * g + i]));
-            }
-            if (valid) store32_f32(o32 + c0, v);
-            // heads run in fp16 under autocast: relu(net) is rounded to fp16 before the Linear
-#pragma unroll
-            for (int g = 0; g < 8; g++) {
-              const float4 wd0 = __ldg(reinterpret_cast<const float4*>(a.Wd + c0) + g);
-              const float4 wd1 = __ldg(reinterpret_cast<const float4*>(a.Wd + kCcC + c0) + g);
-              const float4 ww0 = __ldg(reinterpret_cast<const float4*>(a.Ww + c0) + g);
-              const float4 ww1 = __ldg(reinterpret_cast<const float4*>(a.Ww + kCcC + c0) + g);
-              const float h0 = round_h(fmaxf(v[4 * g], 0.f)), h1 = round_h(fmaxf(v[4 * g + 1], 0.f));
-              const float h2 = round_h(fmaxf(v[4 * g + 2], 0.f)), h3 = round_h(fmaxf(v[4 * g + 3], 0.f));
-              acc4[0] += h0 * wd0.x + h1 * wd0.y + h2 * wd0.z + h3 * wd0.w;
-              acc4[1] += h0 * wd1.x + h1 * wd1.y + h2 * wd1.z + h3 * wd1.w;
-              acc4[2] += h0 * ww0.x + h1 * ww0.y + h2 * ww0.z + h3 * ww0.w;
-              acc4[3] += h0 * ww1.x + h1 * ww1.y + h2 * ww1.z + h3 * ww1.w;
-            }
-          }
-          xch[row][part] = make_float4(acc4[0], acc4[1], acc4[2], acc4[3]);
-          workers_sync();
-          if (part == 0 && valid) {
-            float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int p = 0; p < kCcParts; p++) {
-              const float4 u = xch[row][p];
-              s4[0] += u.x; s4[1] += u.y; s4[2] += u.z; s4[3] += u.w;
-            }
-            const float d0 = round_h(s4[0] + a.bd[0]), d1 = round_h(s4[1] + a.bd[1]);
-            const float w0 = round_h(s4[2] + a.bw[0]), w1 = round_h(s4[3] + a.bw[1]);
-            reinterpret_cast<float2*>(a.delta)[e] = make_float2(d0, d1);
-            reinterpret_cast<float2*>(a.weight)[e] =
-                make_float2(round_h(1.0f / (1.0f + __expf(-w0))), round_h(1.0f / (1.0f + __expf(-w1))));
-          }
-        } else {
-          // ---- LayerNorm epilogues: pass 1 forms the pre-norm value and its row statistics, pass 2 normalises ----
-          const float* nin = a.net_in ? a.net_in + (size_t)e * kCcC : nullptr;
-          const __half* im = nullptr;
-          if (epi == RVO_CHAIN_EPI_ADD3_LN && valid) {
-            int64_t k = a.imap_idx[e];
-            if (a.imap_mod > 0) k %= a.imap_mod;
-            im = reinterpret_cast<const __half*>(a.imap16) + (size_t)k * kCcC;
-          }
-          float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-          for (int ci = 0; ci < 3; ci++) {
-            const int c0 = cbase + 32 * ci;
-            float v[32];
-            tmem_ld32(trow + acc_col(c0), v);
-            add_bias32(bias, c0, v);
-            if (epi == RVO_CHAIN_EPI_LN_RELU) {
-#pragma unroll
-              for (int i = 0; i < 32; i++) v[i] = round_h(v[i]);
-            } else if (epi == RVO_CHAIN_EPI_ADD3_LN) {
-              if (valid) {
-                float x[32];
-                load32_f32(nin + c0, x);
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                  float m8[8];
-                  unpack8(__ldg(reinterpret_cast<const uint4*>(im + c0) + g), m8);
-#pragma unroll
-                  for (int i = 0; i < 8; i++) v[8 * g + i] = (x[8 * g + i] + m8[i]) + round_h(v[8 * g + i]);
-                }
-              }
-              tmem_st32(trow + acc_col(c0), v);
-            } else {                                          // GATED_LN
-              float x[32];
-              load32_f32(scr32 + c0, x);
-#pragma unroll
-              for (int g = 0; g < 4; g++) {
-                float gt[8];
-                unpack8(reinterpret_cast<const uint4*>(scr16 + c0)[g], gt);
-#pragma unroll
-                for (int i = 0; i < 8; i++) v[8 * g + i] = x[8 * g + i] + round_h(gt[i] * round_h(v[8 * g + i]));
-              }
-              tmem_st32(trow + acc_col(c0), v);
-            }
-#pragma unroll
-            for (int i = 0; i < 32; i++) { s1 += v[i]; s2 += v[i] * v[i]; }
-          }
+        };
+        pipelined_chunks(cbase, fetch(cbase), fetch, chunk);
+        if (with_ln) {
           xch[row][part] = make_float4(s1, s2, 0.f, 0.f);
           workers_sync();
           float t1 = 0.f, t2 = 0.f;
@@ -515,54 +481,335 @@ up_chain_kernel(const rvo_chain_t a, const __grid_constant__ ChainMaps maps) {
           }
           const float mean = t1 * (1.0f / kCcC);
           const float rstd = rsqrtf(fmaxf(t2 * (1.0f / kCcC) - mean * mean, 0.f) + 1e-3f);
-          float* o32 = a.out32 ? a.out32 + (size_t)e * kCcC : nullptr;
-          __half* o16 = a.out16 ? reinterpret_cast<__half*>(a.out16) + (size_t)e * kCcC : nullptr;
-#pragma unroll 1
-          for (int ci = 0; ci < 3; ci++) {
-            const int c0 = cbase + 32 * ci;
-            float v[32];
-            tmem_ld32(trow + acc_col(c0), v);
-            if (epi == RVO_CHAIN_EPI_LN_RELU) {
-              add_bias32(bias, c0, v);
+#pragma unroll 2
+          for (int ci = 0; ci < kCcChunks; ci++) {
+            const int c0 = cbase + 16 * ci;
+            float v[16];
+            tmem_ld16(trow + acc_col(c0), v);
+            layer_norm16(v, mean, rstd, a.pro_gamma + c0, a.pro_beta + c0);
+            store16_blk32(a.scratch32, cta, row, c0, v);
+            store16_tile(A_u, row, c0, v);
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        mbar_arrive(&hfull);
+      }
+
+      // ---------------- layers ----------------
+      for (int l = 0; l < n_layers; l++) {
+        const rvo_chain_layer_t& L = a.layer[l];
+        const __half* bias = reinterpret_cast<const __half*>(L.bias16);
+        const bool has_next = l + 1 < n_layers;
+        const int epi = L.epilogue;
+        const bool writes_tile = epi == RVO_CHAIN_EPI_RELU || epi == RVO_CHAIN_EPI_LN_RELU ||
+                                 epi == RVO_CHAIN_EPI_GATED_LN ||
+                                 ((epi == RVO_CHAIN_EPI_RES || epi == RVO_CHAIN_EPI_ADD3_LN) && (has_next || a.out16));
+        const bool tile_out16 = (epi == RVO_CHAIN_EPI_RES || epi == RVO_CHAIN_EPI_ADD3_LN) && a.out16;
+
+        if (epi == RVO_CHAIN_EPI_RES) {
+          // v = res32[e] + t ; out32[e] = v ; tile = half(v)  — the residual chunk is fetched one chunk ahead
+          auto fetch = [&](int c0) {
+            Pre p;
+            if (valid) pre_blk32(p, a.res32, t, row, c0);
+            return p;
+          };
+          const Pre first = fetch(cbase);
+          mbar_wait(&tfull, t_ph);
+          if (wtid == 0) CC_TRACE(2, it * n_layers + l);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          if (tile_store_pending && writes_tile) {
+            if (wtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+            workers_sync();
+            tile_store_pending = false;
+          }
+          auto chunk = [&](int c0, const Pre& p) {
+            float v[16], x[16];
+            tmem_ld16(trow + acc_col(c0), v);
+            add_bias16(bias, c0, v);
+            pre_x(p, x);
 #pragma unroll
-              for (int i = 0; i < 32; i++) v[i] = round_h(v[i]);
+            for (int i = 0; i < 16; i++) v[i] = (valid ? x[i] : 0.f) + round_h(v[i]);
+            if (valid) store16_blk32(a.out32, t, row, c0, v);
+            if (writes_tile) store16_tile(A_u, row, c0, v);
+          };
+          pipelined_chunks(cbase, first, fetch, chunk);
+        } else if (epi == RVO_CHAIN_EPI_GATED_LN || epi == RVO_CHAIN_EPI_GATED_HEADS) {
+          // y = residual + half(gate * t); then LayerNorm (GATED_LN) or the heads (GATED_HEADS)
+          const bool heads = epi == RVO_CHAIN_EPI_GATED_HEADS;
+          auto fetch = [&](int c0) {
+            Pre p;
+            pre_blk32(p, a.scratch32, cta, row, c0);
+            p.g[0] = *reinterpret_cast<const uint4*>(scr16 + blk16_off(cta, row, c0));
+            p.g[1] = *reinterpret_cast<const uint4*>(scr16 + blk16_off(cta, row, c0 + 8));
+            return p;
+          };
+          const Pre first = fetch(cbase);
+          mbar_wait(&tfull, t_ph);
+          if (wtid == 0) CC_TRACE(2, it * n_layers + l);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          if (tile_store_pending && writes_tile) {
+            if (wtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+            workers_sync();
+            tile_store_pending = false;
+          }
+          float s1 = 0.f, s2 = 0.f;
+          float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+          float* o32 = heads ? a.out32 + (size_t)e * kCcC : nullptr;
+          // one chunk: y = residual + half(gate * t), then the head partial sums (kHeads) or the row statistics
+          auto chunk_t = [&](auto heads_c, int c0, const Pre& p) {
+            constexpr bool kHeads = decltype(heads_c)::value;
+            float v[16], x[16];
+            tmem_ld16(trow + acc_col(c0), v);
+            add_bias16(bias, c0, v);
+            pre_x(p, x);
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) {
+              float gt[8];
+              unpack8(p.g[hf], gt);
+#pragma unroll
+              for (int i = 0; i < 8; i++) v[8 * hf + i] = x[8 * hf + i] + round_h(gt[i] * round_h(v[8 * hf + i]));
             }
+            if constexpr (kHeads) {
+              if (valid) store16_row32(o32 + c0, v);
+              // heads run in fp16 under autocast: relu(net) is rounded to fp16 before the Linear
 #pragma unroll
-            for (int g = 0; g < 8; g++) {
-              const float4 ga = __ldg(reinterpret_cast<const float4*>(L.gamma + c0) + g);
-              const float4 be = __ldg(reinterpret_cast<const float4*>(L.beta + c0) + g);
-              v[4 * g] = (v[4 * g] - mean) * rstd * ga.x + be.x;
-              v[4 * g + 1] = (v[4 * g + 1] - mean) * rstd * ga.y + be.y;
-              v[4 * g + 2] = (v[4 * g + 2] - mean) * rstd * ga.z + be.z;
-              v[4 * g + 3] = (v[4 * g + 3] - mean) * rstd * ga.w + be.w;
-            }
-            if (epi == RVO_CHAIN_EPI_LN_RELU) {
-#pragma unroll
-              for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.f);
-            } else if (epi == RVO_CHAIN_EPI_ADD3_LN) {
-              if (valid) {
-                store32_f32(o32 + c0, v);
-                if (o16) store32_f16(o16 + c0, v);
+              for (int gq = 0; gq < 4; gq++) {
+                const float4 wd0 = __ldg(reinterpret_cast<const float4*>(a.Wd + c0) + gq);
+                const float4 wd1 = __ldg(reinterpret_cast<const float4*>(a.Wd + kCcC + c0) + gq);
+                const float h0 = round_h(fmaxf(v[4 * gq], 0.f)), h1 = round_h(fmaxf(v[4 * gq + 1], 0.f));
+                const float h2 = round_h(fmaxf(v[4 * gq + 2], 0.f)), h3 = round_h(fmaxf(v[4 * gq + 3], 0.f));
+                acc4[0] += h0 * wd0.x + h1 * wd0.y + h2 * wd0.z + h3 * wd0.w;
+                acc4[1] += h0 * wd1.x + h1 * wd1.y + h2 * wd1.z + h3 * wd1.w;
+                const float4 ww0 = __ldg(reinterpret_cast<const float4*>(a.Ww + c0) + gq);
+                const float4 ww1 = __ldg(reinterpret_cast<const float4*>(a.Ww + kCcC + c0) + gq);
+                acc4[2] += h0 * ww0.x + h1 * ww0.y + h2 * ww0.z + h3 * ww0.w;
+                acc4[3] += h0 * ww1.x + h1 * ww1.y + h2 * ww1.z + h3 * ww1.w;
               }
             } else {
-              store32_f32(scr32 + c0, v);
+#pragma unroll
+              for (int i = 0; i < 16; i++) { s1 += v[i]; s2 += v[i] * v[i]; }
+              tmem_st16(trow + acc_col(c0), v);
             }
-            if (has_next) store32_tile(A_u, row, c0, v);
+          };
+          if (heads) pipelined_chunks(cbase, first, fetch, [&](int c0, const Pre& p) { chunk_t(std::true_type{}, c0, p); });
+          else pipelined_chunks(cbase, first, fetch, [&](int c0, const Pre& p) { chunk_t(std::false_type{}, c0, p); });
+          if (heads) {
+            xch[row][part] = make_float4(acc4[0], acc4[1], acc4[2], acc4[3]);
+            workers_sync();
+            if (part == 0 && valid) {
+              float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int p = 0; p < kCcParts; p++) {
+                const float4 u = xch[row][p];
+                s4[0] += u.x; s4[1] += u.y; s4[2] += u.z; s4[3] += u.w;
+              }
+              const float d0 = round_h(s4[0] + a.bd[0]), d1 = round_h(s4[1] + a.bd[1]);
+              const float w0 = round_h(s4[2] + a.bw[0]), w1 = round_h(s4[3] + a.bw[1]);
+              reinterpret_cast<float2*>(a.delta)[e] = make_float2(d0, d1);
+              reinterpret_cast<float2*>(a.weight)[e] =
+                  make_float2(round_h(1.0f / (1.0f + __expf(-w0))), round_h(1.0f / (1.0f + __expf(-w1))));
+            }
+          } else {
+            xch[row][part] = make_float4(s1, s2, 0.f, 0.f);
+            workers_sync();
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int p = 0; p < kCcParts; p++) {
+              const float4 u = xch[row][p];
+              t1 += u.x; t2 += u.y;
+            }
+            const float mean = t1 * (1.0f / kCcC);
+            const float rstd = rsqrtf(fmaxf(t2 * (1.0f / kCcC) - mean * mean, 0.f) + 1e-3f);
+#pragma unroll 2
+            for (int ci = 0; ci < kCcChunks; ci++) {
+              const int c0 = cbase + 16 * ci;
+              float v[16];
+              tmem_ld16(trow + acc_col(c0), v);
+              layer_norm16(v, mean, rstd, L.gamma + c0, L.beta + c0);
+              store16_blk32(a.scratch32, cta, row, c0, v);
+              store16_tile(A_u, row, c0, v);
+            }
+          }
+        } else if (epi == RVO_CHAIN_EPI_ADD3_LN) {
+          // out32[e] = LN((net_in[e] + imap[idx % mod]) + t)
+          const float* nin = a.net_in + (size_t)e * kCcC;
+          const __half* im = nullptr;
+          if (valid) {
+            int64_t k = a.imap_idx[e];
+            if (a.imap_mod > 0) k %= a.imap_mod;
+            im = reinterpret_cast<const __half*>(a.imap16) + (size_t)k * kCcC;
+          }
+          auto fetch = [&](int c0) {
+            Pre p;
+            if (valid) {
+              pre_row32(p, nin + c0);
+              p.g[0] = __ldg(reinterpret_cast<const uint4*>(im + c0));
+              p.g[1] = __ldg(reinterpret_cast<const uint4*>(im + c0) + 1);
+            }
+            return p;
+          };
+          const Pre first = fetch(cbase);
+          mbar_wait(&tfull, t_ph);
+          if (wtid == 0) CC_TRACE(2, it * n_layers + l);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          if (tile_store_pending && writes_tile) {
+            if (wtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+            workers_sync();
+            tile_store_pending = false;
+          }
+          float s1 = 0.f, s2 = 0.f;
+          auto chunk = [&](int c0, const Pre& p) {
+            float v[16];
+            tmem_ld16(trow + acc_col(c0), v);
+            add_bias16(bias, c0, v);
+            if (valid) {
+              float x[16];
+              pre_x(p, x);
+#pragma unroll
+              for (int hf = 0; hf < 2; hf++) {
+                float m8[8];
+                unpack8(p.g[hf], m8);
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[8 * hf + i] = (x[8 * hf + i] + m8[i]) + round_h(v[8 * hf + i]);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) { s1 += v[i]; s2 += v[i] * v[i]; }
+            tmem_st16(trow + acc_col(c0), v);
+          };
+          pipelined_chunks(cbase, first, fetch, chunk);
+          xch[row][part] = make_float4(s1, s2, 0.f, 0.f);
+          workers_sync();
+          float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+          for (int p = 0; p < kCcParts; p++) {
+            const float4 u = xch[row][p];
+            t1 += u.x; t2 += u.y;
+          }
+          const float mean = t1 * (1.0f / kCcC);
+          const float rstd = rsqrtf(fmaxf(t2 * (1.0f / kCcC) - mean * mean, 0.f) + 1e-3f);
+#pragma unroll 2
+          for (int ci = 0; ci < kCcChunks; ci++) {
+            const int c0 = cbase + 16 * ci;
+            float v[16];
+            tmem_ld16(trow + acc_col(c0), v);
+            layer_norm16(v, mean, rstd, L.gamma + c0, L.beta + c0);
+            if (valid) store16_blk32(a.out32, t, row, c0, v);
+            if (writes_tile) store16_tile(A_u, row, c0, v);
+          }
+        } else {
+          // ---- epilogues without global loads: RELU, LN_RELU, STORE16, GATE ----
+          mbar_wait(&tfull, t_ph);
+          if (wtid == 0) CC_TRACE(2, it * n_layers + l);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          if (tile_store_pending && writes_tile) {
+            if (wtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+            workers_sync();
+            tile_store_pending = false;
+          }
+          if (epi == RVO_CHAIN_EPI_RELU) {
+#pragma unroll 2
+            for (int ci = 0; ci < kCcChunks; ci++) {
+              const int c0 = cbase + 16 * ci;
+              float v[16];
+              tmem_ld16(trow + acc_col(c0), v);
+              add_bias16(bias, c0, v);
+#pragma unroll
+              for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
+              store16_tile(A_u, row, c0, v);
+            }
+          } else if (epi == RVO_CHAIN_EPI_STORE16) {
+            __half* y = reinterpret_cast<__half*>(L.y16) + (size_t)e * L.ldy;
+#pragma unroll 2
+            for (int ci = 0; ci < kCcChunks; ci++) {
+              const int c0 = cbase + 16 * ci;
+              float v[16];
+              tmem_ld16(trow + acc_col(c0), v);
+              add_bias16(bias, c0, v);
+              if (valid) store16_row16(y + c0, v);
+            }
+          } else if (epi == RVO_CHAIN_EPI_GATE) {
+#pragma unroll 2
+            for (int ci = 0; ci < kCcChunks; ci++) {
+              const int c0 = cbase + 16 * ci;
+              float v[16];
+              tmem_ld16(trow + acc_col(c0), v);
+              add_bias16(bias, c0, v);
+#pragma unroll
+              for (int i = 0; i < 16; i++) v[i] = 1.0f / (1.0f + __expf(-round_h(v[i])));
+              store16_blk16(scr16, cta, row, c0, v);
+            }
+          } else {                                           // LN_RELU: next A = half(relu(LN(t)))
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll 2
+            for (int ci = 0; ci < kCcChunks; ci++) {
+              const int c0 = cbase + 16 * ci;
+              float v[16];
+              tmem_ld16(trow + acc_col(c0), v);
+              add_bias16(bias, c0, v);
+#pragma unroll
+              for (int i = 0; i < 16; i++) {
+                v[i] = round_h(v[i]);
+                s1 += v[i];
+                s2 += v[i] * v[i];
+              }
+            }
+            xch[row][part] = make_float4(s1, s2, 0.f, 0.f);
+            workers_sync();
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int p = 0; p < kCcParts; p++) {
+              const float4 u = xch[row][p];
+              t1 += u.x; t2 += u.y;
+            }
+            const float mean = t1 * (1.0f / kCcC);
+            const float rstd = rsqrtf(fmaxf(t2 * (1.0f / kCcC) - mean * mean, 0.f) + 1e-3f);
+#pragma unroll 2
+            for (int ci = 0; ci < kCcChunks; ci++) {
+              const int c0 = cbase + 16 * ci;
+              float v[16];
+              tmem_ld16(trow + acc_col(c0), v);
+              add_bias16(bias, c0, v);
+#pragma unroll
+              for (int i = 0; i < 16; i++) v[i] = round_h(v[i]);
+              layer_norm16(v, mean, rstd, L.gamma + c0, L.beta + c0);
+#pragma unroll
+              for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
+              store16_tile(A_u, row, c0, v);
+            }
           }
         }
+        t_ph ^= 1;
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-        if (has_next) {
-          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-          mbar_arrive(&hfull);
+        if (writes_tile) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        if (wtid == 0) CC_TRACE(3, it * n_layers + l);
+        if (tile_out16) {
+          // out16 = half(v) is exactly the activation tile: six TMA box stores straight out of the K-block slots
+          workers_sync();
+          if (wtid == 0 && t < n_tiles) {
+#pragma unroll
+            for (int kb = 0; kb < kCcSlots; kb++)
+              tma_store_2d(&maps.out16, A_u + kb * kCcSlotBytes, kb * 64, t * kCcM);
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+          }
+          tile_store_pending = true;
         }
+        if (has_next) mbar_arrive(&hfull);
       }
-      // the exchange buffer and (GATED stretches) the scratch rows are reused by the next tile
+      // the exchange buffer, the scratch rows and the activation tile are reused by the next tile
+      if (tile_store_pending) {
+        if (wtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        tile_store_pending = false;
+      }
       workers_sync();
     }
     if (stream0) asm volatile("cp.async.wait_all;\n" ::: "memory");
+    if (wtid == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  cluster_sync_all();                                     // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
   }
@@ -571,6 +818,70 @@ up_chain_kernel(const rvo_chain_t a, const __grid_constant__ ChainMaps maps) {
 }  // namespace rvo
 
 using namespace rvo;
+
+// Cluster size of the chain kernel: the largest of 4 / 2 / 1 whose co-resident clusters cover (nearly) the whole
+// device — the kernel is persistent, a cluster that does not fit in the first wave would serialise behind it.
+// g_chain_ctas = CTAs of one wave at that size.  rvo_up_chain_set_cluster forces a size (benchmarks).
+static int g_chain_csize = 0, g_chain_ctas = 0, g_chain_forced = 0;
+
+static int chain_cluster_size() {
+  if (g_chain_csize) return g_chain_csize;
+  if (cudaFuncSetAttribute(up_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCcSmemBytes) != cudaSuccess)
+    return -1;
+  const int cand[3] = {4, 2, 1};
+  for (int i = 0; i < 3; i++) {
+    const int cs = cand[i];
+    if (g_chain_forced && cs != g_chain_forced) continue;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(kNumSMs / cs * cs);
+    cfg.blockDim = dim3(kCcThreads);
+    cfg.dynamicSmemBytes = kCcSmemBytes;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = cs;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, up_chain_kernel, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    int ctas = n * cs;
+    if (ctas > kNumSMs) ctas = kNumSMs / cs * cs;
+    if (ctas >= (g_chain_forced ? cs : (cs == 1 ? 1 : kNumSMs * 7 / 8))) {   // accept 4 only if >= 129 CTAs fit, ...
+      g_chain_csize = cs;
+      g_chain_ctas = ctas;
+      return cs;
+    }
+  }
+  return -1;
+}
+
+extern "C" int rvo_up_chain_set_cluster(int cluster_size) {
+  RVO_CHECK_ARG(cluster_size == 0 || cluster_size == 1 || cluster_size == 2 || cluster_size == 4,
+                "rvo_up_chain_set_cluster: %d (0 = automatic, 1, 2 or 4)", cluster_size);
+  g_chain_forced = cluster_size;
+  g_chain_csize = 0;
+  return RVO_OK;
+}
+
+extern "C" int rvo_up_chain_info(int* cluster_size, int* ctas) {
+  RVO_CHECK_ARG(chain_cluster_size() > 0, "rvo_up_chain_info: no cluster size of up_chain_kernel fits this device");
+  if (cluster_size) *cluster_size = g_chain_csize;
+  if (ctas) *ctas = g_chain_ctas;
+  return RVO_OK;
+}
+
+#ifdef RVO_DEBUG
+extern "C" int rvo_up_chain_trace(long long* host_out) {
+  RVO_CUDA(cudaDeviceSynchronize());
+  RVO_CUDA(cudaMemcpyFromSymbol(host_out, g_cc_trace, sizeof(long long) * 4 * 64));
+  return RVO_OK;
+}
+#endif
 
 extern "C" int64_t rvo_up_chain_scratch_rows(void) { return (int64_t)kNumSMs * kCcM; }
 
@@ -595,6 +906,8 @@ extern "C" int rvo_up_chain(const rvo_chain_t* c, void* stream) {
   }
   ChainMaps maps;
   memset(&maps, 0, sizeof(maps));
+  const int csize = chain_cluster_size();
+  RVO_CHECK_ARG(csize > 0, "rvo_up_chain: no cluster size of up_chain_kernel fits this device");
   bool gate_pending = false;
   for (int l = 0; l < c->n_layers; l++) {
     const rvo_chain_layer_t& L = c->layer[l];
@@ -640,13 +953,30 @@ extern "C" int rvo_up_chain(const rvo_chain_t* c, void* stream) {
       default:
         RVO_CHECK_ARG(false, "rvo_up_chain: layer %d: epilogue %d", l, L.epilogue);
     }
-    int rc = make_tmap_2d_f16(L.w16, kCcC, L.K, L.K, kCcNH, &maps.m[l], "rvo_up_chain(w)");
+    int rc = make_tmap_2d_f16(L.w16, kCcC, L.K, L.K, kCcNH / csize, &maps.m[l], "rvo_up_chain(w)");
+    if (rc != RVO_OK) return rc;
+  }
+  if (c->out16) {
+    int rc = make_tmap_2d_f16(c->out16, c->M, kCcC, kCcC, kCcM, &maps.out16, "rvo_up_chain(out16)");
     if (rc != RVO_OK) return rc;
   }
   const int n_tiles = (c->M + kCcM - 1) / kCcM;
-  const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-  RVO_CUDA(cudaFuncSetAttribute(up_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCcSmemBytes));
-  up_chain_kernel<<<grid, kCcThreads, kCcSmemBytes, (cudaStream_t)stream>>>(*c, maps);
+  int grid = (n_tiles + csize - 1) / csize * csize;          // whole clusters
+  if (grid > g_chain_ctas) grid = g_chain_ctas;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kCcThreads);
+  cfg.dynamicSmemBytes = kCcSmemBytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = csize;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  RVO_CUDA(cudaLaunchKernelEx(&cfg, up_chain_kernel, *c, maps));
   RVO_LAUNCH_CHECK("up_chain_kernel");
   return RVO_OK;
 }

@@ -38,6 +38,26 @@ def _addr(t, off=0):
     return ctypes.c_void_p(t.data_ptr() + off)
 
 
+def chain_rows(M):
+    """rows of a tile-blocked fp32 array that holds M edge rows (whole 128-row tiles)"""
+    return (M + 127) // 128 * 128
+
+
+def chain_block32(x):
+    """[M, 384] fp32 row-major -> the tile-blocked layout rvo_up_chain keeps its private fp32 arrays in
+    ([tile][16-byte chunk 0..95][row 0..127][4 floats], include/rampvo_b200.h); tests / debugging only"""
+    M = x.shape[0]
+    T = chain_rows(M) // 128
+    xp = torch.zeros(T * 128, DIM, dtype=x.dtype, device=x.device)
+    xp[:M] = x
+    return xp.view(T, 128, DIM // 4, 4).permute(0, 2, 1, 3).contiguous().view(T * 128, DIM)
+
+
+def chain_unblock32(xb, M):
+    T = xb.shape[0] // 128
+    return xb.view(T, DIM // 4, 128, 4).permute(0, 2, 1, 3).reshape(T * 128, DIM)[:M]
+
+
 def run_chain(M, prologue, layers, stream, **kw):
     """rvo_up_chain (include/rampvo_b200.h): `layers` = [(w16, bias16, epilogue, {K, gamma, beta, y16, ldy})],
     keyword arguments = the other fields of rvo_chain_t (tensors, ctypes pointers or ints)."""
@@ -190,8 +210,10 @@ class Update(nn.Module):
         """the fused mixed-precision path needs CUDA parameters (it has no other requirement)"""
         return self.norm.weight.is_cuda
 
-    def _forward_fused(self, net, inp, corr, ii, jj, kk, plans, net_out=None):
-        """Same arithmetic and dtypes as the reference under autocast in 9 launches: the five row-local stretches of
+    def _forward_chains(self, net, inp, corr, ii, jj, kk, plans, net_out=None):
+        """EXPERIMENTAL alternative to _forward_fused (Update.use_chains = True; off by default because it is slower:
+        1.05 ms vs 0.77 ms at E = 45 888, profiles/r02_up_chain_experiment.md).
+        Same arithmetic and dtypes as the reference under autocast in 9 launches: the five row-local stretches of
         net.py:69-90 are one rvo_up_chain each (csrc/up_chain.cu: the 128-row activation tile stays in shared memory
         from Linear to Linear, LayerNorm / residual / gate / heads in the epilogues), separated by the two neighbour
         gathers (folded into the next stretch's operand load) and the two SoftAgg reductions (rvo_up_softagg_fg +
@@ -203,7 +225,7 @@ class Update(nn.Module):
         st = _lib.stream_ptr(dev)
         P = _lib.ptr
         f16 = lambda *shape: torch.empty(*(shape or (E, DIM)), dtype=torch.float16, device=dev)
-        f32 = lambda: torch.empty(E, DIM, dtype=torch.float32, device=dev)
+        f32 = lambda: torch.empty(chain_rows(E), DIM, dtype=torch.float32, device=dev)    # tile-blocked layout
         addr = _addr
         chain = lambda prologue, layers, **kw: run_chain(E, prologue, layers, st, **kw)
 
@@ -277,10 +299,9 @@ class Update(nn.Module):
               scratch32=scr32, scratch16=scr16)
         return out, (delta, weight, None)
 
-    def _forward_layers(self, net, inp, corr, ii, jj, kk, plans, net_out=None):
-        """The layer-by-layer form of _forward_fused (one rvo_up_linear per nn.Linear + the row kernels of
-        update_ops.cu): kept as the differential-test reference of the chain kernel (tests/test_gpu_up_chain.py);
-        Update.forward never calls it."""
+    def _forward_fused(self, net, inp, corr, ii, jj, kk, plans, net_out=None):
+        """Same arithmetic and dtypes as the reference under autocast, 17 fp16 GEMMs + 13 fused
+        kernels instead of ~250 launches.  inp: [1,E,384] tensor or (imap_table [N,384] fp16, idx, mod)."""
         L = _lib.lib()
         W = self._fused_weights()
         E = ii.numel()
@@ -408,7 +429,8 @@ class Update(nn.Module):
         dev = net.device
         if torch.is_autocast_enabled() and E > 0:
             with torch.cuda.device(dev), torch.autocast("cuda", enabled=False):
-                return self._forward_fused(net, inp, corr, ii, jj, kk, plans, net_out)
+                fwd = self._forward_chains if getattr(self, "use_chains", False) else self._forward_fused
+                return fwd(net, inp, corr, ii, jj, kk, plans, net_out)
         if isinstance(inp, tuple):
             table, idx, mod = inp
             inp = table.reshape(-1, DIM)[(idx % mod) if mod else idx][None]

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from rampvo_b200 import _lib
-from rampvo_b200.net import DIM, GraphPlans, Update, run_chain
+from rampvo_b200.net import DIM, GraphPlans, Update, chain_block32, chain_rows, chain_unblock32, run_chain
 
 pytestmark = pytest.mark.gpu
 SIZES = [1, 127, 128, 129, 1000, 45312]
@@ -79,14 +79,16 @@ def test_gather_res_chain(M):
     x16 = x32.half()
     idx = torch.randint(-1, M, (M,), device="cuda", dtype=torch.int64)
     ws = weights(r, 4)
-    o32 = torch.empty(M, DIM, device="cuda")
+    o32b = torch.empty(chain_rows(M), DIM, device="cuda")
     o16 = torch.empty(M, DIM, device="cuda", dtype=torch.float16)
     fg = torch.empty(M, 2 * DIM, device="cuda", dtype=torch.float16)
+    x32b = chain_block32(x32)
     run_chain(M, _lib.PRO_ROWS, [(ws[0][0], ws[0][1], _lib.EPI_RELU, {}), (ws[1][0], ws[1][1], _lib.EPI_RES, {}),
                                  (ws[2][0], ws[2][1], _lib.EPI_STORE16, {"y16": fg, "ldy": 2 * DIM}),
                                  (ws[3][0], ws[3][1], _lib.EPI_STORE16, {"y16": ctypes.c_void_p(fg.data_ptr() + 2 * DIM), "ldy": 2 * DIM})],
-              st(), a16=x16, lda=DIM, gather=idx, res32=x32, out32=o32, out16=o16)
+              st(), a16=x16, lda=DIM, gather=idx, res32=x32b, out32=o32b, out16=o16)
     torch.cuda.synchronize()
+    o32 = chain_unblock32(o32b, M)
     g = torch.where((idx >= 0)[:, None], x16[idx.clamp(min=0)].float(), torch.zeros(1, device="cuda"))
     t = rh(lin(rh(torch.relu(lin(g, *ws[0]))), *ws[1]))
     v = x32 + t
@@ -106,13 +108,14 @@ def test_corr_stretch(M):
     net_in = r(M, DIM)
     table = r(50, DIM).half()
     idx = torch.randint(0, 500, (M,), device="cuda", dtype=torch.int64)
-    o32 = torch.empty(M, DIM, device="cuda")
+    o32b = torch.empty(chain_rows(M), DIM, device="cuda")
     o16 = torch.empty(M, DIM, device="cuda", dtype=torch.float16)
     run_chain(M, _lib.PRO_ROWS, [(ws[0][0], ws[0][1], _lib.EPI_RELU, {"K": 1008}),
                                  (ws[1][0], ws[1][1], _lib.EPI_LN_RELU, {"gamma": g1, "beta": be1}),
                                  (ws[2][0], ws[2][1], _lib.EPI_ADD3_LN, {"gamma": g2, "beta": be2})],
-              st(), a16=c, lda=1008, net_in=net_in, imap16=table, imap_idx=idx, imap_mod=50, out32=o32, out16=o16)
+              st(), a16=c, lda=1008, net_in=net_in, imap16=table, imap_idx=idx, imap_mod=50, out32=o32b, out16=o16)
     torch.cuda.synchronize()
+    o32 = chain_unblock32(o32b, M)
     h = rh(torch.relu(lin(c, *ws[0])))
     h = rh(torch.relu(ln(rh(lin(h, *ws[1])), g1, be1)))
     t = rh(lin(h, *ws[2]))
@@ -132,7 +135,7 @@ def test_expand_store(M):
     fg = torch.empty(M, 2 * DIM, device="cuda", dtype=torch.float16)
     run_chain(M, _lib.PRO_EXPAND, [(ws[0][0], ws[0][1], _lib.EPI_STORE16, {"y16": fg, "ldy": 2 * DIM}),
                                    (ws[1][0], ws[1][1], _lib.EPI_STORE16, {"y16": ctypes.c_void_p(fg.data_ptr() + 2 * DIM), "ldy": 2 * DIM})],
-              st(), x32=x32, hy_a=hy, grp_a=grp)
+              st(), x32=chain_block32(x32), hy_a=hy, grp_a=grp)
     torch.cuda.synchronize()
     a = x32 + hy[grp.long()].float()
     close(fg[:, :DIM], lin(a, *ws[0]), "f")
@@ -162,7 +165,7 @@ def test_gru_stretch(M):
                (ws[2][0], ws[2][1], E.EPI_GATED_LN, {"gamma": g2, "beta": b2}),
                (ws[3][0], ws[3][1], E.EPI_GATE, {}), (ws[4][0], ws[4][1], E.EPI_RELU, {}),
                (ws[5][0], ws[5][1], E.EPI_GATED_HEADS, {})],
-              st(), x32=x32, hy_a=hya, grp_a=ga, hy_b=hyb, grp_b=gb, pro_gamma=g0, pro_beta=b0, out32=out,
+              st(), x32=chain_block32(x32), hy_a=hya, grp_a=ga, hy_b=hyb, grp_b=gb, pro_gamma=g0, pro_beta=b0, out32=out,
               Wd=Wd, bd=bd, Ww=Ww, bw=bw, delta=delta, weight=weight, scratch32=s32, scratch16=s16)
     torch.cuda.synchronize()
 
@@ -207,8 +210,8 @@ def test_update_on_chains_matches_layered_form(n_frames, M):
     corr = torch.randn(1, E, 882, generator=g, device="cuda").half()
     plans = GraphPlans(ii, jj, kk)
     with torch.no_grad():
-        a_net, (a_d, a_w, _) = up._forward_fused(net, (imap, kk, 0), corr, ii, jj, kk, plans)
-        b_net, (b_d, b_w, _) = up._forward_layers(net, (imap, kk, 0), corr, ii, jj, kk, plans)
+        a_net, (a_d, a_w, _) = up._forward_chains(net, (imap, kk, 0), corr, ii, jj, kk, plans)
+        b_net, (b_d, b_w, _) = up._forward_fused(net, (imap, kk, 0), corr, ii, jj, kk, plans)
     torch.cuda.synchronize()
     scale = float(b_net.abs().max())
     e_net = float((a_net - b_net).abs().max()) / scale
