@@ -360,13 +360,18 @@ int rvo_gather_rows(const float* src, const int64_t* idx, int E, int C, void* ou
  * in elements (multiples of 8, 16-byte aligned bases); bias16 may be NULL; relu != 0 applies max(., 0). */
 int rvo_up_linear(const void* x16, int64_t ldx, const void* w16, const void* bias16, int M, int K, int N,
                   int relu, void* y16, int64_t ldy, void* stream);
+/* rvo_up_linear whose input row r is x16[gather[r]] (gather[r] < 0: a zero row) — `mask_ix * net[:, ix]` of
+ * ramp/net.py:78-82 folded into the operand load (the gathered copy is never materialised); gather == NULL is
+ * rvo_up_linear. */
+int rvo_up_linear_gather(const void* x16, int64_t ldx, const int64_t* gather, const void* w16, const void* bias16,
+                         int M, int K, int N, int relu, void* y16, int64_t ldy, void* stream);
 
 /* Fused row kernels of the mixed-precision update operator (C = 384; fp16 GEMM operands, fp32
  * hidden state and LayerNorm, eps 1e-3 — the dtypes Update.forward has under autocast,
  * ramp/Ramp_vo.py:280, SURVEY.md appendix "dtype drift").  Each replaces 3-8 elementwise / cast /
  * LayerNorm launches of the reference:
  *   rvo_up_ln_relu        y16 = relu(LN(x16))                               net.py:54-56
- *   rvo_up_add3_ln        net = LN(net + imap16[idx % mod] + h16)           net.py:74-75, Ramp_vo.py:282
+ *   rvo_up_add3_ln        net = LN(net + imap16[idx % mod] + h16) [; net16 = half(net)]  net.py:74-75, Ramp_vo.py:282
  *   rvo_up_add_cast       net += t16 [; net16 = half(net)]                  net.py:81-82
  *   rvo_up_softagg_fg     rvo_softagg on a fused [E,2C] = [f(x) | g(x)] GEMM output; rows of y past the
  *                         last group are zeroed                             blocks.py:42-45
@@ -379,7 +384,7 @@ int rvo_up_ln_relu(const void* x16, const float* gamma, const float* beta, int E
                    void* stream);
 int rvo_up_add3_ln(const float* net_in, const void* imap16, const int64_t* idx, int64_t mod,
                    const void* h16, const float* gamma, const float* beta, int E, int C,
-                   float* net_out, void* stream);
+                   float* net_out, void* net16_out, void* stream);
 int rvo_up_add_cast(float* net, const void* t16, int E, int C, void* net16, void* stream);
 int rvo_up_softagg_fg(const void* fg16, const void* plan, int E, int C, int64_t max_groups, void* y16,
                       void* stream);

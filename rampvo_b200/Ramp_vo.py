@@ -629,7 +629,10 @@ class Ramp_vo:
         return new_net, weight
 
     def _new_plans(self, ii, jj, kk):
-        frames = self.cfg.REMOVAL_WINDOW + 2        # source frames that can still own edges
+        # source frames that can still own edges: REMOVAL_WINDOW + 2 in steady state, and all 8 frames that exist
+        # before initialisation (nothing is removed until n == 8, Ramp_vo.py:385-395) — the SoftAgg group buffers
+        # are sized from this bound (a REMOVAL_WINDOW < 6 used to overflow them silently)
+        frames = max(self.cfg.REMOVAL_WINDOW + 2, 8)
         return GraphPlans(ii, jj, kk, kmax=self.N * self.M, jmax=self.N, max_patches=frames * self.M,
                           max_pairs=frames * (2 * self.cfg.PATCH_LIFETIME + 1))
 

@@ -68,6 +68,7 @@ _SIGNATURES = {
     "rvo_corr_backward": (c_int, [POINTER(FMap), POINTER(FMap), _P, _P, _P, _P, c_int, c_int, _P, _P, _P]),
     "rvo_patchify_backward": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "rvo_up_linear": (c_int, [_P, _I64, _P, _P, c_int, c_int, c_int, c_int, _P, _I64, _P]),
+    "rvo_up_linear_gather": (c_int, [_P, _I64, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _I64, _P]),
     "rvo_corr_tiles_ws_bytes": (_I64, [POINTER(FMap), c_int, c_int]),
     "rvo_corr_tiles": (c_int, [POINTER(FMap), POINTER(FMap), POINTER(c_float), c_int, _P, _P, _P, _I64,
                                _I64, c_int, _P, _I64, _P, _I64, _P]),
@@ -122,7 +123,7 @@ _SIGNATURES = {
     "rvo_expand_add": (c_int, [_P, c_int, _P, c_int, c_int, _P, _P]),
     "rvo_gather_rows": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P]),
     "rvo_up_ln_relu": (c_int, [_P, _P, _P, c_int, c_int, _P, _P]),
-    "rvo_up_add3_ln": (c_int, [_P, _P, _P, _I64, _P, _P, _P, c_int, c_int, _P, _P]),
+    "rvo_up_add3_ln": (c_int, [_P, _P, _P, _I64, _P, _P, _P, c_int, c_int, _P, _P, _P]),
     "rvo_up_add_cast": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "rvo_up_softagg_fg": (c_int, [_P, _P, c_int, c_int, _I64, _P, _P]),
     "rvo_up_expand_add_ln": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),

@@ -40,9 +40,9 @@ __device__ long long g_ug_trace[8 * 64];
 
 template <bool kRelu>
 __global__ void __launch_bounds__(kUgThreads, 1)
-up_linear_kernel(const __half* __restrict__ X, int64_t ldx, const __grid_constant__ TcTmap tmw,
-                 const __half* __restrict__ bias, int M, int n_slices, __half* __restrict__ Y,
-                 int64_t ldy, int trace_arg) {
+up_linear_kernel(const __half* __restrict__ X, int64_t ldx, const int64_t* __restrict__ gather,
+                 const __grid_constant__ TcTmap tmw, const __half* __restrict__ bias, int M, int n_slices,
+                 __half* __restrict__ Y, int64_t ldy, int trace_arg) {
 #ifdef RVO_DEBUG
   const int trace = trace_arg;      // -DRVO_DEBUG builds only
 #else
@@ -131,7 +131,15 @@ up_linear_kernel(const __half* __restrict__ X, int64_t ldx, const __grid_constan
     // ===== X producers: thread owns 16-byte chunk `ch` of rows r0 + 16 j of every K block =====
     const int ptid = tid - 20 * 32, ch = ptid & 7, r0 = ptid >> 3;
     int it = 0;                                            // K-block counter over all tiles of this CTA
-    for (int t = walker; t < n_tiles; t += n_walkers)
+    for (int t = walker; t < n_tiles; t += n_walkers) {
+      // source row of each of this thread's 8 rows: the row itself, or gather[row] (< 0: a zero row — the
+      // mask_ix * net[:, ix] of ramp/net.py:78-82 folded into the operand load)
+      int64_t src[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int row = t * kUgM + r0 + 16 * j;
+        src[j] = row < M ? (gather ? gather[row] : (int64_t)row) : -1;
+      }
       for (int kb = 0; kb < kUgKB; kb++, it++) {
         const int s = it % kUgStages;
         mbar_wait(&xempty[s], ((it / kUgStages) & 1) ^ 1);
@@ -140,9 +148,8 @@ up_linear_kernel(const __half* __restrict__ X, int64_t ldx, const __grid_constan
         const __half* src0 = X + kb * 64 + ch * 8;
 #pragma unroll
         for (int j = 0; j < 8; j++) {                      // (r0 + 16 j) & 7 == r0 & 7: one swizzle per thread
-          const int row = t * kUgM + r0 + 16 * j;
-          const bool ok = row < M;
-          cp_async16(dst0 + j * (16 * 128), src0 + (int64_t)(ok ? row : 0) * ldx, ok ? 16u : 0u);
+          const bool ok = src[j] >= 0;
+          cp_async16(dst0 + j * (16 * 128), src0 + (ok ? src[j] : 0) * ldx, ok ? 16u : 0u);
         }
         // hardware-triggered arrival: the barrier is signalled when THIS thread's copies of the K block have
         // landed.  (The first version waited with cp.async.wait_group + fence.proxy.async before a software
@@ -150,6 +157,7 @@ up_linear_kernel(const __half* __restrict__ X, int64_t ldx, const __grid_constan
         // memory round trip — ~630 ns per K block, three times the 196 ns the four MMAs need.)
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&xfull[s])) : "memory");
       }
+    }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
   } else if (warp >= 4) {
     // ===== epilogue: group g drains accumulator g (tiles lt == g mod 2); quadrant q, thread = row; the two
@@ -221,8 +229,18 @@ up_linear_kernel(const __half* __restrict__ X, int64_t ldx, const __grid_constan
 
 using namespace rvo;
 
+extern "C" int rvo_up_linear_gather(const void* x16, int64_t ldx, const int64_t* gather, const void* w16,
+                                    const void* bias16, int M, int K, int N, int relu, void* y16, int64_t ldy,
+                                    void* stream);
+
 extern "C" int rvo_up_linear(const void* x16, int64_t ldx, const void* w16, const void* bias16, int M, int K,
                              int N, int relu, void* y16, int64_t ldy, void* stream) {
+  return rvo_up_linear_gather(x16, ldx, nullptr, w16, bias16, M, K, N, relu, y16, ldy, stream);
+}
+
+extern "C" int rvo_up_linear_gather(const void* x16, int64_t ldx, const int64_t* gather, const void* w16,
+                                    const void* bias16, int M, int K, int N, int relu, void* y16, int64_t ldy,
+                                    void* stream) {
   RVO_CHECK_ARG(M >= 0 && K == kUgK && N > 0 && N % kUgN == 0 && kNumSMs % (N / kUgN) == 0,
                 "rvo_up_linear: M=%d K=%d N=%d (K must be %d, N a multiple of %d that divides the grid)", M, K, N,
                 kUgK, kUgN);
@@ -242,12 +260,14 @@ extern "C" int rvo_up_linear(const void* x16, int64_t ldx, const void* w16, cons
 #endif
   if (relu) {
     RVO_CUDA(cudaFuncSetAttribute(up_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUgSmemBytes));
-    up_linear_kernel<true><<<kNumSMs, kUgThreads, kUgSmemBytes, st>>>((const __half*)x16, ldx, tmw, (const __half*)bias16,
-                                                                      M, N / kUgN, (__half*)y16, ldy, trace);
+    up_linear_kernel<true><<<kNumSMs, kUgThreads, kUgSmemBytes, st>>>((const __half*)x16, ldx, gather, tmw,
+                                                                      (const __half*)bias16, M, N / kUgN,
+                                                                      (__half*)y16, ldy, trace);
   } else {
     RVO_CUDA(cudaFuncSetAttribute(up_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUgSmemBytes));
-    up_linear_kernel<false><<<kNumSMs, kUgThreads, kUgSmemBytes, st>>>((const __half*)x16, ldx, tmw, (const __half*)bias16,
-                                                                       M, N / kUgN, (__half*)y16, ldy, trace);
+    up_linear_kernel<false><<<kNumSMs, kUgThreads, kUgSmemBytes, st>>>((const __half*)x16, ldx, gather, tmw,
+                                                                       (const __half*)bias16, M, N / kUgN,
+                                                                       (__half*)y16, ldy, trace);
   }
   RVO_LAUNCH_CHECK("up_linear_kernel");
   return RVO_OK;

@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256)
 add3_ln_kernel(const float* __restrict__ net_in, const __half* __restrict__ imap,
                const int64_t* __restrict__ idx, int64_t mod, const __half* __restrict__ h,
                const float* __restrict__ gamma, const float* __restrict__ beta, int E,
-               float* __restrict__ net_out) {
+               float* __restrict__ net_out, __half* __restrict__ net16_out) {
   const int lane = threadIdx.x & 31;
   RVO_ROW_LOOP(e, E) {
     Row a, b, c;
@@ -276,6 +276,7 @@ add3_ln_kernel(const float* __restrict__ net_in, const __half* __restrict__ imap
       for (int q = 0; q < 4; q++) a.v[j][q] = (a.v[j][q] + b.v[j][q]) + c.v[j][q];
     row_layer_norm(a, gamma, beta, lane, 1e-3f);
     row_store_f32(net_out + (size_t)e * kC, lane, a);
+    if (net16_out) row_store_f16(net16_out + (size_t)e * kC, lane, a);
   }
 }
 
@@ -483,12 +484,12 @@ extern "C" int rvo_up_ln_relu(const void* x16, const float* gamma, const float* 
 
 extern "C" int rvo_up_add3_ln(const float* net_in, const void* imap16, const int64_t* idx,
                               int64_t mod, const void* h16, const float* gamma, const float* beta,
-                              int E, int C, float* net_out, void* stream) {
+                              int E, int C, float* net_out, void* net16_out, void* stream) {
   RVO_CHECK_ARG(C == kC, "rvo_up_add3_ln: C=%d (384 expected)", C);
   if (E <= 0) return RVO_OK;
   RVO_CHECK_ARG(net_in && imap16 && idx && h16 && gamma && beta && net_out, "rvo_up_add3_ln: null pointer");
   add3_ln_kernel<<<row_grid(E), 256, 0, (cudaStream_t)stream>>>(
-      net_in, (const __half*)imap16, idx, mod, (const __half*)h16, gamma, beta, E, net_out);
+      net_in, (const __half*)imap16, idx, mod, (const __half*)h16, gamma, beta, E, net_out, (__half*)net16_out);
   RVO_LAUNCH_CHECK("add3_ln_kernel");
   return RVO_OK;
 }

@@ -175,9 +175,12 @@ class Update(nn.Module):
     def _fused_weights(self):
         """fp16 copies of the Linear weights (concatenated where two layers share an input) and
         fp32 LayerNorm / head parameters, cached for inference."""
+        # keyed on every parameter's storage and version: load_state_dict / .to() / an optimiser step rebuild it
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
         w = getattr(self, "_fw", None)
-        if w is not None:
+        if w is not None and getattr(self, "_fw_key", None) == key:
             return w
+        self._fw_key = key
         h = lambda t: t.detach().to(torch.float16).contiguous()
         f = lambda t: t.detach().float().contiguous()
         w = {}
@@ -205,6 +208,7 @@ class Update(nn.Module):
 
     def invalidate_cache(self):
         self._fw = None
+        self._fw_key = None
 
     def _fused_ready(self):
         """the fused mixed-precision path needs CUDA parameters (it has no other requirement)"""
@@ -342,15 +346,18 @@ class Update(nn.Module):
         else:
             table, idx, mod = inp.reshape(E, DIM).to(torch.float16).contiguous(), torch.arange(E, device=dev), 0
         net_in = net.reshape(E, DIM).float().contiguous()
-        x = f32()
+        x, x16 = f32(), f16()
         _lib.check(L.rvo_up_add3_ln(P(net_in), P(table), P(idx), mod, P(h4), P(W["ln_norm"][0]),
-                                    P(W["ln_norm"][1]), E, DIM, P(x), st), "rvo_up_add3_ln")
-        g = f16()
-        x16 = f16()
-        for ka, kb, nbr, last in (("c1a", "c1b", plans.ix, False), ("c2a", "c2b", plans.jx, True)):
-            _lib.check(L.rvo_gather_rows(P(x), P(nbr), E, DIM, P(g), _lib.RVO_F16, st), "rvo_gather_rows")
-            t = lin(lin_relu(g, ka), kb)
-            _lib.check(L.rvo_up_add_cast(P(x), P(t), E, DIM, P(x16) if last else None, st), "rvo_up_add_cast")
+                                    P(W["ln_norm"][1]), E, DIM, P(x), P(x16), st), "rvo_up_add3_ln")
+        for ka, kb, nbr in (("c1a", "c1b", plans.ix), ("c2a", "c2b", plans.jx)):
+            # mask * net[:, nbr] (net.py:78-82) is the operand load of the first Linear: rows of the fp16 copy of
+            # the hidden state gathered by cp.async, a zero row where there is no neighbour
+            w, b = W[ka]
+            g = f16()
+            _lib.check(L.rvo_up_linear_gather(P(x16), DIM, P(nbr), P(w), P(b), E, DIM, DIM, 1, P(g), DIM, st),
+                       "rvo_up_linear_gather")
+            t = lin(g, kb)
+            _lib.check(L.rvo_up_add_cast(P(x), P(t), E, DIM, P(x16), st), "rvo_up_add_cast")
         n32, n16 = f32(), f16()
         for kfg, kh, plan, cap, with_ln in (("kk_fg", "kk_h", plans.plan_k, plans.cap_k, False),
                                             ("ij_fg", "ij_h", plans.plan_ij, plans.cap_ij, True)):

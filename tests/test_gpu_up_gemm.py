@@ -55,3 +55,26 @@ def test_up_linear_rejects_unsupported_shapes():
     y = torch.zeros(8, 384, dtype=torch.float16, device="cuda")
     rc = L.rvo_up_linear(_lib.ptr(x), 128, _lib.ptr(w), None, 8, 128, 384, 0, _lib.ptr(y), 384, _lib.stream_ptr())
     assert rc != 0 and b"K must be 384" in L.rvo_last_error()
+
+
+@pytest.mark.parametrize("M", [129, 5000])
+def test_up_linear_gather_equals_linear_of_gathered_rows(M):
+    """rvo_up_linear_gather: input row r = x[gather[r]], a zero row for gather[r] < 0 (mask_ix * net[:, ix],
+    ramp/net.py:78-82) — bit-identical to materialising the gathered matrix first"""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(M, 384, device="cuda", generator=g).half()
+    w = (torch.randn(384, 384, device="cuda", generator=g) / 384 ** 0.5).half()
+    b = torch.randn(384, device="cuda", generator=g).half()
+    idx = torch.randint(-1, M, (M,), device="cuda", dtype=torch.int64, generator=g)
+    xg = torch.where((idx >= 0)[:, None], x[idx.clamp(min=0)], torch.zeros(1, dtype=torch.float16, device="cuda"))
+    L = _lib.lib()
+    ya = torch.empty(M, 384, dtype=torch.float16, device="cuda")
+    yb = torch.empty(M, 384, dtype=torch.float16, device="cuda")
+    _lib.check(L.rvo_up_linear_gather(_lib.ptr(x), 384, _lib.ptr(idx), _lib.ptr(w), _lib.ptr(b), M, 384, 384, 1,
+                                      _lib.ptr(ya), 384, _lib.stream_ptr()), "rvo_up_linear_gather")
+    _lib.check(L.rvo_up_linear(_lib.ptr(xg), 384, _lib.ptr(w), _lib.ptr(b), M, 384, 384, 1, _lib.ptr(yb), 384,
+                               _lib.stream_ptr()), "rvo_up_linear")
+    torch.cuda.synchronize()
+    assert torch.equal(ya, yb)
+    ref = (xg.float() @ w.float().t() + b.float()).clamp_min(0)
+    assert ((ya.float() - ref).abs() <= 2.0 ** -10 * ref.abs() + 2e-3).all()
