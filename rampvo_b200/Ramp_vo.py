@@ -247,6 +247,9 @@ class Ramp_vo:
         dev = self.device
 
         self.tlist = []
+        self.last_weight = None
+        self.patch_dict_ = None          # pose-prediction caches (Ramp_vo.py:94-95)
+        self.patches_models = None
         self.counter = 0
         self.tstamps_ = torch.zeros(N, dtype=torch.long, device=dev)
         self.poses_ = torch.zeros(N, 7, dtype=torch.float, device=dev)
@@ -363,6 +366,85 @@ class Ramp_vo:
         poses = lietorch.stack(poses, dim=0)
         poses = poses.inv().data.cpu().numpy()
         return poses, np.array(self.tlist, dtype=float)
+
+    # ------------------------------------------------------------------ pose prediction (Ramp_vo.py:412-545)
+    def _virtual_frame(self, last_keyframe_number):
+        """the common head of both prediction entry points: clone the state, bootstrap the pose of the virtual frame
+        `last_keyframe_number` (0-based index) with the motion model, connect every patch of the last
+        PATCH_LIFETIME - 1 frames to it and reproject (Ramp_vo.py:415-443 == :449-475)"""
+        from . import pose_prediction as PP
+        self.sync()
+        next_frame_number = last_keyframe_number + 1
+        next_frame_index = next_frame_number - 1
+        poses = self.poses.clone()
+        poses[:, next_frame_index] = PP.motion_bootstrap(poses=poses[0], n=self.n, MOTION_MODEL=self.cfg.MOTION_MODEL,
+                                                         MOTION_DAMPING=self.cfg.MOTION_DAMPING)
+        intrinsics = self.intrinsics.clone()
+        intrinsics[:, next_frame_index] = intrinsics[:, next_frame_index - 1]
+        patches = self.patches.clone()
+        if self.last_weight is None:
+            raise RuntimeError("pose prediction needs at least one update() (last_weight is empty)")
+        weights = self.last_weight.clone().float()
+        ii, jj, kk, weights_up = PP.add_forward_elements(
+            frame_num=next_frame_number, patch_extracted_num=self.M, ii=self.ii, jj=self.jj, kk=self.kk, ix=self.ix,
+            r=self.cfg.PATCH_LIFETIME, weights=weights)
+        coords = self.reproject(indicies=(ii, jj, kk), poses=poses, patches=patches, intrinsics=intrinsics)
+        return next_frame_number, next_frame_index, poses, patches, intrinsics, ii, jj, kk, weights_up, coords
+
+    @torch.no_grad()
+    def efficient_pose_prediction(self, sec_to_pred_future, abs_time, last_keyframe_number, deg=3, frequency=30):
+        """Ramp_vo.py:414-443: motion-model bootstrap of the virtual frame only (the reference computes the
+        reprojection and discards it; the state is not modified)"""
+        return self._virtual_frame(last_keyframe_number)[2][:, last_keyframe_number]
+
+    @torch.no_grad()
+    def predict_future_pose(self, sec_to_pred_future, abs_time, last_keyframe_number, deg=3, frequency=30):
+        """Ramp_vo.py:446-514: extrapolate every patch track `sec_to_pred_future` frames ahead with per-patch
+        smoothing splines (fitted once and cached, like the reference's patch_dict_ / patches_models), use the
+        predictions as BA targets of a virtual frame behind the last keyframe, run 2 Gauss-Newton iterations on
+        CLONES of the state and append the virtual frame's pose to the trajectory (update_attributes).
+        Deviation: the reference hands the whole [1,E,2,3,3] coordinate tensor to cuda_ba, whose `view(-1, 2)`
+        (ba_cuda.cu:462) then reads the first E/9 edges' grids as E targets; here the patch-centre pixel of every
+        edge is the target, as in update() (Ramp_vo.py:288)."""
+        from . import pose_prediction as PP
+        (next_frame_number, next_frame_index, poses, patches, intrinsics, ii, jj, kk, weights_up,
+         coords) = self._virtual_frame(last_keyframe_number)
+        if self.patch_dict_ is None:
+            self.patch_dict_ = PP.compute_patch_track(coords=coords, ii=ii, jj=jj, kk=kk, image_to_proj=next_frame_index)
+        if self.patches_models is None:
+            self.patches_models = PP.fit_model_patch_track(
+                next_frame_index=next_frame_index, patch_dict=self.patch_dict_, img_to_keyframe_map=self.tstamps_,
+                ii=ii, jj=jj, data_shape=(self.ht, self.wd), frequency=frequency, deg=deg)
+        coords, updated_weight = PP.predict_patch_on_model(
+            patch_models=self.patches_models, step_to_pred_future=sec_to_pred_future, frequency=frequency,
+            next_frame_index=next_frame_index, coords=coords.contiguous(), weights=weights_up, ii=ii, jj=jj, kk=kk)
+        target = coords[:, :, :, self.P // 2, self.P // 2].contiguous()
+        t0 = max(next_frame_number - self.cfg.OPTIMIZATION_WINDOW if self.is_initialized else 1, 1)
+        t1 = next_frame_number
+        try:
+            fastba.BA(poses, patches, intrinsics, target, updated_weight.contiguous(), self.lmbda, ii, jj, kk, t0, t1,
+                      self.M, 2, eff_impl=False)
+        except RuntimeError as e:
+            print(f"WARNING: BA failed...{e}")
+        self.update_attributes(abs_time=abs_time, next_frame_index=next_frame_index, poses=poses)
+
+    def update_attributes(self, abs_time, next_frame_index, poses):
+        """make the virtual frame visible to terminate() (Ramp_vo.py:517-524)"""
+        assert int(self.tstamps_[self.n - 1].item()) != 0
+        self.tstamps_[self.n] = abs_time
+        self.poses_[self.n] = poses[0, next_frame_index]
+        self.tlist.append(abs_time)
+        self.counter += 1
+        self.n += 1
+
+    def remove_attributes(self):
+        """undo update_attributes (Ramp_vo.py:526-533)"""
+        self.n -= 1
+        self.counter -= 1
+        self.tlist.pop()
+        self.poses_[self.n] = torch.zeros(7, dtype=torch.float, device=self.device)
+        self.poses_[:, 6] = 1.0
+        self.tstamps_[self.n] = 0
 
     # ------------------------------------------------------------------ hot-path pieces
     def corr(self, coords, indicies=None):

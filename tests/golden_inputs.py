@@ -100,3 +100,22 @@ def encoder_clip_inputs(device="cpu", T=4, ht=32, wd=48):
     ev = ev * (torch.randint(0, 2, ev.shape, generator=g) * 2 - 1)
     im = torch.rand(1, T, 3, ht, wd, generator=g) * 2 - 0.5
     return ev.to(device), im.to(device), torch.ones(1, T, dtype=torch.bool)
+
+
+def pose_pred_graph():
+    """toy patch graph with a virtual frame (the input of the pose-prediction fixture, tests/golden/pose_pred.npz)"""
+    import torch
+    M, nfr = 3, 9
+    ii, jj, kk = [], [], []
+    for i in range(nfr - 1):
+        for p in range(M):
+            for j in range(max(0, i - 3), min(nfr - 1, i + 4)):
+                ii.append(i); jj.append(j); kk.append(i * M + p)
+    for i in range(nfr - 1 - 3, nfr - 1):            # edges to the virtual frame nfr - 1, appended last
+        for p in range(M):
+            ii.append(i); jj.append(nfr - 1); kk.append(i * M + p)
+    g = torch.Generator().manual_seed(7)
+    E = len(ii)
+    coords = torch.rand(1, E, 2, 3, 3, generator=g) * 200 - 20        # some observations leave the 160 x 120 map
+    return {"ii": torch.tensor(ii), "jj": torch.tensor(jj), "kk": torch.tensor(kk), "coords": coords,
+            "tstamps": torch.arange(0, 5 * nfr, 5), "next_frame_index": nfr - 1, "data_shape": (120, 160), "M": M}
