@@ -93,6 +93,12 @@ def build_vo(device, seed=1234, config="default", world_size=1, rank=0):
     train_cfg = {"event_bias": True, "input_mode": "MultiScale", "num_event_bins": 5}
     cfg = preset(config)
     cfg.KEYFRAME_THRESH = 0.0                    # never drop a keyframe: the no-drop upper-bound graph
+    if os.environ.get("RVO_ENC_AFTER_CORR"):
+        cfg.ENCODER_AFTER_CORR = bool(int(os.environ["RVO_ENC_AFTER_CORR"]))
+    if os.environ.get("RVO_ENC_IN_GAP"):
+        cfg.ENCODER_IN_GAP = bool(int(os.environ["RVO_ENC_IN_GAP"]))
+    if os.environ.get("RVO_SM_SPLIT"):           # experiment hook: "enc,upd" SMs of the two stream graphs
+        cfg.SM_SPLIT = tuple(int(v) for v in os.environ["RVO_SM_SPLIT"].split(","))
     # pipeline: the keyframe step of frame t (its decision is a device->host read) is finished at the start
     # of call t+1, after that frame's encoder graph was launched — same work, overlapped (Ramp_vo.sync())
     vo = Ramp_vo(cfg, VONet(train_cfg), train_cfg, ht=480, wd=640, device=device, pipeline=True,

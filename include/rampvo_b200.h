@@ -49,6 +49,12 @@ int rvo_device_cc(void);
 /* number of kernels this library has launched so far in this process (library-internal cub sort /
  * scan passes are not counted) */
 uint64_t rvo_launch_count(void);
+/* SMs the persistent grids launched by the CALLING host thread may fill (1..148; 0 = all, the default).  Every heavy
+ * kernel of this library keeps one CTA per SM, so two streams whose kernels are launched (or captured into CUDA
+ * graphs) under disjoint budgets share the GPU spatially: Ramp_vo gives the encoder stream and the update stream
+ * their own budgets (config SM_SPLIT).  Results do not depend on it. */
+int rvo_set_sm_budget(int n_sms);
+int rvo_get_sm_budget(void);
 
 /* A strided view of a 4-D feature tensor, logical dims [N, C, H, W], strides in ELEMENTS.
  * Channels-last storage (sC == 1) selects the tensor-core fast path of rvo_corr_*. */
@@ -394,6 +400,18 @@ int rvo_up_gated_tail(const float* x32, const void* a16, const void* r16, int E,
                       const float* gamma, const float* beta, float* out32, void* out16,
                       const float* Wd, const float* bd, const float* Ww, const float* bw, float* delta,
                       float* weight, void* stream);
+
+/* The patch-graph step of a new frame when no keyframe was dropped, in two launches instead of a dozen tensor ops:
+ * remove_factors of the edges whose source frame is < lim (ramp/Ramp_vo.py:203-208, order preserved) followed by the
+ * forward edges (every patch of frames [max(n-r,0), n-1) -> frame n-1, Ramp_vo.py:312-318) and the backward edges
+ * (every patch of frame n-1 -> frames [max(n-r,0), n), patch-major, Ramp_vo.py:320-325) of the new frame n-1
+ * (n = number of frames AFTER the new one was added, M patches per frame, r = PATCH_LIFETIME).
+ *   ii/jj/kk [E0] -> ii_out/jj_out/kk_out [E_new]; src_row [E_new] int32 = old row of a surviving edge, -1 for a new
+ *   one; net_in [E0,C] -> net_out [E_new,C] (rows follow their edges, new edges start at zero; may be NULL).
+ *   E_new is the caller's (host-side) edge count: status[0] (device float) is 0 when the device agrees, else its count + 1. */
+int rvo_edges_step(const int64_t* ii, const int64_t* jj, const int64_t* kk, int E0, int lim, int n, int M, int r,
+                   int64_t* ii_out, int64_t* jj_out, int64_t* kk_out, int E_new, int32_t* src_row, float* status,
+                   const float* net_in, int C, float* net_out, void* stream);
 
 /* ---- fused Linear chains of the update operator (csrc/up_chain.cu) ------------------------------- */
 

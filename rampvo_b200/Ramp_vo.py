@@ -62,6 +62,8 @@ class _PatchifyGraph:
         # parallel branches of the captured graph: context CNN and patch selection on side streams
         enc.branch_stream = torch.cuda.Stream(device=dev)
         vo.network.patchify.branch_stream = torch.cuda.Stream(device=dev)
+        # spatial split of the GPU between the two streams (cfg.SM_SPLIT): the grids captured here fill `enc` SMs
+        _lib.check(_lib.lib().rvo_set_sm_budget(vo.sm_split[0]), "rvo_set_sm_budget")
         # warm up on a side stream (cuDNN / cuBLAS handles, lazy module init), then capture
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
@@ -83,6 +85,7 @@ class _PatchifyGraph:
                 buf.copy_(new)
         self.n_kernels = _lib.lib().rvo_launch_count() - l0   # librampvo kernels inside the graph
         self._held = _lib.Workspace.snapshot(dev)             # scratch the capture baked pointers to
+        _lib.lib().rvo_set_sm_budget(0)
         enc.super_states = saved
         for b in self.state:
             b.zero_()
@@ -159,11 +162,13 @@ class _UpdateGraph:
         self.t0 = torch.zeros(1, dtype=torch.int32, device=dev)
         self.n_free = n_free
         self.side = torch.cuda.Stream(device=dev)
+        self.mid_event = torch.cuda.Event(external=True)
         self.net_in = vo.net                     # view of the current ping-pong buffer
         self.net_out = vo._net_other(E)
         self._load(vo.n - n_free)
         vo.corr_tiles(vo.reproject())            # sizes the persistent corr buffer outside the capture
         snap = (vo.poses_.clone(), vo.patches_.clone(), self.net_in.clone())
+        _lib.check(_lib.lib().rvo_set_sm_budget(vo.sm_split[1]), "rvo_set_sm_budget")
         try:
             # the capture stream is where the replays' scratch lives: warm up ON it so that every workspace
             # (keyed by stream) has its final size before pointers are baked in
@@ -183,6 +188,7 @@ class _UpdateGraph:
                 self._body()
             self.n_kernels = _lib.lib().rvo_launch_count() - l0   # librampvo kernels inside the graph
         finally:
+            _lib.lib().rvo_set_sm_budget(0)
             # the warm-up / capture passes ran BA on the live state: always put it back
             vo.poses_.copy_(snap[0]); vo.patches_.copy_(snap[1]); self.net_in.copy_(snap[2])
         # every buffer the capture baked a raw pointer to and does not own stays alive with the graph: the
@@ -204,9 +210,14 @@ class _UpdateGraph:
         with torch.cuda.stream(side):
             plans = vo._new_plans(self.ii, self.jj, self.kk)
         self.plans = plans
+        def after_corr():
+            cur.wait_stream(side)
+            # an EXTERNAL event node: the encoder stream of the next frame can wait for "reproject + corr of this
+            # update are done" (Ramp_vo.encoder_after_corr) — the latency-critical head of the update then has the
+            # GPU to itself
+            self.mid_event.record(cur)
         _, self.weight = vo._update_body(self.ii, self.jj, self.kk, self.net_in, self.net_out, plans,
-                                         0, self.n_free, t0_dev=self.t0,
-                                         before_update=lambda: cur.wait_stream(side),
+                                         0, self.n_free, t0_dev=self.t0, before_update=after_corr,
                                          with_ba=vo.world_size == 1)
 
     def run(self, t0):
@@ -247,6 +258,24 @@ class Ramp_vo:
         dev = self.device
 
         self.tlist = []
+        # (encoder SMs, update SMs) for the two CUDA graphs of the pipelined frame; 0 = the whole GPU
+        # Scheduling of the pipelined frame (measured on B200, default.yaml; profiles/r02_frame_scheduling.md):
+        #   SM_SPLIT            the encoder graph of frame t+1 and the update graph of frame t are captured with
+        #                       disjoint SM budgets (rvo_set_sm_budget): they run side by side instead of time-slicing
+        #                       the GPU kernel by kernel;
+        #   ENCODER_AFTER_CORR  the encoder of frame t+1 starts once reproject + corr of update t are done;
+        #   ENCODER_IN_GAP      (alternative) the encoder of frame t+1 starts when update t has finished.
+        split = getattr(cfg, "SM_SPLIT", None)
+        self.sm_split = tuple(split) if split is not None else ((32, 116) if pipeline and world_size == 1 else (0, 0))
+        self.encoder_in_gap = bool(getattr(cfg, "ENCODER_IN_GAP", False))
+        self.encoder_after_corr = bool(getattr(cfg, "ENCODER_AFTER_CORR", True))
+        self._last_ugraph = None
+        self.fast_edges = bool(getattr(cfg, "FAST_EDGES", True))   # fused patch-graph step (rvo_edges_step)
+        self._pending_lim = None
+        self._edge_status = None
+        self._edge_src = None
+        self._min_src = 0
+        self._frame_done = None
         self.last_weight = None
         self.patch_dict_ = None          # pose-prediction caches (Ramp_vo.py:94-95)
         self.patches_models = None
@@ -512,6 +541,7 @@ class Ramp_vo:
             key = (self.ii * (self.N + 1) + self.jj).cpu().numpy()
             u, c = np.unique(key, return_counts=True)
             pc = self._pair_cnt = {(int(k) // (self.N + 1), int(k) % (self.N + 1)): int(v) for k, v in zip(u, c)}
+            self._min_src = 0
         return pc
 
     def append_factors(self, ii, jj, pairs=None):
@@ -558,6 +588,40 @@ class Ramp_vo:
         self._net_swap(keep.numel())
         self._plans = None
 
+    def _edges_step(self, lim):
+        """remove_factors(ii < lim) + append_factors(forward) + append_factors(backward) of the frame that was just
+        added (self.n already counts it) in two launches: the edge lists and the hidden-state rows are rebuilt on the
+        device by rvo_edges_step, the host only keeps its pair counts in step."""
+        pc = self._pair_counts()
+        r, M, n = self.cfg.PATCH_LIFETIME, self.M, self.n
+        E0 = self.ii.numel()
+        n_removed = 0
+        for i in range(self._min_src, max(lim, self._min_src)):      # source frames that leave the window
+            for j in range(max(i - r - 1, 0), i + r + 2):
+                n_removed += pc.pop((i, j), 0)
+        self._min_src = max(lim, self._min_src)
+        f0, f1, j0 = max(n - r, 0), max(n - 1, 0), max(n - r, 0)
+        for i in range(f0, f1):
+            pc[(i, n - 1)] = pc.get((i, n - 1), 0) + M
+        for j in range(j0, n):
+            pc[(n - 1, j)] = pc.get((n - 1, j), 0) + M
+        E1 = E0 - n_removed + M * (f1 - f0) + M * (n - j0)
+        dev = self.device
+        if self._edge_status is None:
+            self._edge_status = torch.zeros(1, dtype=torch.float32, device=dev)
+        if self._edge_src is None or self._edge_src.numel() < E1:
+            self._edge_src = torch.empty(max(E1 * 5 // 4, 4096), dtype=torch.int32, device=dev)
+        ii, jj, kk = (torch.empty(E1, dtype=torch.long, device=dev) for _ in range(3))
+        out = self._net_other(E1)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().rvo_edges_step(
+                _lib.ptr(self.ii), _lib.ptr(self.jj), _lib.ptr(self.kk), E0, int(lim), n, M, r, _lib.ptr(ii), _lib.ptr(jj),
+                _lib.ptr(kk), E1, _lib.ptr(self._edge_src), _lib.ptr(self._edge_status), _lib.ptr(self.net), self.DIM, _lib.ptr(out),
+                _lib.stream_ptr(dev)), "rvo_edges_step")
+        self.ii, self.jj, self.kk = ii, jj, kk
+        self._net_swap(E1)
+        self._plans = None
+
     def _graph_plans(self):
         if self._plans is None:
             self._plans = self._new_plans(self.ii, self.jj, self.kk)
@@ -587,13 +651,21 @@ class Ramp_vo:
                              self.kk[k], beta=0.5)
         return flow.mean().item()
 
-    def sync(self):
-        """finish a keyframe step deferred by pipeline mode (no-op otherwise)"""
+    def sync(self, defer_removal=False):
+        """finish a keyframe step deferred by pipeline mode (no-op otherwise).  defer_removal (internal, __call__ only):
+        leave the removal of the edges that fell out of the window to the fused graph step of the new frame"""
+        if self._pending_lim is not None:      # never observable from outside: flush a removal left pending
+            lim, self._pending_lim = self._pending_lim, None
+            self.remove_factors(self.ii < lim, lambda i, j: i < lim)
         if self._pending_kf is not None:
             host, ev = self._pending_kf
             self._pending_kf = None
             ev.synchronize()
-            self._keyframe_finish(host.tolist())
+            vals = host.tolist()
+            if vals[4] != 0.0:
+                raise RuntimeError("rvo_edges_step: the device built %d edges, the host expected another count "
+                                   "(patch-graph bookkeeping out of sync)" % (int(vals[4]) - 1))
+            self._keyframe_finish(vals[:4], defer_removal=defer_removal)
 
     def _keyframe_begin(self):
         """launch the flow-magnitude reduction of the keyframe test (Ramp_vo.py:237-241); returns the device
@@ -623,13 +695,16 @@ class Ramp_vo:
         out4 = self._keyframe_begin()
         host = getattr(self, "_kf_host", None)
         if host is None:
-            host = self._kf_host = torch.empty(4, dtype=torch.float32).pin_memory()
-        host.copy_(out4, non_blocking=True)
+            host = self._kf_host = torch.zeros(5, dtype=torch.float32).pin_memory()
+        host[:4].copy_(out4, non_blocking=True)
+        if self._edge_status is not None:       # status of this frame's rvo_edges_step rides along
+            host[4:].copy_(self._edge_status, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self._pending_kf = (host, ev)
+        self._frame_done = ev           # everything frame t put on the main stream has finished
 
-    def _keyframe_finish(self, vals):
+    def _keyframe_finish(self, vals, defer_removal=False):
         s1, c1, s2, c2 = vals
         nan = float("nan")      # the reference takes the mean of an empty selection (nan) too
         m = (s1 / c1 if c1 else nan) + (s2 / c2 if c2 else nan)
@@ -646,6 +721,7 @@ class Ramp_vo:
             self.ii -= gi.to(self.ii.dtype)
             self.jj -= (self.jj > k).to(self.jj.dtype)
             self._pair_cnt = {(i - (i > k), j - (j > k)): v for (i, j), v in self._pair_counts().items()}
+            self._min_src = max(self._min_src - 1, 0)
             # shift every per-frame buffer one slot down (the reference loops frame by frame)
             n = self.n
             for buf in (self.tstamps_, self.colors_, self.poses_, self.patches_, self.intrinsics_):
@@ -665,6 +741,9 @@ class Ramp_vo:
             self.n -= 1
             self.m -= self.M
         lim = self.n - self.cfg.REMOVAL_WINDOW
+        if defer_removal:           # __call__ fuses it with the new frame's appends (rvo_edges_step)
+            self._pending_lim = lim
+            return
         self.remove_factors(self.ii < lim, lambda i, j: i < lim)     # ix[kk] == ii (index_[f] == f)
 
     def _update_body(self, ii, jj, kk, net_in, net_out, plans, t0, t1, t0_dev=None, before_update=None,
@@ -810,6 +889,7 @@ class Ramp_vo:
                 self._ugraphs.pop(next(iter(self._ugraphs)))
             g = self._ugraphs[key] = _UpdateGraph(self, E, t1 - t0)
         g.run(t0)
+        self._last_ugraph = g
         self._net_swap(E)
         self.last_weight = g.weight
 
@@ -854,8 +934,18 @@ class Ramp_vo:
                 self.sync()
                 self._pgraph = _PatchifyGraph(self)
             g = self._pgraph
+            if self.encoder_after_corr and self._last_ugraph is not None:
+                g.enc_stream.wait_event(self._last_ugraph.mid_event)
+            if self.encoder_in_gap and getattr(self, "_frame_done", None) is not None:
+                # the recurrent chain update(t-1) -> keyframe decision -> host bookkeeping -> update(t) leaves the GPU
+                # idle while the host does its bookkeeping (~0.5 ms); start this frame's encoder exactly then,
+                # instead of letting it compete with update(t-1) for the SMs
+                g.enc_stream.wait_event(self._frame_done)
             g.run(events, images, reinit=(tstamp == 0))      # writes only the graph's staging buffers
-        self.sync()     # pipeline mode: the previous frame's keyframe step, overlapped with the encoder graph
+        # pipeline mode: the previous frame's keyframe step, overlapped with the encoder graph.  In the steady state
+        # the removal of the edges that left the window is fused with this frame's appends (rvo_edges_step)
+        fast = (graphable and self.fast_edges and self.is_initialized and self.world_size == 1 and self.pipeline)
+        self.sync(defer_removal=fast)
         slot = self.n % self.mem
         gslot_store = self._gmap_store[slot * M:(slot + 1) * M]
         if graphable:
@@ -920,8 +1010,12 @@ class Ramp_vo:
             self._owner_dev[self.n] = self._owner[-1]
         self.n += 1
         self.m += self.M
-        self.append_factors(*self._edges_forw())
-        self.append_factors(*self._edges_back())
+        if self._pending_lim is not None:
+            lim, self._pending_lim = self._pending_lim, None
+            self._edges_step(lim)
+        else:
+            self.append_factors(*self._edges_forw())
+            self.append_factors(*self._edges_back())
 
         if self.n == 8 and not self.is_initialized:
             self.is_initialized = True

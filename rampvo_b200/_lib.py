@@ -59,6 +59,10 @@ _SIGNATURES = {
     "rvo_last_error": (c_char_p, []),
     "rvo_device_cc": (c_int, []),
     "rvo_launch_count": (ctypes.c_uint64, []),
+    "rvo_set_sm_budget": (c_int, [c_int]),
+    "rvo_edges_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                               c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "rvo_get_sm_budget": (c_int, []),
     "rvo_patchify_forward": (c_int, [POINTER(FMap), _P, c_int, c_int, _P, _P]),
     "rvo_patchify_bilinear": (c_int, [POINTER(FMap), _P, c_int, c_int, _P, c_int, _I64, _I64, _I64,
                                       _I64, _I64, _P]),

@@ -466,7 +466,7 @@ static int corr_launch(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const flo
     static const int variant = getenv("RVO_CORR_VARIANT") ? atoi(getenv("RVO_CORR_VARIANT")) : 22;
     const int occ = variant % 10;
     int grid = cdiv(E, kWarpsPerCta);
-    if (grid > kNumSMs * occ) grid = kNumSMs * occ;   // persistent: `occ` resident CTAs per SM
+    if (grid > sm_budget() * occ) grid = sm_budget() * occ;   // persistent: `occ` resident CTAs per SM
 #define RVO_CORR_LAUNCH(NL_, NTB_, OCC_)                                                       \
     corr_mma_kernel<128, NL_, NTB_, OCC_><<<grid, kWarpsPerCta * 32, 0, st>>>(                  \
         (const __half*)g.data, g.N, g.sN, g.sH, g.sW, L, coords, kk, jj, pmod, fmod, E,         \
@@ -491,7 +491,7 @@ static int corr_launch(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, const flo
   const size_t smem = (size_t)8 * D * D * sizeof(float);
   const int64_t nwork = (int64_t)E * g.H * g.W * nlevels;
   int64_t grid = (nwork + 7) / 8;
-  if (grid > (int64_t)kNumSMs * 64) grid = (int64_t)kNumSMs * 64;
+  if (grid > (int64_t)sm_budget() * 64) grid = (int64_t)sm_budget() * 64;
   if (fmap1->dtype == RVO_F16)
     corr_generic_kernel<__half><<<(int)grid, 256, smem, st>>>(g, L, coords, kk, jj, pmod, fmod, E,
                                                               radius, (__half*)out, out_ld);
@@ -517,7 +517,7 @@ extern "C" int rvo_patchify_forward(const rvo_fmap_t* net, const float* coords, 
   const int D = 2 * radius + 2;
   const int64_t total = (int64_t)v.N * M * v.C * D * D;
   int64_t grid = (total + 255) / 256;
-  if (grid > (int64_t)kNumSMs * 32) grid = (int64_t)kNumSMs * 32;
+  if (grid > (int64_t)sm_budget() * 32) grid = (int64_t)sm_budget() * 32;
   const bool c_fast = (v.sC == 1);
   cudaStream_t st = (cudaStream_t)stream;
   if (net->dtype == RVO_F16)
@@ -540,7 +540,7 @@ extern "C" int rvo_patchify_bilinear(const rvo_fmap_t* net, const float* coords,
   const int d = 2 * radius + 1;
   const int64_t total = (int64_t)v.N * M * v.C * d * d;
   int64_t grid = (total + 255) / 256;
-  if (grid > (int64_t)kNumSMs * 32) grid = (int64_t)kNumSMs * 32;
+  if (grid > (int64_t)sm_budget() * 32) grid = (int64_t)sm_budget() * 32;
   const bool c_fast = (v.sC == 1);
   cudaStream_t st = (cudaStream_t)stream;
 #define RVO_PB(TI, TO)                                                                          \

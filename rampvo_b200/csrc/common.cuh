@@ -43,6 +43,14 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 constexpr int kNumSMs = 148;  // B200
 
+// SMs the persistent grids of the calling host thread may fill (default: all).  The two-stream frame loop gives the
+// encoder stream and the update stream disjoint budgets: every heavy kernel here holds one CTA per SM (shared
+// memory), so a kernel launched with a grid of `budget` CTAs leaves the other SMs to the other stream's kernels
+// — spatial partitioning without MPS / green contexts.  rvo_set_sm_budget() sets it (CUDA graphs bake the grid
+// sizes in at capture).
+extern thread_local int g_sm_budget;
+static inline int sm_budget() { return g_sm_budget; }
+
 // ---- SE3 device helpers (quaternion xyzw, as ramp/fastba/ba_cuda.cu:36-174 and
 // ramp/lietorch/include/so3.h:55-60, se3.h:36-56 define the algebra) ----
 

@@ -350,9 +350,10 @@ extern "C" int rvo_conv2d_nhwc(const void* src0, int C0, const void* src1, int C
   };
   while (n_slices <= 16 && !fits(n_slices)) n_slices++;
   RVO_CHECK_ARG(n_slices <= 16, "rvo_conv2d_nhwc: Cout = %d with K = %d does not fit", Cout, Kpad);
-  while (fits(n_slices * 2) && Cout / (n_slices * 2) >= 32 && (int64_t)n_tiles * n_slices < kNumSMs) n_slices *= 2;
+  while (fits(n_slices * 2) && Cout / (n_slices * 2) >= 32 && (int64_t)n_tiles * n_slices < sm_budget()) n_slices *= 2;
   const int N = Cout / n_slices;
-  int grid = kNumSMs - kNumSMs % n_slices;
+  int grid = sm_budget() - sm_budget() % n_slices;
+  if (grid < n_slices) grid = n_slices;
   if ((int64_t)n_tiles * n_slices < grid) grid = n_tiles * n_slices;
   TcTmap tmw;
   int rc = make_tmap_2d_f16(w_packed, Cout, Kpad, Kpad, N, &tmw, "rvo_conv2d_nhwc(w)");

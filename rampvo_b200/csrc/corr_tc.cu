@@ -752,7 +752,7 @@ extern "C" int rvo_corr_tiles(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, co
   RVO_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)((char*)w.tot - (char*)w.cnt) + (size_t)G.nbins * 4, st));   // cnt + tot
   RVO_CHECK_ARG(G.nbins <= kScanMaxBins, "rvo_corr_tiles: %d tiles exceed the scan capacity", G.nbins);
   int grid = (int)((R + 255) / 256);
-  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  if (grid > sm_budget() * 16) grid = sm_budget() * 16;
   tc_bin_count_kernel<<<(int)(((int64_t)E * nlevels + 255) / 256), 256, 0, st>>>(G, coords, kk, jj, pmod, fmod, fmap1->N, E,
                                                                                   w.cnt, w.tot, w.rowbin, w.rowrank,
                                                                                   (__half*)out, out_ld);
@@ -778,7 +778,7 @@ extern "C" int rvo_corr_tiles(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, co
     if (rc != RVO_OK) return rc;
   }
   RVO_CUDA(cudaFuncSetAttribute(corr_tile_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
-  corr_tile_tma_kernel<<<kNumSMs, kTmaThreads, kTmaSmemBytes, st>>>(tm[0], tm[1], (const __half*)fmap1->data,
+  corr_tile_tma_kernel<<<sm_budget(), kTmaThreads, kTmaSmemBytes, st>>>(tm[0], tm[1], (const __half*)fmap1->data,
                                                                     w.hdr, w.rows, w.total, (__half*)out, dbg);
   RVO_LAUNCH_CHECK("corr_tile_tma_kernel");
   return RVO_OK;

@@ -119,7 +119,7 @@ extern "C" int rvo_in_stats(const void* x16, int64_t npix, int C, float* sums, v
   if (npix == 0) return RVO_OK;
   const int rows = 256 / (C / 8);
   int64_t grid = (npix + rows - 1) / rows;
-  if (grid > kNumSMs * 4) grid = kNumSMs * 4;
+  if (grid > sm_budget() * 4) grid = sm_budget() * 4;
   in_stats_kernel<<<(int)grid, 256, 0, st>>>((const __half*)x16, npix, C, sums);
   RVO_LAUNCH_CHECK("in_stats_kernel");
   return RVO_OK;
@@ -134,7 +134,7 @@ extern "C" int rvo_in_apply(const void* t16, const float* sums_t, const void* re
   RVO_CHECK_ARG(res16 || !sums_res, "rvo_in_apply: shortcut statistics without a shortcut");
   if (npix == 0) return RVO_OK;
   int64_t grid = (npix * (C / 8) + 255) / 256;
-  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  if (grid > sm_budget() * 8) grid = sm_budget() * 8;
   in_apply_kernel<<<(int)grid, 256, 4 * (size_t)C * sizeof(float), (cudaStream_t)stream>>>(
       (const __half*)t16, sums_t, (const __half*)res16, sums_res, npix, C, eps, (__half*)out16);
   RVO_LAUNCH_CHECK("in_apply_kernel");
@@ -498,7 +498,7 @@ extern "C" int rvo_stem_forward(const float* params, int Ce, int Ci, int k, int 
     const size_t sm2 = stem_mma_smem(sp, h);
     int per_sm = (int)((220 * 1024) / (sm2 + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
-    const int grid2 = grid < kNumSMs * per_sm ? grid : kNumSMs * per_sm;
+    const int grid2 = grid < sm_budget() * per_sm ? grid : sm_budget() * per_sm;
 #define RVO_STEM2(HID, KK)                                                                         \
   do {                                                                                             \
     RVO_CUDA(cudaFuncSetAttribute(stem_mma_kernel<HID, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

@@ -29,6 +29,18 @@ extern "C" const char* rvo_last_error(void) { return rvo::g_err; }
 
 extern "C" uint64_t rvo_launch_count(void) { return rvo::g_launches; }
 
+namespace rvo {
+thread_local int g_sm_budget = kNumSMs;
+}
+
+extern "C" int rvo_set_sm_budget(int n_sms) {
+  RVO_CHECK_ARG(n_sms >= 0 && n_sms <= rvo::kNumSMs, "rvo_set_sm_budget: %d (1..%d, 0 = all)", n_sms, rvo::kNumSMs);
+  rvo::g_sm_budget = n_sms == 0 ? rvo::kNumSMs : n_sms;
+  return RVO_OK;
+}
+
+extern "C" int rvo_get_sm_budget(void) { return rvo::g_sm_budget; }
+
 extern "C" int rvo_device_cc(void) {
   int dev = 0, major = 0, minor = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }

@@ -128,7 +128,7 @@ static inline int ceil_log2(int64_t v) {
 
 static inline int grid1d(int64_t n, int per_sm = 8) {
   int64_t b = (n + 255) / 256;
-  const int64_t cap = (int64_t)kNumSMs * per_sm;
+  const int64_t cap = (int64_t)sm_budget() * per_sm;
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
@@ -686,7 +686,7 @@ static int ba_assemble(const BaWs& w, const float* poses, const float* patches,
   RVO_CHECK_ARG(smem <= kSmemMax, "rvo_ba: optimisation window of %d poses is too large", N);
   int64_t want = (cap + kBaWarps - 1) / kBaWarps;
   const int ctas_per_sm = smem_s ? (int)(kSmemMax / (smem + 1024) < 1 ? 1 : (kSmemMax / (smem + 1024) > 4 ? 4 : kSmemMax / (smem + 1024))) : 4;
-  int grid = (int)(want < 1 ? 1 : (want > (int64_t)kNumSMs * ctas_per_sm ? (int64_t)kNumSMs * ctas_per_sm : want));
+  int grid = (int)(want < 1 ? 1 : (want > (int64_t)sm_budget() * ctas_per_sm ? (int64_t)sm_budget() * ctas_per_sm : want));
   if (smem_s) {
     RVO_CUDA(cudaFuncSetAttribute(ba_assemble_kernel<true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
@@ -723,7 +723,7 @@ static int ba_solve(const BaWs& w, float* poses, float* patches, const float* Sy
   }
   int64_t warps = cap;
   int grid = (int)((warps * 32 + 255) / 256);
-  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  if (grid > sm_budget() * 8) grid = sm_budget() * 8;
   if (grid < 1) grid = 1;
   ba_depth_kernel<<<grid, 256, 0, st>>>(w.plan.count, w.plan.kx, (int)cap, n6, w.Qg, w.ug, w.Eg,
                                         w.dX, P, patches);

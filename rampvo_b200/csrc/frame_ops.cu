@@ -455,7 +455,7 @@ extern "C" int rvo_copy_segments(const void* const* src, void* const* dst, const
   const int64_t total = s.start[n];
   if (total == 0) return RVO_OK;
   int grid = cdiv(total, 256);
-  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  if (grid > sm_budget() * 16) grid = sm_budget() * 16;
   if (vec)
     copy_segments_kernel<uint4><<<grid, 256, 0, (cudaStream_t)stream>>>(s);
   else
@@ -479,10 +479,137 @@ extern "C" int rvo_event_stack(const uint16_t* x, const uint16_t* y, const float
   }
   RVO_CHECK_ARG(x && y && p, "rvo_event_stack: null event arrays");
   int grid = cdiv(n_events, 256);
-  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  if (grid > sm_budget() * 8) grid = sm_budget() * 8;
   event_scatter_kernel<<<grid, 256, 0, st>>>(x, y, p, n_events, bins, H, W, stack_f32);
   RVO_LAUNCH_CHECK("event_scatter_kernel");
   event_finalize_kernel<<<cdiv(n, 256), 256, 0, st>>>(stack_f32, n, stack_i8);
   RVO_LAUNCH_CHECK("event_finalize_kernel");
+  return RVO_OK;
+}
+
+// ------------------------------------------------------------------ patch-graph step of a new frame ----
+//
+// What Ramp_vo does to the edge list between two recurrent updates when no keyframe is dropped
+// (ramp/Ramp_vo.py:203-208 remove_factors of the edges whose source frame left the removal window, :194-201 +
+// :312-325 append_factors of the new frame's forward and backward edges) costs the reference — and cost this
+// repo's host code — a dozen small tensor ops (boolean index, three cats, a row gather of the hidden state) on the
+// critical path between the keyframe decision and the next update.  Here it is two launches:
+//   edges_step_kernel   ONE CTA: order-preserving compaction of (ii, jj, kk) by `ii >= lim` (chunked block scan),
+//                       then the appended edges generated from (n, M, r); src_row[e'] = the old row of every
+//                       surviving edge, -1 for a new edge;
+//   net_rows_kernel     the hidden state rows follow: net_out[e'] = net_in[src_row[e']] or 0.
+namespace rvo {
+
+constexpr int kEsThreads = 1024;
+
+constexpr int kEsTiles = 64;        // tiles of kEsThreads edges per round: one keep bit per tile in a 64-bit register
+
+__global__ void __launch_bounds__(kEsThreads)
+edges_step_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, const int64_t* __restrict__ kk,
+                  int E0, int lim, int n, int M, int r, int64_t* __restrict__ ii_o, int64_t* __restrict__ jj_o,
+                  int64_t* __restrict__ kk_o, int32_t* __restrict__ src_row, int E_expected,
+                  float* __restrict__ status) {
+  // wpre[j][w]: kept edges of tile j in the warps before w (after the scan); tbase[j]: kept edges before tile j
+  __shared__ int wpre[kEsTiles][kEsThreads / 32];
+  __shared__ int tbase[kEsTiles + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int kept = 0;
+  for (int e0 = 0; e0 < E0; e0 += kEsTiles * kEsThreads) {        // rounds of 65 536 edges
+    const int T = min(kEsTiles, (E0 - e0 + kEsThreads - 1) / kEsThreads);
+    // pass 1: coalesced, independent loads; one keep bit per tile
+    unsigned long long mask = 0ull;
+#pragma unroll 8
+    for (int j = 0; j < T; j++) {
+      const int idx = e0 + j * kEsThreads + tid;
+      if (idx < E0 && ii[idx] >= lim) mask |= 1ull << j;
+    }
+    for (int j = 0; j < T; j++) {
+      const unsigned bal = __ballot_sync(0xffffffffu, (mask >> j) & 1ull);
+      if (lane == 0) wpre[j][warp] = __popc(bal);
+    }
+    __syncthreads();
+    for (int j = warp; j < T; j += kEsThreads / 32) {             // exclusive scan over the warps of tile j
+      const int c = wpre[j][lane];
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      wpre[j][lane] = incl - c;
+      if (lane == 31) tbase[j + 1] = incl;                         // tile total for now
+    }
+    __syncthreads();
+    if (tid == 0) {
+      tbase[0] = kept;
+      for (int j = 0; j < T; j++) tbase[j + 1] += tbase[j];
+    }
+    __syncthreads();
+    // pass 2: every kept edge moves to its rank (order preserved)
+    for (int j = 0; j < T; j++) {
+      const unsigned bal = __ballot_sync(0xffffffffu, (mask >> j) & 1ull);
+      if ((mask >> j) & 1ull) {
+        const int idx = e0 + j * kEsThreads + tid;
+        const int pos = tbase[j] + wpre[j][warp] + __popc(bal & ((1u << lane) - 1u));
+        ii_o[pos] = ii[idx]; jj_o[pos] = jj[idx]; kk_o[pos] = kk[idx];
+        src_row[pos] = idx;
+      }
+    }
+    kept = tbase[T];
+    __syncthreads();
+  }
+  // forward edges: every patch of frames [f0, f1) -> frame n-1 (Ramp_vo.py:312-318)
+  const int f0 = max(n - r, 0), f1 = max(n - 1, 0);
+  const int n_f = M * (f1 - f0);
+  for (int t = tid; t < n_f; t += kEsThreads) {
+    const int k = M * f0 + t;
+    ii_o[kept + t] = k / M; jj_o[kept + t] = n - 1; kk_o[kept + t] = k;
+    src_row[kept + t] = -1;
+  }
+  // backward edges: every patch of frame n-1 -> frames [j0, n), patch-major (Ramp_vo.py:320-325, 'ij' meshgrid)
+  const int j0 = max(n - r, 0), nj = n - j0;
+  const int n_b = n >= 1 ? M * nj : 0;
+  for (int t = tid; t < n_b; t += kEsThreads) {
+    const int p = t / nj, j = j0 + (t - p * nj);
+    const int o = kept + n_f + t;
+    ii_o[o] = n - 1; jj_o[o] = j; kk_o[o] = (int64_t)M * (n - 1) + p;
+    src_row[o] = -1;
+  }
+  if (tid == 0) status[0] = kept + n_f + n_b == E_expected ? 0.0f : (float)(kept + n_f + n_b + 1);
+}
+
+// warp per row of C = 384 floats
+__global__ void __launch_bounds__(256)
+net_rows_kernel(const float* __restrict__ net_in, const int32_t* __restrict__ src_row, int E, int C4,
+                float* __restrict__ net_out) {
+  const int lane = threadIdx.x & 31;
+  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < E; e += (gridDim.x * blockDim.x) >> 5) {
+    const int s = src_row[e];
+    const float4* src = reinterpret_cast<const float4*>(net_in) + (size_t)(s < 0 ? 0 : s) * C4;
+    float4* dst = reinterpret_cast<float4*>(net_out) + (size_t)e * C4;
+    for (int c = lane; c < C4; c += 32) dst[c] = s < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : src[c];
+  }
+}
+
+}  // namespace rvo
+
+extern "C" int rvo_edges_step(const int64_t* ii, const int64_t* jj, const int64_t* kk, int E0, int lim, int n, int M,
+                              int r, int64_t* ii_out, int64_t* jj_out, int64_t* kk_out, int E_new,
+                              int32_t* src_row, float* status, const float* net_in, int C, float* net_out,
+                              void* stream) {
+  RVO_CHECK_ARG(E0 >= 0 && E_new >= 0 && n >= 1 && M >= 1 && r >= 1, "rvo_edges_step: bad sizes");
+  RVO_CHECK_ARG(ii_out && jj_out && kk_out && src_row && status && (E0 == 0 || (ii && jj && kk)),
+                "rvo_edges_step: null pointer");
+  RVO_CHECK_ARG(!net_out || ((net_in || E0 == 0) && C % 4 == 0 && net_out != net_in), "rvo_edges_step: hidden-state buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  rvo::edges_step_kernel<<<1, rvo::kEsThreads, 0, st>>>(ii, jj, kk, E0, lim, n, M, r, ii_out, jj_out, kk_out, src_row,
+                                                       E_new, status);
+  RVO_LAUNCH_CHECK("edges_step_kernel");
+  if (net_out && E_new > 0) {
+    int grid = rvo::cdiv((int64_t)E_new * 32, 256);
+    if (grid > rvo::sm_budget() * 8) grid = rvo::sm_budget() * 8;
+    rvo::net_rows_kernel<<<grid, 256, 0, st>>>(net_in, src_row, E_new, C / 4, net_out);
+    RVO_LAUNCH_CHECK("net_rows_kernel");
+  }
   return RVO_OK;
 }

@@ -199,7 +199,7 @@ flow_mag_kernel(const float* __restrict__ poses, const float* __restrict__ patch
 
 static inline int grid_for(int64_t n) {
   int64_t b = (n + 255) / 256;
-  int64_t cap = (int64_t)kNumSMs * 16;
+  int64_t cap = (int64_t)sm_budget() * 16;
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 

@@ -181,10 +181,10 @@ extern "C" int rvo_scene_lstm_forward(const float* params, int Ce, int Ci, const
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t HW = (int64_t)H * W;
   RVO_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int32_t), st));
-  scene_presence_kernel<<<kNumSMs * 4, 256, 0, st>>>(events, HW * Ce, image, HW * Ci, flags);
+  scene_presence_kernel<<<sm_budget() * 4, 256, 0, st>>>(events, HW * Ce, image, HW * Ci, flags);
   RVO_LAUNCH_CHECK("scene_presence_kernel");
   int grid = cdiv(HW, 128);
-  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  if (grid > sm_budget() * 16) grid = sm_budget() * 16;
   scene_lstm_kernel<5, 3><<<grid, 128, 0, st>>>(params, events, image, HW, state_ev, state_im, super_state, flags,
                                                 first, (__half*)out16);
   RVO_LAUNCH_CHECK("scene_lstm_kernel");

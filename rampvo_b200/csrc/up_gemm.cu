@@ -241,8 +241,8 @@ extern "C" int rvo_up_linear(const void* x16, int64_t ldx, const void* w16, cons
 extern "C" int rvo_up_linear_gather(const void* x16, int64_t ldx, const int64_t* gather, const void* w16,
                                     const void* bias16, int M, int K, int N, int relu, void* y16, int64_t ldy,
                                     void* stream) {
-  RVO_CHECK_ARG(M >= 0 && K == kUgK && N > 0 && N % kUgN == 0 && kNumSMs % (N / kUgN) == 0,
-                "rvo_up_linear: M=%d K=%d N=%d (K must be %d, N a multiple of %d that divides the grid)", M, K, N,
+  RVO_CHECK_ARG(M >= 0 && K == kUgK && N > 0 && N % kUgN == 0 && N / kUgN <= 16,
+                "rvo_up_linear: M=%d K=%d N=%d (K must be %d, N a multiple of %d, at most 16 column slices)", M, K, N,
                 kUgK, kUgN);
   if (M == 0) return RVO_OK;
   RVO_CHECK_ARG(x16 && w16 && y16, "rvo_up_linear: null pointer");
@@ -253,6 +253,9 @@ extern "C" int rvo_up_linear_gather(const void* x16, int64_t ldx, const int64_t*
   int rc = make_tmap_2d_f16(w16, N, K, K, kUgN, &tmw, "rvo_up_linear(w)");
   if (rc != RVO_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  const int ug_slices = N / kUgN;
+  int ug_grid = sm_budget() - sm_budget() % ug_slices;        // (column slices) x (row walkers)
+  if (ug_grid < ug_slices) ug_grid = ug_slices;
 #ifdef RVO_DEBUG
   const int trace = getenv("RVO_UP_TRACE") ? atoi(getenv("RVO_UP_TRACE")) : 0;
 #else
@@ -260,12 +263,12 @@ extern "C" int rvo_up_linear_gather(const void* x16, int64_t ldx, const int64_t*
 #endif
   if (relu) {
     RVO_CUDA(cudaFuncSetAttribute(up_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUgSmemBytes));
-    up_linear_kernel<true><<<kNumSMs, kUgThreads, kUgSmemBytes, st>>>((const __half*)x16, ldx, gather, tmw,
+    up_linear_kernel<true><<<ug_grid, kUgThreads, kUgSmemBytes, st>>>((const __half*)x16, ldx, gather, tmw,
                                                                       (const __half*)bias16, M, N / kUgN,
                                                                       (__half*)y16, ldy, trace);
   } else {
     RVO_CUDA(cudaFuncSetAttribute(up_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUgSmemBytes));
-    up_linear_kernel<false><<<kNumSMs, kUgThreads, kUgSmemBytes, st>>>((const __half*)x16, ldx, gather, tmw,
+    up_linear_kernel<false><<<ug_grid, kUgThreads, kUgSmemBytes, st>>>((const __half*)x16, ldx, gather, tmw,
                                                                        (const __half*)bias16, M, N / kUgN,
                                                                        (__half*)y16, ldy, trace);
   }

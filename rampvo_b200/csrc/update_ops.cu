@@ -8,6 +8,8 @@
 //             torch.unique.  Bound: HBM, 2 * E * C * sizeof(half) bytes in + U * C out.
 //   expand    h(y)[:, group_of_edge] added to the hidden state (blocks.py:47-48 + net.py:84-85).
 //   gather    mask * net[:, ix] (net.py:78-82) for the neighbour MLPs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rvo {
@@ -88,7 +90,7 @@ __global__ void gather_rows384_kernel(const float* __restrict__ src, const int64
                                       int E, __half* __restrict__ out);
 
 static inline int grid_cap(int64_t n, int per_sm) {
-  const int64_t cap = (int64_t)kNumSMs * per_sm;
+  const int64_t cap = (int64_t)sm_budget() * per_sm;
   return (int)(n < 1 ? 1 : (n > cap ? cap : n));
 }
 
@@ -145,7 +147,7 @@ extern "C" int rvo_gather_rows(const float* src, const int64_t* idx, int E, int 
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == RVO_F16 && C == 384) {
     const int64_t b = ((int64_t)E * 32 + 255) / 256;
-    gather_rows384_kernel<<<(int)(b > kNumSMs * 8 ? kNumSMs * 8 : b), 256, 0, st>>>(src, idx, E, (__half*)out);
+    gather_rows384_kernel<<<(int)(b > sm_budget() * 8 ? sm_budget() * 8 : b), 256, 0, st>>>(src, idx, E, (__half*)out);
     RVO_LAUNCH_CHECK("gather_rows384_kernel");
     return RVO_OK;
   }
@@ -463,9 +465,21 @@ gather_rows384_kernel(const float* __restrict__ src, const int64_t* __restrict__
   }
 }
 
+// CTAs of 256 threads per SM for the row kernels.  8 fill every thread slot of the SM; in the two-stream frame
+// (encoder of frame t+1 beside the update of frame t) that keeps the encoder's latency-bound CTAs out until the
+// row kernel has drained.  RVO_ROW_CTAS_PER_SM (debug builds) sweeps it.
+static inline int row_ctas_per_sm() {
+#ifdef RVO_DEBUG
+  static const int v = getenv("RVO_ROW_CTAS_PER_SM") ? atoi(getenv("RVO_ROW_CTAS_PER_SM")) : 8;
+  return v < 1 ? 1 : (v > 8 ? 8 : v);
+#else
+  return 8;
+#endif
+}
+
 static inline int row_grid(int E) {
   const int64_t b = ((int64_t)E * 32 + 255) / 256;
-  const int64_t cap = (int64_t)kNumSMs * 8;
+  const int64_t cap = (int64_t)sm_budget() * row_ctas_per_sm();
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
@@ -513,7 +527,7 @@ extern "C" int rvo_up_softagg_fg(const void* fg16, const void* plan, int E, int 
   int rc = rvo_plan_groups(plan, E, &count, &perm, nullptr, &seg_start, nullptr);
   if (rc != RVO_OK) return rc;
   const int cap = (int)((max_groups > 0 && max_groups < E) ? max_groups : E);
-  int grid = cap < kNumSMs * 16 ? cap : kNumSMs * 16;
+  int grid = cap < sm_budget() * 2 * row_ctas_per_sm() ? cap : sm_budget() * 2 * row_ctas_per_sm();
   if (grid < 1) grid = 1;
   RVO_CHECK_ARG(C == kC, "rvo_up_softagg_fg: C=%d (384 expected)", C);
   softagg_fg_kernel<<<grid, kSaThreads, 0, (cudaStream_t)stream>>>(count, perm, seg_start,

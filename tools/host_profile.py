@@ -34,7 +34,8 @@ def main():
     vo = bench.build_vo(dev)
     for t in range(bench.SETUP_FRAMES + 3):
         vo(t, frames[t], seq.intrinsics)
-    for name in ("update", "keyframe", "append_factors", "remove_factors", "_update_graphed", "_edges_forw", "_edges_back"):
+    for name in ("__call__", "sync", "_keyframe_defer", "update", "keyframe", "append_factors", "remove_factors",
+                 "_update_graphed", "_edges_forw", "_edges_back", "_edges_step", "_keyframe_finish", "_pair_counts"):
         wrap(Ramp_vo, name)
     from rampvo_b200 import Ramp_vo as mod
     wrap(mod._PatchifyGraph, "run")
