@@ -266,7 +266,8 @@ class Ramp_vo:
         #   ENCODER_AFTER_CORR  the encoder of frame t+1 starts once reproject + corr of update t are done;
         #   ENCODER_IN_GAP      (alternative) the encoder of frame t+1 starts when update t has finished.
         split = getattr(cfg, "SM_SPLIT", None)
-        self.sm_split = tuple(split) if split is not None else ((32, 116) if pipeline and world_size == 1 else (0, 0))
+        self.sm_split = tuple(split) if split is not None else (
+            self._auto_sm_split(cfg) if pipeline and world_size == 1 else (0, 0))
         self.encoder_in_gap = bool(getattr(cfg, "ENCODER_IN_GAP", False))
         self.encoder_after_corr = bool(getattr(cfg, "ENCODER_AFTER_CORR", True))
         self._last_ugraph = None
@@ -395,6 +396,27 @@ class Ramp_vo:
         poses = lietorch.stack(poses, dim=0)
         poses = poses.inv().data.cpu().numpy()
         return poses, np.array(self.tlist, dtype=float)
+
+    @staticmethod
+    def _auto_sm_split(cfg, n_sms=148):
+        """(encoder SMs, update SMs) for the pipelined frame: the split that balances the two streams in a two-line
+        cost model fitted to the B200 measurements of profiles/r02_frame_scheduling.md — the encoder is latency-bound
+        (time ~ rounds of its 150-tile layers: flat down to 74 SMs, then ~ 1 / SMs), the update is half tensor-bound,
+        half HBM-bound and scales with the steady-state edge count of the preset.  default.yaml -> (28, 120),
+        fast.yaml -> (60, 88), precise.yaml -> no split; cfg.SM_SPLIT overrides it."""
+        edges = 0.86 * cfg.PATCHES_PER_FRAME * (2 * cfg.PATCH_LIFETIME - 1) * cfg.REMOVAL_WINDOW
+        t_u = 1.14 * edges / 45312.0
+        if t_u > 4.0:       # precise.yaml-sized graphs: the encoder is noise next to the update — measured 73.5 vs 71.2
+            return 0, 0     # frames/s without / with a split
+        best = None
+        for se in range(8, 76, 4):
+            t_enc = 0.58 * (0.25 + 0.75 * max(1.0, 74.0 / se))
+            t_upd = t_u * (0.45 + 0.55 * n_sms / (n_sms - se)) + 0.25
+            cost = max(t_enc, t_upd)
+            if best is None or cost < best[0] - 1e-9:
+                best = (cost, se)
+        se = best[1] + 4       # a starved encoder stalls the whole frame, a starved update only loses its share
+        return se, n_sms - se
 
     # ------------------------------------------------------------------ pose prediction (Ramp_vo.py:412-545)
     def _virtual_frame(self, last_keyframe_number):
