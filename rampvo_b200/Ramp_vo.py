@@ -267,7 +267,7 @@ class Ramp_vo:
         #   ENCODER_IN_GAP      (alternative) the encoder of frame t+1 starts when update t has finished.
         split = getattr(cfg, "SM_SPLIT", None)
         self.sm_split = tuple(split) if split is not None else (
-            self._auto_sm_split(cfg) if pipeline and world_size == 1 else (0, 0))
+            self._auto_sm_split(cfg, tiles=-(-(ht // 4) * (wd // 4) // 128)) if pipeline and world_size == 1 else (0, 0))
         self.encoder_in_gap = bool(getattr(cfg, "ENCODER_IN_GAP", False))
         self.encoder_after_corr = bool(getattr(cfg, "ENCODER_AFTER_CORR", True))
         self._last_ugraph = None
@@ -398,12 +398,12 @@ class Ramp_vo:
         return poses, np.array(self.tlist, dtype=float)
 
     @staticmethod
-    def _auto_sm_split(cfg, n_sms=148):
+    def _auto_sm_split(cfg, tiles=150, n_sms=148):
         """(encoder SMs, update SMs) for the pipelined frame: the split that balances the two streams in a two-line
         cost model fitted to the B200 measurements of profiles/r02_frame_scheduling.md — the encoder is latency-bound
         (time ~ rounds of its 150-tile layers: flat down to 74 SMs, then ~ 1 / SMs), the update is half tensor-bound,
-        half HBM-bound and scales with the steady-state edge count of the preset.  default.yaml -> (28, 120),
-        fast.yaml -> (60, 88), precise.yaml -> no split; cfg.SM_SPLIT overrides it."""
+        half HBM-bound and scales with the steady-state edge count of the preset.  default.yaml -> (30, 118),
+        fast.yaml -> (50, 98), precise.yaml -> no split; cfg.SM_SPLIT overrides it."""
         edges = 0.86 * cfg.PATCHES_PER_FRAME * (2 * cfg.PATCH_LIFETIME - 1) * cfg.REMOVAL_WINDOW
         t_u = 1.14 * edges / 45312.0
         if t_u > 4.0:       # precise.yaml-sized graphs: the encoder is noise next to the update — measured 73.5 vs 71.2
@@ -416,6 +416,10 @@ class Ramp_vo:
             if best is None or cost < best[0] - 1e-9:
                 best = (cost, se)
         se = best[1] + 4       # a starved encoder stalls the whole frame, a starved update only loses its share
+        # wave alignment: most encoder layers run at 1/4 resolution in tiles of 128 pixels, one tile per CTA per round
+        # (150 tiles at 480x640): 30 SMs do them in 5 rounds, 28 SMs need 6 (measured 572 vs 564 frames/s)
+        up = -(-tiles // max(tiles // se, 1))
+        se = up if up <= se + 8 else -(-tiles // -(-tiles // se))
         return se, n_sms - se
 
     # ------------------------------------------------------------------ pose prediction (Ramp_vo.py:412-545)
