@@ -413,6 +413,10 @@ int rvo_edges_step(const int64_t* ii, const int64_t* jj, const int64_t* kk, int 
                    int64_t* ii_out, int64_t* jj_out, int64_t* kk_out, int E_new, int32_t* src_row, float* status,
                    const float* net_in, int C, float* net_out, void* stream);
 
+/* the hidden-state half of rvo_edges_step alone (net_out[e] = net_in[src_row[e]], 0 for src_row[e] < 0), so that it
+ * can run on a side stream beside the head of the next update */
+int rvo_net_rows(const float* net_in, const int32_t* src_row, int E, int C, float* net_out, void* stream);
+
 /* ---- fused Linear chains of the update operator (csrc/up_chain.cu) ------------------------------- */
 
 /* Update.forward (ramp/net.py:69-90) is five row-local stretches separated by four cross-row exchanges (the two

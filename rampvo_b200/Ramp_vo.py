@@ -161,6 +161,7 @@ class _UpdateGraph:
         self.kk = torch.zeros(E, dtype=torch.long, device=dev)
         self.t0 = torch.zeros(1, dtype=torch.int32, device=dev)
         self.n_free = n_free
+        vo._net_join()                           # the warm-up / capture below read vo.net on this stream
         self.side = torch.cuda.Stream(device=dev)
         self.mid_event = torch.cuda.Event(external=True)
         self.net_in = vo.net                     # view of the current ping-pong buffer
@@ -198,7 +199,7 @@ class _UpdateGraph:
 
     def _load(self, t0):
         vo = self.vo
-        self.ii.copy_(vo.ii); self.jj.copy_(vo.jj); self.kk.copy_(vo.kk)
+        copy_segments([(vo.ii, self.ii), (vo.jj, self.jj), (vo.kk, self.kk)])      # one launch
         self.t0.fill_(t0)
 
     def _body(self):
@@ -212,6 +213,9 @@ class _UpdateGraph:
         self.plans = plans
         def after_corr():
             cur.wait_stream(side)
+            # the hidden-state rows of the new edge list (rvo_net_rows on vo._net_stream) are only needed from here
+            # on: an external event-wait node lets reproject + corr start before that gather has finished
+            cur.wait_event(vo._net_ready)
             # an EXTERNAL event node: the encoder stream of the next frame can wait for "reproject + corr of this
             # update are done" (Ramp_vo.encoder_after_corr) — the latency-critical head of the update then has the
             # GPU to itself
@@ -221,6 +225,10 @@ class _UpdateGraph:
                                          with_ba=vo.world_size == 1)
 
     def run(self, t0):
+        vo = self.vo
+        if not vo._net_ready_fresh:          # hidden state produced on this stream (no side-stream gather pending)
+            vo._net_ready.record(torch.cuda.current_stream(vo.device))
+        vo._net_ready_fresh = False
         self._load(t0)
         self.graph.replay()
         self.vo.graph_kernel_launches += self.n_kernels
@@ -273,6 +281,9 @@ class Ramp_vo:
         self._last_ugraph = None
         self.fast_edges = bool(getattr(cfg, "FAST_EDGES", True))   # fused patch-graph step (rvo_edges_step)
         self._pending_lim = None
+        self._net_stream = None
+        self._net_ready = torch.cuda.Event(external=True) if self.device.type == "cuda" else None
+        self._net_ready_fresh = False
         self._edge_status = None
         self._edge_src = None
         self._min_src = 0
@@ -573,6 +584,7 @@ class Ramp_vo:
     def append_factors(self, ii, jj, pairs=None):
         """add factors to the graph (Ramp_vo.py:194-201); new edges start with a zero hidden state.
         pairs: {(i, j): count} of the new edges when the caller knows it (no device read needed)"""
+        self._net_join()
         pc = self._pair_counts()
         if pairs is None:
             key = (torch.div(ii, self.M, rounding_mode="floor") * (self.N + 1) + jj).cpu().numpy()
@@ -594,6 +606,7 @@ class Ramp_vo:
         """remove factors from the graph (Ramp_vo.py:203-208).  m: boolean device mask (reference
         signature).  pair_pred(i, j) -> bool: the same predicate on (source, target) frame pairs; with
         it the number of surviving edges is known on the host and the compaction does not synchronise"""
+        self._net_join()
         pc = self._pair_counts()
         if pair_pred is None:
             n_keep = int((~m).sum().item())
@@ -613,6 +626,12 @@ class Ramp_vo:
         torch.index_select(self.net, 1, keep, out=out)
         self._net_swap(keep.numel())
         self._plans = None
+
+    def _net_join(self):
+        """make the current stream wait for a hidden-state gather still running on the side stream (_edges_step)"""
+        if self._net_ready_fresh:
+            torch.cuda.current_stream(self.device).wait_event(self._net_ready)
+            self._net_ready_fresh = False
 
     def _edges_step(self, lim):
         """remove_factors(ii < lim) + append_factors(forward) + append_factors(backward) of the frame that was just
@@ -639,11 +658,22 @@ class Ramp_vo:
             self._edge_src = torch.empty(max(E1 * 5 // 4, 4096), dtype=torch.int32, device=dev)
         ii, jj, kk = (torch.empty(E1, dtype=torch.long, device=dev) for _ in range(3))
         out = self._net_other(E1)
+        cur = torch.cuda.current_stream(dev)
+        if self._net_stream is None:
+            self._net_stream = torch.cuda.Stream(device=dev)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().rvo_edges_step(
                 _lib.ptr(self.ii), _lib.ptr(self.jj), _lib.ptr(self.kk), E0, int(lim), n, M, r, _lib.ptr(ii), _lib.ptr(jj),
-                _lib.ptr(kk), E1, _lib.ptr(self._edge_src), _lib.ptr(self._edge_status), _lib.ptr(self.net), self.DIM, _lib.ptr(out),
+                _lib.ptr(kk), E1, _lib.ptr(self._edge_src), _lib.ptr(self._edge_status), None, self.DIM, None,
                 _lib.stream_ptr(dev)), "rvo_edges_step")
+            # the rows of the hidden state follow on a side stream: the update graph waits for them (external event)
+            # only before its first use, after reproject + corr
+            ns = self._net_stream
+            ns.wait_stream(cur)
+            _lib.check(_lib.lib().rvo_net_rows(_lib.ptr(self.net), _lib.ptr(self._edge_src), E1, self.DIM, _lib.ptr(out),
+                                               ctypes.c_void_p(ns.cuda_stream)), "rvo_net_rows")
+            self._net_ready.record(ns)
+            self._net_ready_fresh = True
         self.ii, self.jj, self.kk = ii, jj, kk
         self._net_swap(E1)
         self._plans = None
@@ -842,6 +872,7 @@ class Ramp_vo:
                 and (repeat or (key + (self._net_bufs[0].data_ptr(),)) in self._ugraphs)):
             self._update_graphed(E, t0, self.n)
         else:
+            self._net_join()
             plans = self._graph_plans()
             other = self._net_other(E)
             new_net, weight = self._update_body(self.ii, self.jj, self.kk, self.net, other, plans, t0, self.n)
@@ -971,6 +1002,10 @@ class Ramp_vo:
         # pipeline mode: the previous frame's keyframe step, overlapped with the encoder graph.  In the steady state
         # the removal of the edges that left the window is fused with this frame's appends (rvo_edges_step)
         fast = (graphable and self.fast_edges and self.is_initialized and self.world_size == 1 and self.pipeline)
+        # host work that does not depend on the keyframe decision goes BEFORE the wait for it
+        intr = torch.as_tensor(intrinsics, dtype=torch.float32).reshape(-1).tolist() \
+            if not (torch.is_tensor(intrinsics) and intrinsics.is_cuda) else intrinsics.float().cpu().tolist()
+        intr4 = (ctypes.c_float * 4)(*[v / self.RES for v in intr])
         self.sync(defer_removal=fast)
         slot = self.n % self.mem
         gslot_store = self._gmap_store[slot * M:(slot + 1) * M]
@@ -996,9 +1031,6 @@ class Ramp_vo:
         # state writes of the new frame (Ramp_vo.py:345-372) in one launch: tstamps / intrinsics / index rows,
         # colours, depth initialisation (uniform draw, or the median of the last 3 frames) and patches_[n]
         self.tlist.append(tstamp)
-        intr = torch.as_tensor(intrinsics, dtype=torch.float32).reshape(-1).tolist() \
-            if not (torch.is_tensor(intrinsics) and intrinsics.is_cuda) else intrinsics.float().cpu().tolist()
-        intr4 = (ctypes.c_float * 4)(*[v / self.RES for v in intr])
         rnd = None if self.is_initialized else torch.rand_like(patches[:, :, 2, 0, 0, None, None]).contiguous()
         pn = patches if patches.dtype == torch.float32 and patches.is_contiguous() else patches.float().contiguous()
         cl = clr if clr.dtype == torch.float32 and clr.is_contiguous() else clr.float().contiguous()

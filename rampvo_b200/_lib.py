@@ -60,6 +60,7 @@ _SIGNATURES = {
     "rvo_device_cc": (c_int, []),
     "rvo_launch_count": (ctypes.c_uint64, []),
     "rvo_set_sm_budget": (c_int, [c_int]),
+    "rvo_net_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "rvo_edges_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "rvo_get_sm_budget": (c_int, []),

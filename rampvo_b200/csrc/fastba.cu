@@ -515,6 +515,7 @@ __device__ __forceinline__ void retr_se3(const float* xi, float* t, float* q) {
 // Right-looking Cholesky with a 2-D thread mapping (x: column, y: row — no integer division in the
 // trailing update); row n comes out as z = L^-1 y, then one warp solves L^T dX = z
 // (ba_cuda.cu:558-562) with warp-level synchronisation only.
+template <int SETS>
 __global__ void __launch_bounds__(1024)
 ba_solve_kernel(const float* __restrict__ Sy, int N, int t0_arg, const int32_t* __restrict__ t0_dev,
                 float* __restrict__ poses, float* __restrict__ dX_g, float* __restrict__ A_g) {
@@ -546,21 +547,73 @@ ba_solve_kernel(const float* __restrict__ Sy, int N, int t0_arg, const int32_t* 
   // order, so the factor is bit-identical to the right-looking algorithm.
   constexpr int PB = 6;
   for (int j0 = 0; j0 < n; j0 += PB) {
-    if (ty == 0) {
+    if constexpr (SETS == 0) {
+      // large windows (6N + 1 > 64 rows): the panel stays in shared memory, one warp, warp-level synchronisation only
+      // (the register panel below needs 6 x ceil(rows / 32) live values per lane and measured slower at 181 rows)
+      if (ty == 0) {
 #pragma unroll 1
-      for (int jj = 0; jj < PB; jj++) {
-        const int j = j0 + jj;
-        const float d = sqrtf(A[(size_t)j * la + j]);
-        const float inv = 1.0f / d;
-        for (int i = j + 1 + tx; i <= n; i += 32) A[(size_t)i * la + j] *= inv;
-        if (tx == 0) diag[j] = inv;
-        __syncwarp();
-        for (int i = j + 1 + tx; i <= n; i += 32) {
-          const float lij = A[(size_t)i * la + j];
-          const int kmax = min(min(i, n - 1), j0 + PB - 1);
-          for (int k = j + 1; k <= kmax; k++) A[(size_t)i * la + k] -= lij * A[(size_t)k * la + j];
+        for (int jj = 0; jj < PB; jj++) {
+          const int j = j0 + jj;
+          const float d = sqrtf(A[(size_t)j * la + j]);
+          const float inv = 1.0f / d;
+          for (int i = j + 1 + tx; i <= n; i += 32) A[(size_t)i * la + j] *= inv;
+          if (tx == 0) diag[j] = inv;
+          __syncwarp();
+          for (int i = j + 1 + tx; i <= n; i += 32) {
+            const float lij = A[(size_t)i * la + j];
+            const int kmax = min(min(i, n - 1), j0 + PB - 1);
+            for (int k = j + 1; k <= kmax; k++) A[(size_t)i * la + k] -= lij * A[(size_t)k * la + j];
+          }
+          __syncwarp();
         }
-        __syncwarp();
+      }
+    } else {
+    if (ty == 0) {
+        // the panel lives in REGISTERS: lane l owns rows l, l + 32, ... (SETS of them cover rows 0..n), six panel
+        // columns each; pivots and the multipliers L[k][j] travel by warp shuffle.  (Through shared memory every
+        // in-panel update was a dependent load -> FMA -> store round trip: ~900 cycles per column, 27 of the 46 us.)
+        float a[SETS > 0 ? SETS : 1][PB];
+  #pragma unroll
+        for (int s = 0; s < SETS; s++) {
+          const int r = tx + 32 * s;
+  #pragma unroll
+          for (int c = 0; c < PB; c++) a[s][c] = (r >= j0 && r <= n) ? A[(size_t)r * la + j0 + c] : 0.f;
+        }
+  #pragma unroll
+        for (int jj = 0; jj < PB; jj++) {
+          const int j = j0 + jj;                       // j < n: n is a multiple of 6
+          float v = 0.f;
+  #pragma unroll
+          for (int s = 0; s < SETS; s++)
+            if (s == (j >> 5)) v = a[s][jj];
+          const float d = sqrtf(__shfl_sync(0xffffffffu, v, j & 31));
+          const float inv = 1.0f / d;
+  #pragma unroll
+          for (int s = 0; s < SETS; s++)
+            if (tx + 32 * s > j) a[s][jj] *= inv;
+          if (tx == 0) diag[j] = inv;
+  #pragma unroll
+          for (int kk = jj + 1; kk < PB; kk++) {
+            const int k = j0 + kk;
+            float lk = 0.f;
+  #pragma unroll
+            for (int s = 0; s < SETS; s++)
+              if (s == (k >> 5)) lk = a[s][jj];
+            lk = __shfl_sync(0xffffffffu, lk, k & 31);
+  #pragma unroll
+            for (int s = 0; s < SETS; s++)
+              if (tx + 32 * s >= k) a[s][kk] -= a[s][jj] * lk;
+          }
+        }
+  #pragma unroll
+        for (int s = 0; s < SETS; s++) {
+          const int r = tx + 32 * s;
+          if (r >= j0 && r <= n) {
+  #pragma unroll
+            for (int c = 0; c < PB; c++)
+              if (r >= j0 + c) A[(size_t)r * la + j0 + c] = a[s][c];
+          }
+        }
       }
     }
     __syncthreads();
@@ -707,19 +760,35 @@ static int ba_assemble(const BaWs& w, const float* poses, const float* patches,
   return RVO_OK;
 }
 
+// SETS = 2: the 6-column panel of the Cholesky factorisation is register-resident (rows spread over the lanes of one
+// warp, two per lane: windows of up to 10 poses); SETS = 0: the panel stays in shared memory
+static int launch_ba_solve(dim3 threads, size_t smem, cudaStream_t st, const float* Sy, int N, int t0,
+                           const int32_t* t0_dev, float* poses, float* dX, float* A_g) {
+  const int sets = (6 * N + 1 + 31) / 32;
+#define RVO_SOLVE(S)                                                                                         \
+  do {                                                                                                       \
+    RVO_CUDA(cudaFuncSetAttribute(ba_solve_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                  (int)kSmemMax));                                                           \
+    ba_solve_kernel<S><<<1, threads, smem, st>>>(Sy, N, t0, t0_dev, poses, dX, A_g);                         \
+  } while (0)
+  if (sets <= 2) RVO_SOLVE(2);          // up to 10 poses (default.yaml): register-resident panel
+  else RVO_SOLVE(0);                    // shared-memory panel
+#undef RVO_SOLVE
+  RVO_LAUNCH_CHECK("ba_solve_kernel");
+  return RVO_OK;
+}
+
 static int ba_solve(const BaWs& w, float* poses, float* patches, const float* Sy, int64_t cap, int P,
                     int t0, int t1, cudaStream_t st, const int32_t* t0_dev = nullptr) {
   const int N = t1 - t0, n6 = 6 * N;
   if (N > 0) {
     const bool in_smem = solve_smem_bytes(n6) <= kSmemMax;
     const size_t smem = in_smem ? solve_smem_bytes(n6) : 2 * (size_t)n6 * sizeof(float);
-    RVO_CUDA(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)kSmemMax));
-    // (a fully unrolled single-warp register Cholesky was tried for 6N <= 64: 60 us vs 45 us here —
-    // its ~160 KB of straight-line code runs once per launch and is bound by instruction fetch)
+    // (a fully unrolled single-warp register Cholesky of the WHOLE matrix was tried for 6N <= 64: 60 us vs 45 us —
+    // ~160 KB of straight-line code bound by instruction fetch; only the 6-column panel is register-resident now)
     const dim3 threads(32, n6 <= 24 ? 8 : 32);
-    ba_solve_kernel<<<1, threads, smem, st>>>(Sy, N, t0, t0_dev, poses, w.dX, in_smem ? nullptr : w.A);
-    RVO_LAUNCH_CHECK("ba_solve_kernel");
+    int rc = launch_ba_solve(threads, smem, st, Sy, N, t0, t0_dev, poses, w.dX, in_smem ? nullptr : w.A);
+    if (rc != RVO_OK) return rc;
   }
   int64_t warps = cap;
   int grid = (int)((warps * 32 + 255) / 256);
@@ -911,13 +980,9 @@ extern "C" int rvo_ba_solve_poses(float* poses, const float* Sy, int t0, int t1,
   RVO_CHECK_ARG((int64_t)w.total <= ws_bytes, "rvo_ba_solve_poses: workspace too small");
   const bool in_smem = solve_smem_bytes(n6) <= kSmemMax;
   const size_t smem = in_smem ? solve_smem_bytes(n6) : 2 * (size_t)n6 * sizeof(float);
-  RVO_CUDA(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)kSmemMax));
   const dim3 threads(32, n6 <= 24 ? 8 : 32);
-  ba_solve_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(Sy, N, t0, nullptr, poses, w.dX,
-                                                              in_smem ? nullptr : w.A);
-  RVO_LAUNCH_CHECK("ba_solve_kernel");
-  return RVO_OK;
+  return launch_ba_solve(threads, smem, (cudaStream_t)stream, Sy, N, t0, nullptr, poses, w.dX,
+                         in_smem ? nullptr : w.A);
 }
 
 extern "C" int rvo_ba_forward(float* poses, float* patches, const float* intrinsics,

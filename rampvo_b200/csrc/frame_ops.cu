@@ -593,6 +593,17 @@ net_rows_kernel(const float* __restrict__ net_in, const int32_t* __restrict__ sr
 
 }  // namespace rvo
 
+extern "C" int rvo_net_rows(const float* net_in, const int32_t* src_row, int E, int C, float* net_out, void* stream) {
+  RVO_CHECK_ARG(E >= 0 && C % 4 == 0, "rvo_net_rows: bad sizes");
+  if (E == 0) return RVO_OK;
+  RVO_CHECK_ARG(net_in && src_row && net_out && net_out != net_in, "rvo_net_rows: null / aliased pointer");
+  int grid = rvo::cdiv((int64_t)E * 32, 256);
+  if (grid > rvo::sm_budget() * 8) grid = rvo::sm_budget() * 8;
+  rvo::net_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(net_in, src_row, E, C / 4, net_out);
+  RVO_LAUNCH_CHECK("net_rows_kernel");
+  return RVO_OK;
+}
+
 extern "C" int rvo_edges_step(const int64_t* ii, const int64_t* jj, const int64_t* kk, int E0, int lim, int n, int M,
                               int r, int64_t* ii_out, int64_t* jj_out, int64_t* kk_out, int E_new,
                               int32_t* src_row, float* status, const float* net_in, int C, float* net_out,
