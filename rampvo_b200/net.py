@@ -116,15 +116,34 @@ class GraphPlans:
         self.jx = torch.empty(E, dtype=torch.int64, device=dev)
         if E == 0:
             return
-        key_ij = ii * 12345 + jj
         st = _lib.stream_ptr(dev)
         with torch.cuda.device(dev):
             _lib.check(L.rvo_graph_plan(_lib.ptr(kk), _lib.ptr(jj), E, kmax, jmax, _lib.ptr(self.plan_k),
                                         nb, st), "rvo_graph_plan")
             _lib.check(L.rvo_plan_neighbors(_lib.ptr(self.plan_k), E, _lib.ptr(self.ix),
                                             _lib.ptr(self.jx), st), "rvo_plan_neighbors")
-            _lib.check(L.rvo_graph_plan(_lib.ptr(key_ij), _lib.ptr(jj), E, (jmax * 12345 + jmax) if jmax else 0,
-                                        jmax, _lib.ptr(self.plan_ij), nb, st), "rvo_graph_plan")
+            if jmax:
+                # agg_ij groups by ii * 12345 + jj (net.py:85); any key that is injective on (ii, jj) and keeps
+                # their lexicographic order gives the same groups in the same order: ii * 2^b + jj needs 2 radix
+                # passes where the reference's multiplier needs 4 (and the second sort key is redundant here)
+                J = 1 << max(int(jmax - 1).bit_length(), 1)
+                key_ij = ii * J + jj
+                _lib.check(L.rvo_graph_plan(_lib.ptr(key_ij), _lib.ptr(self._zeros(E, dev)), E, jmax * J, 1,
+                                            _lib.ptr(self.plan_ij), nb, st), "rvo_graph_plan")
+            else:
+                key_ij = ii * 12345 + jj
+                _lib.check(L.rvo_graph_plan(_lib.ptr(key_ij), _lib.ptr(jj), E, 0, 0, _lib.ptr(self.plan_ij), nb, st),
+                           "rvo_graph_plan")
+
+    _zero_cache = {}
+
+    @classmethod
+    def _zeros(cls, E, dev):
+        """an all-zero int64 secondary key of at least E entries (cached per device: never written)"""
+        z = cls._zero_cache.get(str(dev))
+        if z is None or z.numel() < E:
+            z = cls._zero_cache[str(dev)] = torch.zeros(max(E, 1 << 16), dtype=torch.int64, device=dev)
+        return z
 
     def edge_groups(self):
         """device pointers (ctypes) to the group id of every edge in the kk plan and in the (ii, jj) plan"""
