@@ -54,6 +54,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag, self.armed = index, [], False, False
+        self.streaming = threading.Event()        # set once nvidia-smi has delivered its first sample
 
     def run(self):
         # one long-running nvidia-smi in loop mode (a fresh process per sample takes ~80 ms)
@@ -68,6 +69,7 @@ class ClockSampler(threading.Thread):
                 line = proc.stdout.readline()
                 if not line:
                     break
+                self.streaming.set()
                 if self.armed:
                     self.rows.append([x.strip() for x in line.split(",")])
         finally:
@@ -84,7 +86,7 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
-def build_vo(device, seed=1234, config="default", world_size=1, rank=0):
+def build_vo(device, seed=1234, config="default", world_size=1, rank=0, keyframe_thresh=0.0):
     import torch
     from rampvo_b200.Ramp_vo import Ramp_vo
     from rampvo_b200.config import preset
@@ -92,7 +94,7 @@ def build_vo(device, seed=1234, config="default", world_size=1, rank=0):
     torch.manual_seed(seed)                      # evaluate.py:40 seeds everything with 1234
     train_cfg = {"event_bias": True, "input_mode": "MultiScale", "num_event_bins": 5}
     cfg = preset(config)
-    cfg.KEYFRAME_THRESH = 0.0                    # never drop a keyframe: the no-drop upper-bound graph
+    cfg.KEYFRAME_THRESH = keyframe_thresh        # 0: never drop a keyframe — the no-drop upper-bound graph
     if os.environ.get("RVO_ENC_AFTER_CORR"):
         cfg.ENCODER_AFTER_CORR = bool(int(os.environ["RVO_ENC_AFTER_CORR"]))
     if os.environ.get("RVO_ENC_IN_GAP"):
@@ -149,28 +151,51 @@ def run_ours(args):
     state = {}
 
     def timed(step_fn, first, profile=False):
+        if profile and args.cuda_profiler_range:
+            # `ncu --profile-from-start off ... bench.py --cuda-profiler-range` captures from here (warm-up + timed
+            # frames).  Opt-in: cudaProfilerStart slows the launch path of the following ~100 ms even with no profiler
+            # attached — unconditional, it made the device-resident number depend on K (230 / 480 / 590 frames/s at
+            # K = 20 / 50 / 200 while tools/frame_times.py shows a flat 1.56 ms per frame from the second frame on)
+            torch.cuda.profiler.start()
         for t in range(first, first + W):
             step_fn(t)
+        # part of the warm-up: finish the deferred keyframe step once through the public (tensor-op) path.  The timed
+        # region ends with the same vo.sync(); in the steady state every other removal goes through rvo_edges_step,
+        # so without this the torch kernels of that path were loaded (CUDA lazy module loading, ~50 ms) inside the
+        # first timed region — the device-resident number read 230 / 480 / 590 frames/s at K = 20 / 50 / 200
+        state["vo"].sync()
         sampler = ClockSampler(local)
         sampler.start()
-        time.sleep(0.3)                      # let nvidia-smi start streaming before the timed region
+        # let nvidia-smi start streaming BEFORE the timed region: its first start on a fresh box initialises NVML for
+        # ~0.5-1 s and contends with the CUDA launch path meanwhile (the first timed run used to read 370-590 frames/s
+        # depending on K while tools/frame_times.py shows a flat 1.56 ms per frame from the second frame on)
+        sampler.streaming.wait(timeout=10.0)
+        time.sleep(0.1)
         barrier()
         sampler.armed = True
         l0 = L.rvo_launch_count() + state["vo"].graph_kernel_launches
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if profile:
-            torch.cuda.profiler.start()      # `ncu --profile-from-start off` captures only this region
         a.record()
+        trace = [] if os.environ.get("RVO_BENCH_TRACE") else None
         for t in range(first + W, first + W + K):
             step_fn(t)
+            if trace is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                trace.append((e, time.perf_counter()))
         state["vo"].sync()                   # the last frame's deferred keyframe step belongs to the timed region
         b.record()
         barrier()
-        if profile:
+        if profile and args.cuda_profiler_range:
             torch.cuda.profiler.stop()
         sampler.armed = False
         sampler.stop_flag = True
         ms = a.elapsed_time(b)
+        if trace:
+            sys.stderr.write("per-frame GPU ms: " + " ".join("%.2f" % (a if i == 0 else trace[i - 1][0]).elapsed_time(trace[i][0])
+                                                            for i in range(len(trace))) + "\n")
+            sys.stderr.write("per-frame host ms: " + " ".join("%.2f" % ((trace[i][1] - trace[i - 1][1]) * 1e3)
+                                                             for i in range(1, len(trace))) + "\n")
         launches = L.rvo_launch_count() + state["vo"].graph_kernel_launches - l0
         sampler.join(timeout=2)
         if world > 1:
@@ -304,6 +329,11 @@ def run_ours(args):
                                "note": "per rank, since the start of the stream (setup + warm-up + timed frames)"}
     if rank == 0 and world == 1 and stages_ours is not None:
         line["stages"] = stages_ours
+    if rank == 0 and world == 1 and args.config == "default" and not args.no_keyframe_path:
+        try:
+            line["keyframe_path"] = keyframe_path_block(frames, intr, dev, min(K, 100))
+        except Exception as e:
+            line["keyframe_path"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     if rank == 0 and world == 1 and not args.no_ref_gpu and args.config == "default":
         try:
             line["ref_gpu"] = ref_gpu_block(state["sd"], frames, intr, min(K, 20), 3, dev)
@@ -315,6 +345,34 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def keyframe_path_block(frames, intr, dev, K):
+    """The same stream with the preset's REAL keyframe threshold (default.yaml: 15): keyframes are dropped, the
+    edge list shrinks and grows, update graphs of several sizes are captured and replayed — the path the pinned
+    headline workload (KEYFRAME_THRESH = 0) never takes.  Context, not the headline: with random weights the flow
+    estimates that drive the drop decision are arbitrary."""
+    import torch
+    with torch.no_grad():
+        vo = build_vo(dev, keyframe_thresh=15.0)
+        n0 = min(SETUP_FRAMES, len(frames) - K)
+        for t in range(n0):
+            vo(t, frames[t], intr)
+        vo.sync()
+        torch.cuda.synchronize()
+        kept0, c0 = vo.n, vo.counter
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for t in range(n0, n0 + K):
+            vo(t, frames[t], intr)
+        vo.sync()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        drops = (vo.counter - c0) - (vo.n - kept0)
+    return {"value": K / (ms * 1e-3), "unit": UNIT, "frames": K, "keyframes_dropped": int(drops),
+            "edges_at_end": int(vo.ii.numel()), "update_graphs_cached": len(vo._ugraphs), "keyframe_thresh": 15.0,
+            "note": "device-resident inputs; includes the CUDA-graph captures of edge counts seen for the first time"}
 
 
 def cpu_reference(steps, warmup, budget_s=150.0):
@@ -493,6 +551,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--cuda-profiler-range", action="store_true",
+                    help="bracket warm-up + timed frames with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
+    ap.add_argument("--no-keyframe-path", action="store_true", help="skip the real-keyframe-threshold context block")
     ap.add_argument("--no-replicas", action="store_true", help="N > 1 sharded mode: skip the replica-throughput leg")
     ap.add_argument("--config", default="default", choices=sorted(WORKLOADS),
                     help="VO preset: default.yaml (the metric's configuration), precise.yaml, fast.yaml")
