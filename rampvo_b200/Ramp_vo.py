@@ -286,6 +286,8 @@ class Ramp_vo:
         self._net_ready_fresh = False
         self._edge_status = None
         self._edge_src = None
+        self._edge_tiles = None
+        self._edge_epoch = 0
         self._min_src = 0
         self._frame_done = None
         self.last_weight = None
@@ -656,6 +658,10 @@ class Ramp_vo:
             self._edge_status = torch.zeros(1, dtype=torch.float32, device=dev)
         if self._edge_src is None or self._edge_src.numel() < E1:
             self._edge_src = torch.empty(max(E1 * 5 // 4, 4096), dtype=torch.int32, device=dev)
+        nt = int(_lib.lib().rvo_edges_step_tiles(E0))
+        if self._edge_tiles is None or self._edge_tiles.numel() < nt:
+            self._edge_tiles = torch.zeros(max(2 * nt, 256), dtype=torch.int64, device=dev)
+        self._edge_epoch = (self._edge_epoch % 0x7fffffff) + 1
         ii, jj, kk = (torch.empty(E1, dtype=torch.long, device=dev) for _ in range(3))
         out = self._net_other(E1)
         cur = torch.cuda.current_stream(dev)
@@ -664,8 +670,8 @@ class Ramp_vo:
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().rvo_edges_step(
                 _lib.ptr(self.ii), _lib.ptr(self.jj), _lib.ptr(self.kk), E0, int(lim), n, M, r, _lib.ptr(ii), _lib.ptr(jj),
-                _lib.ptr(kk), E1, _lib.ptr(self._edge_src), _lib.ptr(self._edge_status), None, self.DIM, None,
-                _lib.stream_ptr(dev)), "rvo_edges_step")
+                _lib.ptr(kk), E1, _lib.ptr(self._edge_src), _lib.ptr(self._edge_status), _lib.ptr(self._edge_tiles),
+                self._edge_epoch, None, self.DIM, None, _lib.stream_ptr(dev)), "rvo_edges_step")
             # the rows of the hidden state follow on a side stream: the update graph waits for them (external event)
             # only before its first use, after reproject + corr
             ns = self._net_stream

@@ -61,8 +61,10 @@ _SIGNATURES = {
     "rvo_launch_count": (ctypes.c_uint64, []),
     "rvo_set_sm_budget": (c_int, [c_int]),
     "rvo_net_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "rvo_edges_step_tiles": (c_int64, [c_int]),
     "rvo_edges_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-                               c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+                               c_void_p, c_int, c_void_p, c_void_p, c_void_p, ctypes.c_uint32, c_void_p, c_int, c_void_p,
+                               c_void_p]),
     "rvo_get_sm_budget": (c_int, []),
     "rvo_patchify_forward": (c_int, [POINTER(FMap), _P, c_int, c_int, _P, _P]),
     "rvo_patchify_bilinear": (c_int, [POINTER(FMap), _P, c_int, c_int, _P, c_int, _I64, _I64, _I64,

@@ -502,62 +502,77 @@ namespace rvo {
 
 constexpr int kEsThreads = 1024;
 
-constexpr int kEsTiles = 64;        // tiles of kEsThreads edges per round: one keep bit per tile in a 64-bit register
-
+// One CTA per tile of kEsThreads edges.  The ranks of the surviving edges need the number of survivors in all earlier
+// tiles: every CTA publishes its count as (epoch << 32 | count) in tile_state[] right after counting and sums the
+// words of its predecessors (spinning until they carry this launch's epoch — predecessors have lower block indices,
+// so they are scheduled no later than their waiters).  The last CTA, which knows the total, appends the new edges.
+// (A single CTA doing all of it is bound by what one SM can move: 42 us for the 2.9 MB of a 47 712-edge list.)
 __global__ void __launch_bounds__(kEsThreads)
 edges_step_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, const int64_t* __restrict__ kk,
                   int E0, int lim, int n, int M, int r, int64_t* __restrict__ ii_o, int64_t* __restrict__ jj_o,
                   int64_t* __restrict__ kk_o, int32_t* __restrict__ src_row, int E_expected,
-                  float* __restrict__ status) {
-  // wpre[j][w]: kept edges of tile j in the warps before w (after the scan); tbase[j]: kept edges before tile j
-  __shared__ int wpre[kEsTiles][kEsThreads / 32];
-  __shared__ int tbase[kEsTiles + 1];
+                  float* __restrict__ status, unsigned long long* __restrict__ tile_state, unsigned int epoch) {
+  __shared__ int wsum[kEsThreads / 32];
+  __shared__ int base_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int kept = 0;
-  for (int e0 = 0; e0 < E0; e0 += kEsTiles * kEsThreads) {        // rounds of 65 536 edges
-    const int T = min(kEsTiles, (E0 - e0 + kEsThreads - 1) / kEsThreads);
-    // pass 1: coalesced, independent loads; one keep bit per tile
-    unsigned long long mask = 0ull;
-#pragma unroll 8
-    for (int j = 0; j < T; j++) {
-      const int idx = e0 + j * kEsThreads + tid;
-      if (idx < E0 && ii[idx] >= lim) mask |= 1ull << j;
-    }
-    for (int j = 0; j < T; j++) {
-      const unsigned bal = __ballot_sync(0xffffffffu, (mask >> j) & 1ull);
-      if (lane == 0) wpre[j][warp] = __popc(bal);
-    }
-    __syncthreads();
-    for (int j = warp; j < T; j += kEsThreads / 32) {             // exclusive scan over the warps of tile j
-      const int c = wpre[j][lane];
-      int incl = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      wpre[j][lane] = incl - c;
-      if (lane == 31) tbase[j + 1] = incl;                         // tile total for now
-    }
-    __syncthreads();
-    if (tid == 0) {
-      tbase[0] = kept;
-      for (int j = 0; j < T; j++) tbase[j + 1] += tbase[j];
-    }
-    __syncthreads();
-    // pass 2: every kept edge moves to its rank (order preserved)
-    for (int j = 0; j < T; j++) {
-      const unsigned bal = __ballot_sync(0xffffffffu, (mask >> j) & 1ull);
-      if ((mask >> j) & 1ull) {
-        const int idx = e0 + j * kEsThreads + tid;
-        const int pos = tbase[j] + wpre[j][warp] + __popc(bal & ((1u << lane) - 1u));
-        ii_o[pos] = ii[idx]; jj_o[pos] = jj[idx]; kk_o[pos] = kk[idx];
-        src_row[pos] = idx;
-      }
-    }
-    kept = tbase[T];
-    __syncthreads();
+  const int T = (int)gridDim.x, j = (int)blockIdx.x;
+  const int idx = j * kEsThreads + tid;
+  int64_t vi = 0, vj = 0, vk = 0;
+  bool keep = false;
+  if (idx < E0) {
+    vi = ii[idx]; vj = jj[idx]; vk = kk[idx];
+    keep = vi >= lim;
   }
+  const unsigned bal = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) wsum[warp] = __popc(bal);
+  __syncthreads();
+  if (warp == 0) {                                     // exclusive scan of the 32 warp counts; publish the tile count
+    const int c = wsum[lane];
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    wsum[lane] = incl - c;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 0) {
+      __threadfence();
+      atomicExch(&tile_state[j], ((unsigned long long)epoch << 32) | (unsigned int)total);
+    }
+    // survivors in the earlier tiles
+    int before = 0;
+    for (int i0 = 0; i0 < j; i0 += 32) {
+      const int i = i0 + lane;
+      int c2 = 0;
+      if (i < j) {
+        unsigned long long w;
+        do {
+          w = *reinterpret_cast<volatile unsigned long long*>(&tile_state[i]);
+        } while ((unsigned int)(w >> 32) != epoch);
+        c2 = (int)(unsigned int)(w & 0xffffffffull);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+      before += c2;
+    }
+    if (lane == 0) base_s = before;
+  }
+  __syncthreads();
+  if (keep) {
+    const int pos = base_s + wsum[warp] + __popc(bal & ((1u << lane) - 1u));
+    ii_o[pos] = vi; jj_o[pos] = vj; kk_o[pos] = vk;
+    src_row[pos] = idx;
+  }
+  if (j != T - 1) return;
+  // ---- last CTA: the edges of the new frame follow the survivors
+  __shared__ int kept_s;
+  if (tid == 0) {
+    const unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(&tile_state[j]);
+    kept_s = base_s + (int)(unsigned int)(w & 0xffffffffull);
+  }
+  __syncthreads();
+  const int kept = E0 > 0 ? kept_s : 0;
   // forward edges: every patch of frames [f0, f1) -> frame n-1 (Ramp_vo.py:312-318)
   const int f0 = max(n - r, 0), f1 = max(n - 1, 0);
   const int n_f = M * (f1 - f0);
@@ -570,9 +585,9 @@ edges_step_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj
   const int j0 = max(n - r, 0), nj = n - j0;
   const int n_b = n >= 1 ? M * nj : 0;
   for (int t = tid; t < n_b; t += kEsThreads) {
-    const int p = t / nj, j = j0 + (t - p * nj);
+    const int p = t / nj, jt = j0 + (t - p * nj);
     const int o = kept + n_f + t;
-    ii_o[o] = n - 1; jj_o[o] = j; kk_o[o] = (int64_t)M * (n - 1) + p;
+    ii_o[o] = n - 1; jj_o[o] = jt; kk_o[o] = (int64_t)M * (n - 1) + p;
     src_row[o] = -1;
   }
   if (tid == 0) status[0] = kept + n_f + n_b == E_expected ? 0.0f : (float)(kept + n_f + n_b + 1);
@@ -604,17 +619,21 @@ extern "C" int rvo_net_rows(const float* net_in, const int32_t* src_row, int E, 
   return RVO_OK;
 }
 
+extern "C" int64_t rvo_edges_step_tiles(int E0) { return E0 <= 0 ? 1 : (E0 + rvo::kEsThreads - 1) / rvo::kEsThreads; }
+
 extern "C" int rvo_edges_step(const int64_t* ii, const int64_t* jj, const int64_t* kk, int E0, int lim, int n, int M,
                               int r, int64_t* ii_out, int64_t* jj_out, int64_t* kk_out, int E_new,
-                              int32_t* src_row, float* status, const float* net_in, int C, float* net_out,
-                              void* stream) {
+                              int32_t* src_row, float* status, uint64_t* tile_state, uint32_t epoch,
+                              const float* net_in, int C, float* net_out, void* stream) {
   RVO_CHECK_ARG(E0 >= 0 && E_new >= 0 && n >= 1 && M >= 1 && r >= 1, "rvo_edges_step: bad sizes");
-  RVO_CHECK_ARG(ii_out && jj_out && kk_out && src_row && status && (E0 == 0 || (ii && jj && kk)),
+  RVO_CHECK_ARG(ii_out && jj_out && kk_out && src_row && status && tile_state && (E0 == 0 || (ii && jj && kk)),
                 "rvo_edges_step: null pointer");
   RVO_CHECK_ARG(!net_out || ((net_in || E0 == 0) && C % 4 == 0 && net_out != net_in), "rvo_edges_step: hidden-state buffers");
   cudaStream_t st = (cudaStream_t)stream;
-  rvo::edges_step_kernel<<<1, rvo::kEsThreads, 0, st>>>(ii, jj, kk, E0, lim, n, M, r, ii_out, jj_out, kk_out, src_row,
-                                                       E_new, status);
+  const int tiles = (int)rvo_edges_step_tiles(E0);
+  rvo::edges_step_kernel<<<tiles, rvo::kEsThreads, 0, st>>>(
+      ii, jj, kk, E0, lim, n, M, r, ii_out, jj_out, kk_out, src_row, E_new, status,
+      reinterpret_cast<unsigned long long*>(tile_state), epoch);
   RVO_LAUNCH_CHECK("edges_step_kernel");
   if (net_out && E_new > 0) {
     int grid = rvo::cdiv((int64_t)E_new * 32, 256);

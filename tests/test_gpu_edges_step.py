@@ -30,10 +30,11 @@ def test_edges_step_matches_remove_then_append(n, lim, E0):
     ii_o, jj_o, kk_o = (torch.full((E1,), -7, dtype=torch.long, device="cuda") for _ in range(3))
     src = torch.empty(E1, dtype=torch.int32, device="cuda")
     status = torch.full((1,), 5.0, device="cuda")
+    tiles = torch.zeros(int(_lib.lib().rvo_edges_step_tiles(E0)), dtype=torch.int64, device="cuda")
     net_o = torch.full((E1, C), float("nan"), device="cuda")
     L = _lib.lib()
     _lib.check(L.rvo_edges_step(_lib.ptr(ii), _lib.ptr(jj), _lib.ptr(kk), E0, lim, n, M, r, _lib.ptr(ii_o), _lib.ptr(jj_o),
-                                _lib.ptr(kk_o), E1, _lib.ptr(src), _lib.ptr(status), _lib.ptr(net), C, _lib.ptr(net_o),
+                                _lib.ptr(kk_o), E1, _lib.ptr(src), _lib.ptr(status), _lib.ptr(tiles), 1, _lib.ptr(net), C, _lib.ptr(net_o),
                                 _lib.stream_ptr()), "rvo_edges_step")
     torch.cuda.synchronize()
     assert float(status) == 0.0
@@ -41,7 +42,7 @@ def test_edges_step_matches_remove_then_append(n, lim, E0):
     assert torch.equal(net_o, net_e)
     # a wrong host-side count is reported, not silently accepted
     _lib.check(L.rvo_edges_step(_lib.ptr(ii), _lib.ptr(jj), _lib.ptr(kk), E0, lim, n, M, r, _lib.ptr(ii_o), _lib.ptr(jj_o),
-                                _lib.ptr(kk_o), E1 + 1, _lib.ptr(src), _lib.ptr(status), None, C, None,
+                                _lib.ptr(kk_o), E1 + 1, _lib.ptr(src), _lib.ptr(status), _lib.ptr(tiles), 2, None, C, None,
                                 _lib.stream_ptr()), "rvo_edges_step")
     torch.cuda.synchronize()
     assert float(status) == E1 + 1
