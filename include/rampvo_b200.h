@@ -408,13 +408,15 @@ int rvo_up_gated_tail(const float* x32, const void* a16, const void* r16, int E,
  * (n = number of frames AFTER the new one was added, M patches per frame, r = PATCH_LIFETIME).
  *   ii/jj/kk [E0] -> ii_out/jj_out/kk_out [E_new]; src_row [E_new] int32 = old row of a surviving edge, -1 for a new
  *   one; net_in [E0,C] -> net_out [E_new,C] (rows follow their edges, new edges start at zero; may be NULL).
+ *   drop_k >= 0: keyframe drop_k was dropped first (ramp/Ramp_vo.py:249-262): its edges (ii == k or jj == k) go, and
+ *   frames / patches behind it are renumbered (ii, jj > k: -1; kk of ii > k: -M) before the lim test; -1 = no drop.
  *   E_new is the caller's (host-side) edge count: status[0] (device float) is 0 when the device agrees, else its count + 1.
  *   tile_state: rvo_edges_step_tiles(E0) device words kept by the caller between calls (zeroed once); epoch: a value
  *   that differs from every earlier call on the same tile_state (a frame counter) — the CTAs of one launch exchange
  *   their counts through it without a reset pass. */
 int64_t rvo_edges_step_tiles(int E0);
-int rvo_edges_step(const int64_t* ii, const int64_t* jj, const int64_t* kk, int E0, int lim, int n, int M, int r,
-                   int64_t* ii_out, int64_t* jj_out, int64_t* kk_out, int E_new, int32_t* src_row, float* status,
+int rvo_edges_step(const int64_t* ii, const int64_t* jj, const int64_t* kk, int E0, int drop_k, int lim, int n, int M,
+                   int r, int64_t* ii_out, int64_t* jj_out, int64_t* kk_out, int E_new, int32_t* src_row, float* status,
                    uint64_t* tile_state, uint32_t epoch, const float* net_in, int C, float* net_out, void* stream);
 
 /* the hidden-state half of rvo_edges_step alone (net_out[e] = net_in[src_row[e]], 0 for src_row[e] < 0), so that it

@@ -281,6 +281,7 @@ class Ramp_vo:
         self._last_ugraph = None
         self.fast_edges = bool(getattr(cfg, "FAST_EDGES", True))   # fused patch-graph step (rvo_edges_step)
         self._pending_lim = None
+        self._pending_drop = -1     # keyframe whose removal rides on the next rvo_edges_step
         self._net_stream = None
         self._net_ready = torch.cuda.Event(external=True) if self.device.type == "cuda" else None
         self._net_ready_fresh = False
@@ -629,6 +630,28 @@ class Ramp_vo:
         self._net_swap(keep.numel())
         self._plans = None
 
+    def _flush_pending_drop(self):
+        """apply a keyframe drop that was left to rvo_edges_step with plain tensor ops (Ramp_vo.py:249-262)"""
+        k, self._pending_drop = self._pending_drop, -1
+        if k < 0:
+            return
+        pc, self._pair_cnt = self._pair_cnt, None       # remove_factors wants counts that match the device lists
+        m = (self.ii == k) | (self.jj == k)
+        n_keep = sum(pc.values())
+        self._net_join()
+        if n_keep != m.numel():
+            keep = torch.nonzero_static(~m, size=n_keep).view(-1)
+            self.ii, self.jj, self.kk = self.ii[keep], self.jj[keep], self.kk[keep]
+            out = self._net_other(n_keep)
+            torch.index_select(self.net, 1, keep, out=out)
+            self._net_swap(n_keep)
+            self._plans = None
+        gi = self.ii > k
+        self.kk = self.kk - gi * self.M
+        self.ii = self.ii - gi.to(self.ii.dtype)
+        self.jj = self.jj - (self.jj > k).to(self.jj.dtype)
+        self._pair_cnt = pc
+
     def _net_join(self):
         """make the current stream wait for a hidden-state gather still running on the side stream (_edges_step)"""
         if self._net_ready_fresh:
@@ -639,10 +662,11 @@ class Ramp_vo:
         """remove_factors(ii < lim) + append_factors(forward) + append_factors(backward) of the frame that was just
         added (self.n already counts it) in two launches: the edge lists and the hidden-state rows are rebuilt on the
         device by rvo_edges_step, the host only keeps its pair counts in step."""
-        pc = self._pair_counts()
+        drop_k, self._pending_drop = self._pending_drop, -1
+        pc = self._pair_cnt if drop_k >= 0 else self._pair_counts()    # (a pending drop already left the host counts)
         r, M, n = self.cfg.PATCH_LIFETIME, self.M, self.n
         E0 = self.ii.numel()
-        n_removed = 0
+        n_removed = E0 - sum(pc.values())                              # edges of the dropped keyframe
         for i in range(self._min_src, max(lim, self._min_src)):      # source frames that leave the window
             for j in range(max(i - r - 1, 0), i + r + 2):
                 n_removed += pc.pop((i, j), 0)
@@ -669,7 +693,8 @@ class Ramp_vo:
             self._net_stream = torch.cuda.Stream(device=dev)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().rvo_edges_step(
-                _lib.ptr(self.ii), _lib.ptr(self.jj), _lib.ptr(self.kk), E0, int(lim), n, M, r, _lib.ptr(ii), _lib.ptr(jj),
+                _lib.ptr(self.ii), _lib.ptr(self.jj), _lib.ptr(self.kk), E0, int(drop_k), int(lim), n, M, r,
+                _lib.ptr(ii), _lib.ptr(jj),
                 _lib.ptr(kk), E1, _lib.ptr(self._edge_src), _lib.ptr(self._edge_status), _lib.ptr(self._edge_tiles),
                 self._edge_epoch, None, self.DIM, None, _lib.stream_ptr(dev)), "rvo_edges_step")
             # the rows of the hidden state follow on a side stream: the update graph waits for them (external event)
@@ -718,6 +743,7 @@ class Ramp_vo:
         leave the removal of the edges that fell out of the window to the fused graph step of the new frame"""
         if self._pending_lim is not None:      # never observable from outside: flush a removal left pending
             lim, self._pending_lim = self._pending_lim, None
+            self._flush_pending_drop()
             self.remove_factors(self.ii < lim, lambda i, j: i < lim)
         if self._pending_kf is not None:
             host, ev = self._pending_kf
@@ -776,13 +802,21 @@ class Ramp_vo:
             t1 = self.tstamps_[k].item()
             dP = SE3(self.poses_[k]) * SE3(self.poses_[k - 1]).inv()
             self.delta[t1] = (t0, dP)
-            self.remove_factors((self.ii == k) | (self.jj == k), lambda i, j: i == k or j == k)
-            # renumber without boolean indexing (no size-dependent sync): subtract masks
-            gi = self.ii > k
-            self.kk -= gi * self.M
-            self.ii -= gi.to(self.ii.dtype)
-            self.jj -= (self.jj > k).to(self.jj.dtype)
-            self._pair_cnt = {(i - (i > k), j - (j > k)): v for (i, j), v in self._pair_counts().items()}
+            if defer_removal:
+                # the edge lists are left as they are: rvo_edges_step of the new frame removes the edges of k and
+                # renumbers the rest in the same pass as the window removal and the appends (drop_k)
+                pc = self._pair_counts()
+                for key in [key for key in pc if key[0] == k or key[1] == k]:
+                    del pc[key]
+                self._pending_drop = k
+            else:
+                self.remove_factors((self.ii == k) | (self.jj == k), lambda i, j: i == k or j == k)
+                # renumber without boolean indexing (no size-dependent sync): subtract masks
+                gi = self.ii > k
+                self.kk -= gi * self.M
+                self.ii -= gi.to(self.ii.dtype)
+                self.jj -= (self.jj > k).to(self.jj.dtype)
+            self._pair_cnt = {(i - (i > k), j - (j > k)): v for (i, j), v in self._pair_cnt.items()}
             self._min_src = max(self._min_src - 1, 0)
             # shift every per-frame buffer one slot down (the reference loops frame by frame)
             n = self.n

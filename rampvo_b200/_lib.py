@@ -62,7 +62,7 @@ _SIGNATURES = {
     "rvo_set_sm_budget": (c_int, [c_int]),
     "rvo_net_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "rvo_edges_step_tiles": (c_int64, [c_int]),
-    "rvo_edges_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+    "rvo_edges_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_int, c_void_p, c_void_p, c_void_p, ctypes.c_uint32, c_void_p, c_int, c_void_p,
                                c_void_p]),
     "rvo_get_sm_budget": (c_int, []),

@@ -509,8 +509,8 @@ constexpr int kEsThreads = 1024;
 // (A single CTA doing all of it is bound by what one SM can move: 42 us for the 2.9 MB of a 47 712-edge list.)
 __global__ void __launch_bounds__(kEsThreads)
 edges_step_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, const int64_t* __restrict__ kk,
-                  int E0, int lim, int n, int M, int r, int64_t* __restrict__ ii_o, int64_t* __restrict__ jj_o,
-                  int64_t* __restrict__ kk_o, int32_t* __restrict__ src_row, int E_expected,
+                  int E0, int drop_k, int lim, int n, int M, int r, int64_t* __restrict__ ii_o,
+                  int64_t* __restrict__ jj_o, int64_t* __restrict__ kk_o, int32_t* __restrict__ src_row, int E_expected,
                   float* __restrict__ status, unsigned long long* __restrict__ tile_state, unsigned int epoch) {
   __shared__ int wsum[kEsThreads / 32];
   __shared__ int base_s;
@@ -521,7 +521,14 @@ edges_step_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj
   bool keep = false;
   if (idx < E0) {
     vi = ii[idx]; vj = jj[idx]; vk = kk[idx];
-    keep = vi >= lim;
+    keep = true;
+    if (drop_k >= 0) {
+      // keyframe drop_k goes first (Ramp_vo.py:249-262): its edges are removed, later frames / patches move down
+      keep = vi != drop_k && vj != drop_k;
+      if (vi > drop_k) { vi -= 1; vk -= M; }
+      if (vj > drop_k) vj -= 1;
+    }
+    keep = keep && vi >= lim;
   }
   const unsigned bal = __ballot_sync(0xffffffffu, keep);
   if (lane == 0) wsum[warp] = __popc(bal);
@@ -621,8 +628,8 @@ extern "C" int rvo_net_rows(const float* net_in, const int32_t* src_row, int E, 
 
 extern "C" int64_t rvo_edges_step_tiles(int E0) { return E0 <= 0 ? 1 : (E0 + rvo::kEsThreads - 1) / rvo::kEsThreads; }
 
-extern "C" int rvo_edges_step(const int64_t* ii, const int64_t* jj, const int64_t* kk, int E0, int lim, int n, int M,
-                              int r, int64_t* ii_out, int64_t* jj_out, int64_t* kk_out, int E_new,
+extern "C" int rvo_edges_step(const int64_t* ii, const int64_t* jj, const int64_t* kk, int E0, int drop_k, int lim,
+                              int n, int M, int r, int64_t* ii_out, int64_t* jj_out, int64_t* kk_out, int E_new,
                               int32_t* src_row, float* status, uint64_t* tile_state, uint32_t epoch,
                               const float* net_in, int C, float* net_out, void* stream) {
   RVO_CHECK_ARG(E0 >= 0 && E_new >= 0 && n >= 1 && M >= 1 && r >= 1, "rvo_edges_step: bad sizes");
@@ -632,7 +639,7 @@ extern "C" int rvo_edges_step(const int64_t* ii, const int64_t* jj, const int64_
   cudaStream_t st = (cudaStream_t)stream;
   const int tiles = (int)rvo_edges_step_tiles(E0);
   rvo::edges_step_kernel<<<tiles, rvo::kEsThreads, 0, st>>>(
-      ii, jj, kk, E0, lim, n, M, r, ii_out, jj_out, kk_out, src_row, E_new, status,
+      ii, jj, kk, E0, drop_k, lim, n, M, r, ii_out, jj_out, kk_out, src_row, E_new, status,
       reinterpret_cast<unsigned long long*>(tile_state), epoch);
   RVO_LAUNCH_CHECK("edges_step_kernel");
   if (net_out && E_new > 0) {

@@ -9,15 +9,26 @@ from rampvo_b200 import _lib
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n,lim,E0", [(12, 3, 5000), (30, 8, 45312), (9, 0, 700), (14, 20, 300), (5, 1, 0)])
-def test_edges_step_matches_remove_then_append(n, lim, E0):
+@pytest.mark.parametrize("n,lim,E0,drop", [(12, 3, 5000, -1), (30, 8, 45312, -1), (9, 0, 700, -1), (14, 20, 300, -1),
+                                           (5, 1, 0, -1), (12, 2, 5000, 7), (30, 8, 45312, 25), (9, 0, 700, 0)])
+def test_edges_step_matches_remove_then_append(n, lim, E0, drop):
+    """n = frames after the new one was added (and after the dropped keyframe, if any, was taken out)"""
     M, r, C = 96, 13, 384
     g = torch.Generator(device="cuda").manual_seed(n)
-    ii = torch.randint(0, n - 1, (E0,), device="cuda", generator=g)
-    jj = torch.randint(0, n - 1, (E0,), device="cuda", generator=g)
+    n_old = n - 1 + (drop >= 0)                      # frames the old edge list refers to
+    ii = torch.randint(0, n_old, (E0,), device="cuda", generator=g)
+    jj = torch.randint(0, n_old, (E0,), device="cuda", generator=g)
     kk = ii * M + torch.randint(0, M, (E0,), device="cuda", generator=g)
     net = torch.randn(max(E0, 1), C, device="cuda", generator=g)[:E0]
-    keep = ii >= lim
+    ii_in, jj_in, kk_in = ii, jj, kk
+    keep = torch.ones_like(ii, dtype=torch.bool)
+    if drop >= 0:                                    # the tensor ops of the keyframe drop (Ramp_vo.py:249-262)
+        keep = (ii != drop) & (jj != drop)
+        gi = ii > drop
+        kk = kk - gi * M
+        ii = ii - gi.long()
+        jj = jj - (jj > drop).long()
+    keep = keep & (ii >= lim)
     f0, f1, j0 = max(n - r, 0), max(n - 1, 0), max(n - r, 0)
     kf = torch.arange(M * f0, M * f1, device="cuda")
     kb = torch.arange(M * (n - 1), M * n, device="cuda").repeat_interleave(n - j0)
@@ -33,7 +44,7 @@ def test_edges_step_matches_remove_then_append(n, lim, E0):
     tiles = torch.zeros(int(_lib.lib().rvo_edges_step_tiles(E0)), dtype=torch.int64, device="cuda")
     net_o = torch.full((E1, C), float("nan"), device="cuda")
     L = _lib.lib()
-    _lib.check(L.rvo_edges_step(_lib.ptr(ii), _lib.ptr(jj), _lib.ptr(kk), E0, lim, n, M, r, _lib.ptr(ii_o), _lib.ptr(jj_o),
+    _lib.check(L.rvo_edges_step(_lib.ptr(ii_in), _lib.ptr(jj_in), _lib.ptr(kk_in), E0, drop, lim, n, M, r, _lib.ptr(ii_o), _lib.ptr(jj_o),
                                 _lib.ptr(kk_o), E1, _lib.ptr(src), _lib.ptr(status), _lib.ptr(tiles), 1, _lib.ptr(net), C, _lib.ptr(net_o),
                                 _lib.stream_ptr()), "rvo_edges_step")
     torch.cuda.synchronize()
@@ -41,7 +52,7 @@ def test_edges_step_matches_remove_then_append(n, lim, E0):
     assert torch.equal(ii_o, ii_e) and torch.equal(jj_o, jj_e) and torch.equal(kk_o, kk_e)
     assert torch.equal(net_o, net_e)
     # a wrong host-side count is reported, not silently accepted
-    _lib.check(L.rvo_edges_step(_lib.ptr(ii), _lib.ptr(jj), _lib.ptr(kk), E0, lim, n, M, r, _lib.ptr(ii_o), _lib.ptr(jj_o),
+    _lib.check(L.rvo_edges_step(_lib.ptr(ii_in), _lib.ptr(jj_in), _lib.ptr(kk_in), E0, drop, lim, n, M, r, _lib.ptr(ii_o), _lib.ptr(jj_o),
                                 _lib.ptr(kk_o), E1 + 1, _lib.ptr(src), _lib.ptr(status), _lib.ptr(tiles), 2, None, C, None,
                                 _lib.stream_ptr()), "rvo_edges_step")
     torch.cuda.synchronize()
