@@ -70,82 +70,73 @@ __device__ __forceinline__ int64_t tc_mod(int64_t v, int64_t mod) {
   return v % mod;
 }
 
-// one thread per (edge, level): the 9 patch pixels of an edge almost always share a tile and fall into
-// ~3 window-origin rows, so the histogram updates are aggregated in registers — one atomicAdd per
-// distinct sub-bin (its return value ranks the rows, ranks stay unique per sub-bin) and one
-// fire-and-forget add per distinct tile for the per-tile totals
+// Both binning passes run one thread per (edge, level) and see the edge's 9 patch pixels together: they almost
+// always share a tile and fall into ~3 window-origin rows, so everything is aggregated in registers first.
+struct TcEdgeBins {
+  int sub[9];        // (tile, oy) sub-bin of every pixel's row, -1: window entirely outside the map / invalid index
+  int tile[9];
+  unsigned same[9];  // bit q: pixel q falls into the same sub-bin
+  unsigned tfirst;   // bit p: pixel p is the first of its tile
+};
+
+__device__ __forceinline__ void tc_edge_bins(const TcGeom& G, int lvl, const float* __restrict__ cp, int64_t ip,
+                                             int64_t jf, int64_t gN, TcEdgeBins& B, float (&xs)[9], float (&ys)[9]) {
+  const bool l1 = lvl != 0;
+  const float scale = l1 ? G.lv[1].scale : G.lv[0].scale;
+  const int LW = l1 ? G.lv[1].W : G.lv[0].W, LH = l1 ? G.lv[1].H : G.lv[0].H;
+  const int LN = l1 ? G.lv[1].N : G.lv[0].N, TX = l1 ? G.lv[1].TX : G.lv[0].TX;
+  const int TY = l1 ? G.lv[1].TY : G.lv[0].TY, base = l1 ? G.lv[1].binbase : G.lv[0].binbase;
+  const bool idx_ok = ip >= 0 && ip < gN && jf >= 0 && jf < LN;
+#pragma unroll
+  for (int pix = 0; pix < 9; pix++) {
+    xs[pix] = cp[pix] * scale;
+    ys[pix] = cp[9 + pix] * scale;
+    const int x0 = tc_floor(xs[pix]) - kTcR, y0 = tc_floor(ys[pix]) - kTcR;
+    const bool ok = idx_ok && x0 > -kTcWin && x0 < LW && y0 > -kTcWin && y0 < LH;
+    // sub-bin = (tile, oy): rows of a tile end up sorted by the tile row their window starts in, so a
+    // warp of the tile kernel's epilogue reads few more than 8 accumulator rows
+    const int ty = (y0 + kTcWin) / kTcStep;
+    B.tile[pix] = ok ? base + ((int)jf * TY + ty) * TX + (x0 + kTcWin) / kTcStep : -1;
+    B.sub[pix] = ok ? B.tile[pix] * kTcSub + (y0 + kTcWin) - ty * kTcStep : -1;
+  }
+  // 36 comparisons each for the sub-bins and the tiles
+  B.tfirst = 0x1ffu;
+#pragma unroll
+  for (int pix = 0; pix < 9; pix++) B.same[pix] = 1u << pix;
+#pragma unroll
+  for (int pix = 1; pix < 9; pix++)
+#pragma unroll
+    for (int q = 0; q < pix; q++) {
+      if (B.sub[q] == B.sub[pix]) {
+        B.same[pix] |= 1u << q;
+        B.same[q] |= 1u << pix;
+      }
+      if (B.tile[q] == B.tile[pix]) B.tfirst &= ~(1u << pix);
+    }
+}
+
+// histogram pass: one fire-and-forget add per distinct sub-bin and per distinct tile of the edge
 __global__ void __launch_bounds__(256)
 tc_bin_count_kernel(TcGeom G, const float* __restrict__ coords, const int64_t* __restrict__ kk,
                     const int64_t* __restrict__ jj, int64_t pmod, int64_t fmod, int64_t gN, int E,
-                    int32_t* __restrict__ cnt, int32_t* __restrict__ tot, int32_t* __restrict__ rowbin,
-                    int32_t* __restrict__ rowrank, __half* __restrict__ out, int64_t out_ld) {
+                    int32_t* __restrict__ cnt, int32_t* __restrict__ tot) {
   const int NL = G.nlevels;
   const int T = E * NL;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
     const int e = t / NL;
     const int lvl = t - e * NL;
-    const bool l1 = lvl != 0;
-    const float scale = l1 ? G.lv[1].scale : G.lv[0].scale;
-    const int LW = l1 ? G.lv[1].W : G.lv[0].W, LH = l1 ? G.lv[1].H : G.lv[0].H;
-    const int LN = l1 ? G.lv[1].N : G.lv[0].N, TX = l1 ? G.lv[1].TX : G.lv[0].TX;
-    const int TY = l1 ? G.lv[1].TY : G.lv[0].TY, base = l1 ? G.lv[1].binbase : G.lv[0].binbase;
-    const int64_t ip = tc_mod(kk[e], pmod), jf = tc_mod(jj[e], fmod);
-    const bool idx_ok = ip >= 0 && ip < gN && jf >= 0 && jf < LN;
-    const float* cp = coords + (int64_t)e * 18;
-    int subs[9];
+    TcEdgeBins B;
+    float xs[9], ys[9];
+    tc_edge_bins(G, lvl, coords + (int64_t)e * 18, tc_mod(kk[e], pmod), tc_mod(jj[e], fmod), gN, B, xs, ys);
 #pragma unroll
     for (int pix = 0; pix < 9; pix++) {
-      const int x0 = tc_floor(cp[pix] * scale) - kTcR, y0 = tc_floor(cp[9 + pix] * scale) - kTcR;
-      const bool ok = idx_ok && x0 > -kTcWin && x0 < LW && y0 > -kTcWin && y0 < LH;
-      // sub-bin = (tile, oy): rows of a tile end up sorted by the tile row their window starts in, so a
-      // warp of the tile kernel's epilogue reads few more than 8 accumulator rows
-      subs[pix] = ok ? (base + ((int)jf * TY + (y0 + kTcWin) / kTcStep) * TX + (x0 + kTcWin) / kTcStep) * kTcSub +
-                           (y0 + kTcWin) % kTcStep
-                     : -1;
-    }
-    int ranks[9];
+      if (B.sub[pix] < 0) continue;
+      if ((B.same[pix] & ((1u << pix) - 1u)) == 0) atomicAdd(&cnt[B.sub[pix]], __popc(B.same[pix]));
+      if ((B.tfirst >> pix) & 1u) {
+        int n = 0;
 #pragma unroll
-    for (int pix = 0; pix < 9; pix++) ranks[pix] = -1;
-    unsigned done = 0, tdone = 0;
-#pragma unroll
-    for (int pix = 0; pix < 9; pix++) {
-      if (subs[pix] < 0 || ((done >> pix) & 1u)) continue;
-      int n = 0;
-#pragma unroll
-      for (int q = 0; q < 9; q++)
-        if (q >= pix && subs[q] == subs[pix]) n++;
-      int r0 = atomicAdd(&cnt[subs[pix]], n);
-#pragma unroll
-      for (int q = 0; q < 9; q++)
-        if (q >= pix && subs[q] == subs[pix]) {
-          ranks[q] = r0++;
-          done |= 1u << q;
-        }
-    }
-#pragma unroll
-    for (int pix = 0; pix < 9; pix++) {
-      if (subs[pix] < 0 || ((tdone >> pix) & 1u)) continue;
-      const int tile = subs[pix] / kTcSub;
-      int n = 0;
-#pragma unroll
-      for (int q = 0; q < 9; q++)
-        if (q >= pix && subs[q] >= 0 && subs[q] / kTcSub == tile) {
-          n++;
-          tdone |= 1u << q;
-        }
-      atomicAdd(&tot[tile], n);
-    }
-#pragma unroll
-    for (int pix = 0; pix < 9; pix++) {
-      const int r = (e * 9 + pix) * NL + lvl;
-      rowbin[r] = subs[pix];
-      if (subs[pix] >= 0) {
-        rowrank[r] = ranks[pix];
-      } else {
-        // window entirely outside the map (or invalid index): the 7x7 outputs are zero
-        uint4* o = reinterpret_cast<uint4*>(out + (int64_t)e * out_ld + (lvl * 9 + pix) * kTcGroup);
-#pragma unroll
-        for (int q = 0; q < kTcGroup / 8; q++) o[q] = make_uint4(0u, 0u, 0u, 0u);
+        for (int q = 0; q < 9; q++) n += (B.tile[q] == B.tile[pix]) ? 1 : 0;
+        atomicAdd(&tot[B.tile[pix]], n);
       }
     }
   }
@@ -154,54 +145,6 @@ tc_bin_count_kernel(TcGeom G, const float* __restrict__ coords, const int64_t* _
 struct __align__(16) TcHdr {
   int nrows, rbase, lvl, f, X0, Y0, flags, pad1;   // flags: bit 0 = same tile as the previous block, bit 1 = as the next
 };
-
-// one CTA: exclusive scans of the per-tile row totals and 128-row block counts -> first row and first
-// block of every tile.  Kept tiny on purpose — it runs on ONE SM: coalesced loads / stores staged
-// through shared memory (a single SM keeps few scattered sectors in flight), everything heavier (the
-// block headers) is done by the row-parallel scatter pass.
-constexpr int kScanMaxBins = 24576;          // 6 B x bins + 4 KB of dynamic shared memory
-__global__ void __launch_bounds__(1024)
-tc_bin_scan_kernel(const int32_t* __restrict__ tot, int nbins, int32_t* __restrict__ rowstart,
-                   int32_t* __restrict__ blkstart, int32_t* __restrict__ total_blocks) {
-  typedef cub::BlockScan<int, 1024, cub::BLOCK_SCAN_WARP_SCANS> Scan;
-  __shared__ typename Scan::TempStorage tmp_r, tmp_b;
-  extern __shared__ int32_t scan_sm[];
-  int32_t* bfirst_s = scan_sm;                               // [1024]
-  int32_t* r_s = scan_sm + 1024;                             // [nbins]
-  uint16_t* b_s = reinterpret_cast<uint16_t*>(r_s + nbins);  // [nbins]
-  for (int b = threadIdx.x; b < nbins; b += 1024) r_s[b] = tot[b];
-  __syncthreads();
-  // thread t owns tiles t*per .. t*per + per - 1
-  const int per = (nbins + 1023) / 1024;
-  const int b0 = threadIdx.x * per;
-  int rows = 0, blks = 0;
-  for (int i = 0; i < per; i++) {
-    const int c = (b0 + i < nbins) ? r_s[b0 + i] : 0;
-    rows += c;
-    blks += (c + kTcRows - 1) / kTcRows;
-  }
-  int rpre, bpre, btot;
-  Scan(tmp_r).ExclusiveSum(rows, rpre);
-  Scan(tmp_b).ExclusiveSum(blks, bpre, btot);
-  if (threadIdx.x == 0) total_blocks[0] = btot;
-  // in place: counts -> exclusive row offsets; block offsets relative to the thread's first block fit 16 bits
-  const int bfirst = bpre;
-  for (int i = 0; i < per; i++) {
-    if (b0 + i < nbins) {
-      const int c = r_s[b0 + i];
-      r_s[b0 + i] = rpre;
-      b_s[b0 + i] = (uint16_t)(bpre - bfirst);
-      rpre += c;
-      bpre += (c + kTcRows - 1) / kTcRows;
-    }
-  }
-  bfirst_s[threadIdx.x] = bfirst;
-  __syncthreads();
-  for (int b = threadIdx.x; b < nbins; b += 1024) {
-    rowstart[b] = r_s[b];
-    blkstart[b] = bfirst_s[b / per] + b_s[b];
-  }
-}
 
 // everything the tile kernel needs to know about a row, written in bin order by the scatter pass so
 // that the main kernel does one coalesced 32-byte load per row instead of a chain of dependent loads
@@ -212,40 +155,110 @@ struct __align__(16) TcRow {
   int ox, oy;        // window origin inside the 16x16 tile, 0..8
 };
 
-__global__ void __launch_bounds__(256)
+// Exclusive scans of the per-tile row totals and 128-row block counts -> first row and first block of every tile.
+// The table is small (~10 k tiles, 40 KB), so there is no separate scan launch: EVERY CTA of the scatter pass scans
+// it for itself into shared memory (coalesced loads that hit the L2, two block scans) and then serves its rows'
+// lookups from there — one launch and one dependent global round trip less than a scan kernel on a single SM.
+constexpr int kScanMaxBins = 24576;          // 6 B x bins + 4 KB of dynamic shared memory
+constexpr int kScatterThreads = 1024;
+
+// scatter pass, one thread per row: a second set of counters (cursor, zeroed with cnt / tot) hands the row its slot
+// inside its sub-bin — first row of the tile + rows of the lower sub-bins + cursor — and the thread writes the row's
+// record there.  The row that opens a 128-row block also writes the block header.
+__global__ void __launch_bounds__(kScatterThreads)
 tc_bin_scatter_kernel(TcGeom G, const float* __restrict__ coords, const int64_t* __restrict__ kk,
-                      const int64_t* __restrict__ jj, int64_t pmod, int64_t fmod, int64_t g_sN, int64_t g_sH,
-                      int64_t g_sW, int64_t out_ld, int64_t R, const int32_t* __restrict__ rowbin,
-                      const int32_t* __restrict__ rowrank, const int32_t* __restrict__ rowstart,
-                      const int32_t* __restrict__ blkstart, const int32_t* __restrict__ cnt,
-                      const int32_t* __restrict__ tot, TcRow* __restrict__ rows, TcHdr* __restrict__ hdr) {
+                      const int64_t* __restrict__ jj, int64_t pmod, int64_t fmod, int64_t gN, int64_t g_sN,
+                      int64_t g_sH, int64_t g_sW, int64_t out_ld, int64_t R, const int32_t* __restrict__ cnt,
+                      const int32_t* __restrict__ tot, int32_t* __restrict__ cursor, TcRow* __restrict__ rows,
+                      TcHdr* __restrict__ hdr, int32_t* __restrict__ total_blocks, __half* __restrict__ out) {
+  typedef cub::BlockScan<int, kScatterThreads, cub::BLOCK_SCAN_WARP_SCANS> Scan;
+  __shared__ typename Scan::TempStorage tmp_r, tmp_b;
+  extern __shared__ int32_t scan_sm[];
+  const int nbins = G.nbins;
+  int32_t* bfirst_s = scan_sm;                               // [threads] first block of the thread's first tile
+  int32_t* r_s = scan_sm + kScatterThreads;                  // [nbins] row totals -> first row of the tile
+  uint16_t* b_s = reinterpret_cast<uint16_t*>(r_s + nbins);  // [nbins] first block, relative to bfirst_s
+  for (int b = threadIdx.x; b < nbins; b += kScatterThreads) r_s[b] = tot[b];
+  __syncthreads();
+  // thread t owns tiles t*per .. t*per + per - 1
+  const int per = (nbins + kScatterThreads - 1) / kScatterThreads;
+  {
+    const int b0 = threadIdx.x * per;
+    int nrow = 0, blks = 0;
+    for (int i = 0; i < per; i++) {
+      const int c = (b0 + i < nbins) ? r_s[b0 + i] : 0;
+      nrow += c;
+      blks += (c + kTcRows - 1) / kTcRows;
+    }
+    int rpre, bpre, btot;
+    Scan(tmp_r).ExclusiveSum(nrow, rpre);
+    Scan(tmp_b).ExclusiveSum(blks, bpre, btot);
+    if (blockIdx.x == 0 && threadIdx.x == 0) total_blocks[0] = btot;
+    // in place: counts -> exclusive row offsets; block offsets relative to the thread's first block fit 16 bits
+    bfirst_s[threadIdx.x] = bpre;
+    int brel = 0;
+    for (int i = 0; i < per; i++) {
+      if (b0 + i < nbins) {
+        const int c = r_s[b0 + i];
+        r_s[b0 + i] = rpre;
+        b_s[b0 + i] = (uint16_t)brel;
+        rpre += c;
+        brel += (c + kTcRows - 1) / kTcRows;
+      }
+    }
+  }
+  __syncthreads();
+
   const int NL = G.nlevels;
   const int Ri = (int)R;                                     // < 2^31 (checked on the host)
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < Ri; r += gridDim.x * blockDim.x) {
-    const int bin = rowbin[r];
-    if (bin < 0) continue;
     const int ep = r / NL;
     const int lvl = r - ep * NL;
     const int e = ep / 9;
     const int pix = ep - e * 9;
-    const TcLevel& L = G.lv[lvl];
-    const int64_t ip = tc_mod(kk[e], pmod);
-    const float x = coords[(int64_t)e * 18 + pix] * L.scale;
-    const float y = coords[(int64_t)e * 18 + 9 + pix] * L.scale;
-    const float fxf = floorf(x), fyf = floorf(y);
-    TcRow rec;
-    rec.src = ip * g_sN + (pix / 3) * g_sH + (pix % 3) * g_sW;
-    rec.out = (long long)e * out_ld + (lvl * 9 + pix) * kTcGroup;
-    rec.dx = x - fxf;
-    rec.dy = y - fyf;
-    rec.ox = ((int)fxf - kTcR + kTcWin) % kTcStep;
-    rec.oy = ((int)fyf - kTcR + kTcWin) % kTcStep;
-    // rows of a tile are ordered by oy: first row of the tile + rows of the lower sub-bins + rank
-    const int tile = bin / kTcSub, oy = bin - tile * kTcSub;
+    const bool l1 = lvl != 0;
+    const float scale = l1 ? G.lv[1].scale : G.lv[0].scale;
+    const int LW = l1 ? G.lv[1].W : G.lv[0].W, LH = l1 ? G.lv[1].H : G.lv[0].H;
+    const int LN = l1 ? G.lv[1].N : G.lv[0].N, TX = l1 ? G.lv[1].TX : G.lv[0].TX;
+    const int TY = l1 ? G.lv[1].TY : G.lv[0].TY, base = l1 ? G.lv[1].binbase : G.lv[0].binbase;
+    const int64_t ip = tc_mod(kk[e], pmod), jf = tc_mod(jj[e], fmod);
+    const float x = coords[(int64_t)e * 18 + pix] * scale;
+    const float y = coords[(int64_t)e * 18 + 9 + pix] * scale;
+    const int x0 = tc_floor(x) - kTcR, y0 = tc_floor(y) - kTcR;
+    const long long out_off = (long long)e * out_ld + (lvl * 9 + pix) * kTcGroup;
+    const bool ok = ip >= 0 && ip < gN && jf >= 0 && jf < LN && x0 > -kTcWin && x0 < LW && y0 > -kTcWin && y0 < LH;
+    const int wx = x0 + kTcWin, wy = y0 + kTcWin;            // > 0 for a valid row
+    const int tx = wx / kTcStep, ty = wy / kTcStep;
+    const int ox = wx - tx * kTcStep, oy = wy - ty * kTcStep;
+    const int tile = base + ((int)jf * TY + ty) * TX + tx;
+    // neighbouring lanes are the pixels of one edge and mostly share a sub-bin: one atomic per distinct sub-bin of
+    // the warp, its lanes take consecutive slots
+    const unsigned act = __activemask();
+    const int sub = ok ? tile * kTcSub + oy : -1 - (int)(threadIdx.x & 31);
+    const unsigned peers = __match_any_sync(act, sub);
+    const int leader = __ffs(peers) - 1;
+    int rank = 0;
+    if (ok && (int)(threadIdx.x & 31) == leader) rank = atomicAdd(&cursor[sub], __popc(peers));
+    rank = __shfl_sync(act, rank, leader) + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+    if (!ok) {
+      // window entirely outside the map (or invalid index): the 7x7 outputs are zero
+      uint4* o = reinterpret_cast<uint4*>(out + out_off);
+#pragma unroll
+      for (int q = 0; q < kTcGroup / 8; q++) o[q] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
     const int4* c4 = reinterpret_cast<const int4*>(cnt) + tile * 3;
     const int4 v0 = c4[0], v1 = c4[1];
-    const int rs = rowstart[tile];
-    int pos = rs + rowrank[r];
+    TcRow rec;
+    rec.src = ip * g_sN + (pix / 3) * g_sH + (pix % 3) * g_sW;
+    rec.out = out_off;
+    rec.dx = x - floorf(x);
+    rec.dy = y - floorf(y);
+    rec.ox = ox;
+    rec.oy = oy;
+    // rows of a tile are ordered by oy: first row of the tile + rows of the lower sub-bins + rank
+    const int rs = r_s[tile];
+    int pos = rs + rank;
     pos += (oy > 0 ? v0.x : 0) + (oy > 1 ? v0.y : 0) + (oy > 2 ? v0.z : 0) + (oy > 3 ? v0.w : 0);
     pos += (oy > 4 ? v1.x : 0) + (oy > 5 ? v1.y : 0) + (oy > 6 ? v1.z : 0) + (oy > 7 ? v1.w : 0);
     rows[pos] = rec;
@@ -253,17 +266,16 @@ tc_bin_scatter_kernel(TcGeom G, const float* __restrict__ coords, const int64_t*
     const int k = pos - rs;
     if ((k & (kTcRows - 1)) == 0) {
       const int total = tot[tile];
-      const int64_t jf = tc_mod(jj[e], fmod);
       TcHdr h;
       h.nrows = min(kTcRows, total - k);
       h.rbase = pos;
       h.lvl = lvl;
       h.f = (int)jf;
-      h.X0 = ((int)fxf - kTcR + kTcWin) / kTcStep * kTcStep - kTcWin;
-      h.Y0 = ((int)fyf - kTcR + kTcWin) / kTcStep * kTcStep - kTcWin;
+      h.X0 = tx * kTcStep - kTcWin;
+      h.Y0 = ty * kTcStep - kTcWin;
       h.flags = (k > 0 ? 1 : 0) | (k + kTcRows < total ? 2 : 0);
       h.pad1 = 0;
-      hdr[blkstart[tile] + k / kTcRows] = h;
+      hdr[bfirst_s[tile / per] + b_s[tile] + k / kTcRows] = h;
     }
   }
 }
@@ -325,11 +337,22 @@ __device__ __forceinline__ int tma_block(int i) {
   return ((int)blockIdx.x + (i >> kChunkLog2) * (int)gridDim.x) * kChunk + (i & (kChunk - 1));
 }
 
-// row of a block that lives in TMEM lane (quadrant q, lane l): row r sits in lane r (fewest partially
-// filled warps — the epilogue is instruction-bound); odd blocks of a CTA's schedule (rot = 1) are rotated
-// by 64 lanes, so that the half-empty level-1 blocks load the four schedulers evenly (lane quadrant ==
-// scheduler: even blocks fill quadrants 0,1 first, odd blocks 2,3).
+// row of a block that lives in TMEM lane (quadrant q, lane l).
+//   more than 64 rows: row r sits in lane r (fewest partially filled warps — the epilogue is instruction-bound); odd
+//     blocks of a CTA's schedule (rot = 1) are rotated by 64 lanes, so that partly filled blocks load the four
+//     schedulers evenly (lane quadrant == scheduler: even blocks fill quadrants 0,1 first, odd blocks 2,3);
+//   at most 64 rows (the typical level-1 block, ~52 rows): every row sits in TWO lanes, r and r + 64 — the M = 128
+//     MMA computes the copy for free — and the epilogue warps of quadrants q and q + 2 each take half of the
+//     accumulator rows the windows cover.  The epilogue of a block is a latency chain of one warp per quadrant
+//     (measured 2 500-3 000 cycles for a 26-row warp against 1 350 for the block's MMAs, and the two-deep
+//     accumulator ring makes the MMAs of block i + 2 wait for it); halving the chain on otherwise idle
+//     schedulers is what shortens the period.
+constexpr int kTcDupRows = 64;
 __device__ __forceinline__ int tma_row_of(int q, int l, int nrows, int rot) {
+  if (nrows <= kTcDupRows) {
+    const int r = (q * 32 + l) & 63;
+    return r < nrows ? r : -1;
+  }
   const int r = (q * 32 + l + 64 * rot) & 127;
   return r < nrows ? r : -1;
 }
@@ -599,8 +622,24 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
         float hprev[7];
 #pragma unroll
         for (int k = 0; k < 7; k++) hprev[k] = 0.f;
+        // accumulator rows w_lo .. w_hi in trips of two; a block of duplicated rows (tma_row_of) is split between the
+        // warps of quadrants q and q + 2: the second one starts from the blended row just above its first trip
+        int w_lo = (lo + a_first) & ~1, w_hi = hi + a_last;
+        if (B.nrows <= kTcDupRows) {
+          const int trips = ((w_hi - w_lo) >> 1) + 1, first = (trips + 1) >> 1;
+          if (q < 2) {
+            w_hi = w_lo + 2 * first - 1;
+          } else {
+            w_lo += 2 * first;
+            if (w_lo <= w_hi && !(dbg & 1)) {
+              float v[16];
+              tmem_ld16(tlane + (w_lo - 1) * kTcTile, v);
+              epi_hrow(v, p8, p4, w, hprev);
+            }
+          }
+        }
 #pragma unroll 1
-        for (int wy = (lo + a_first) & ~1; wy <= hi + a_last; wy += 2) {   // accumulator rows wy, wy + 1
+        for (int wy = w_lo; wy <= w_hi; wy += 2) {                 // accumulator rows wy, wy + 1
           float v[32];
           tmem_ld32(tlane + wy * kTcTile, v);
           if (dbg & 1) continue;
@@ -634,7 +673,7 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
 // ------------------------------------------------------------------ host ----
 
 struct TcWs {
-  int32_t *cnt, *tot, *rowstart, *blkstart, *total, *rowbin, *rowrank;
+  int32_t *cnt, *cursor, *tot, *total;
   TcRow* rows;
   TcHdr* hdr;
   size_t total_bytes;
@@ -649,13 +688,10 @@ static TcWs tc_layout(void* base, int64_t R, int nbins) {
   size_t off = 0;
   auto take = [&](size_t bytes) { char* r = c + off; off += al256(bytes ? bytes : 4); return r; };
   w.maxblocks = R / kTcRows + nbins + 1;
-  w.cnt = (int32_t*)take((size_t)nbins * kTcSub * 4);   // cnt and tot are adjacent: one memset
+  w.cnt = (int32_t*)take((size_t)nbins * kTcSub * 4);   // cnt, cursor and tot are adjacent: one memset
+  w.cursor = (int32_t*)take((size_t)nbins * kTcSub * 4);
   w.tot = (int32_t*)take((size_t)nbins * 4);
-  w.rowstart = (int32_t*)take((size_t)(nbins + 1) * 4);
-  w.blkstart = (int32_t*)take((size_t)(nbins + 1) * 4);
   w.total = (int32_t*)take(16);
-  w.rowbin = (int32_t*)take((size_t)R * 4);
-  w.rowrank = (int32_t*)take((size_t)R * 4);
   w.rows = (TcRow*)take((size_t)R * sizeof(TcRow));
   w.hdr = (TcHdr*)take((size_t)w.maxblocks * sizeof(TcHdr));
   w.total_bytes = off;
@@ -749,21 +785,20 @@ extern "C" int rvo_corr_tiles(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, co
   RVO_CHECK_ARG((int64_t)w.total_bytes <= ws_bytes, "rvo_corr_tiles: workspace %lld < %lld bytes",
                 (long long)ws_bytes, (long long)w.total_bytes);
   cudaStream_t st = (cudaStream_t)stream;
-  RVO_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)((char*)w.tot - (char*)w.cnt) + (size_t)G.nbins * 4, st));   // cnt + tot
+  RVO_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)((char*)w.total - (char*)w.cnt), st));   // cnt + cursor + tot: one memset
   RVO_CHECK_ARG(G.nbins <= kScanMaxBins, "rvo_corr_tiles: %d tiles exceed the scan capacity", G.nbins);
-  int grid = (int)((R + 255) / 256);
-  if (grid > sm_budget() * 16) grid = sm_budget() * 16;
-  tc_bin_count_kernel<<<(int)(((int64_t)E * nlevels + 255) / 256), 256, 0, st>>>(G, coords, kk, jj, pmod, fmod, fmap1->N, E,
-                                                                                  w.cnt, w.tot, w.rowbin, w.rowrank,
-                                                                                  (__half*)out, out_ld);
+  const int64_t T = (int64_t)E * nlevels;
+  tc_bin_count_kernel<<<(int)((T + 255) / 256), 256, 0, st>>>(G, coords, kk, jj, pmod, fmod, fmap1->N, E, w.cnt, w.tot);
   RVO_LAUNCH_CHECK("tc_bin_count_kernel");
-  RVO_CUDA(cudaFuncSetAttribute(tc_bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                kScanMaxBins * 6 + 4096));
-  tc_bin_scan_kernel<<<1, 1024, (size_t)G.nbins * 6 + 4096, st>>>(w.tot, G.nbins, w.rowstart, w.blkstart, w.total);
-  RVO_LAUNCH_CHECK("tc_bin_scan_kernel");
-  tc_bin_scatter_kernel<<<grid, 256, 0, st>>>(G, coords, kk, jj, pmod, fmod, fmap1->sN, fmap1->sH, fmap1->sW,
-                                              out_ld, R, w.rowbin, w.rowrank, w.rowstart, w.blkstart, w.cnt, w.tot, w.rows,
-                                              w.hdr);
+  // scatter pass, every CTA with its own copy of the scanned tile table in shared memory
+  const size_t scan_smem = (size_t)G.nbins * 6 + (size_t)kScatterThreads * 4 + 64;
+  RVO_CUDA(cudaFuncSetAttribute(tc_bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kScanMaxBins * 6 + kScatterThreads * 4 + 64));
+  int grid = sm_budget() * (scan_smem <= 100 * 1024 ? 2 : 1);         // two CTAs per SM while the table allows it
+  if ((int64_t)grid * kScatterThreads > R) grid = (int)((R + kScatterThreads - 1) / kScatterThreads);
+  tc_bin_scatter_kernel<<<grid, kScatterThreads, scan_smem, st>>>(G, coords, kk, jj, pmod, fmod, fmap1->N, fmap1->sN,
+                                                                fmap1->sH, fmap1->sW, out_ld, R, w.cnt, w.tot, w.cursor,
+                                                                w.rows, w.hdr, w.total, (__half*)out);
   RVO_LAUNCH_CHECK("tc_bin_scatter_kernel");
 #ifdef RVO_DEBUG
   const char* dbg_s = getenv("RVO_CORR_DBG");      // debugging aid: see the kernel's dbg bits
