@@ -258,11 +258,16 @@ def run_ours(args):
             E_dev = int(vo.ii.numel())
         # roofline of the dominant hand-written kernel (altcorr lookup), timed live on this stream
         coords = vo.reproject()
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+        # cold L2 before every timed launch: 256 MB (> 126 MB L2) written, then 256 MB of a second buffer read, so that
+        # the L2 is left full of CLEAN foreign lines — after a bare memset the timed kernels would also pay for the
+        # write-back of the flusher's dirty lines (~10 us per kernel, profiles/r01_kernel_experiments.md)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        flush_r = torch.zeros(64 << 20, dtype=torch.int32, device=dev)
         out = vo.corr_tiles(coords)
         ts = []
         for _ in range(10):
             flush.zero_()
+            flush_r.max()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             vo.corr_tiles(coords)
@@ -277,7 +282,7 @@ def run_ours(args):
         alg = E * 882 * 2 + E * (18 * 4 + 16) + U * 128 * 9 * 2
         for (h, w) in ((120, 160), (30, 40)):
             alg += min(Fr * 128 * h * w * 2, E * 100 * 128 * 2)
-        del out, flush
+        del out, flush, flush_r
         stages_ours = our_stages(vo, frames) if (rank == 0 and world == 1 and args.config == "default") else None
         state["sd"] = {k: v.detach().clone() for k, v in vo.network.state_dict().items()}
 
@@ -309,7 +314,8 @@ def run_ours(args):
                    "pipeline": "encoder graph of frame t+1 runs on its own stream while the update graph / keyframe "
                                "step of frame t finish (Ramp_vo pipeline=True); e2e: the pose of every frame is copied "
                                "D->H into a 2-deep pinned ring and consumed one frame later",
-                   "l2": "per-step working set (167 MB feature rings + 80 MB corr volume) exceeds the 126 MB L2",
+                   "l2": "per-step working set (167 MB feature rings + 80 MB corr volume) exceeds the 126 MB L2; roofline "
+                         "launches: L2 flushed before each (256 MB written, then 256 MB of another buffer read)",
                    "parallelism": par, "poses_finite": finite},
         "e2e": {"value": fps_e2e, "unit": UNIT,
                 "h2d_bytes_per_step": int(host[0][0].numel() * 4 + host[0][1].numel() * 4),
@@ -317,7 +323,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": "altcorr lookup, both pyramid levels: corr_tile_tma_kernel (tcgen05/TMEM, TMA "
-                               "tile loads) incl. its 3 binning passes", "bound": "hbm",
+                               "tile loads) incl. its 2 binning passes and their memset (the whole rvo_corr_tiles call)", "bound": "hbm",
                      "achieved": alg / corr_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": alg / corr_s / 1e9 / peaks["hbm_gbs"], "traffic": traffic,
                      "peak_source": which, "algorithmic_bytes": alg, "launch_us": corr_s * 1e6},

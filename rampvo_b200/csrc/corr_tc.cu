@@ -143,8 +143,9 @@ tc_bin_count_kernel(TcGeom G, const float* __restrict__ coords, const int64_t* _
 }
 
 struct __align__(16) TcHdr {
-  int nrows, rbase, lvl, f, X0, Y0, flags, pad1;   // flags: bit 0 = same tile as the previous block, bit 1 = as the next
-};
+  int nrows, rbase, lvl, f, X0, Y0, flags, oy_max;   // flags: bit 0 = same tile as the previous block, bit 1 = as the
+};                                                   // next, bits 8.. = smallest window-origin row of the block's rows;
+                                                     // oy_max = the largest (written by the block's LAST row)
 
 // everything the tile kernel needs to know about a row, written in bin order by the scatter pass so
 // that the main kernel does one coalesced 32-byte load per row instead of a chain of dependent loads
@@ -176,8 +177,8 @@ tc_bin_scatter_kernel(TcGeom G, const float* __restrict__ coords, const int64_t*
   extern __shared__ int32_t scan_sm[];
   const int nbins = G.nbins;
   int32_t* bfirst_s = scan_sm;                               // [threads] first block of the thread's first tile
-  int32_t* r_s = scan_sm + kScatterThreads;                  // [nbins] row totals -> first row of the tile
-  uint16_t* b_s = reinterpret_cast<uint16_t*>(r_s + nbins);  // [nbins] first block, relative to bfirst_s
+  int32_t* r_s = scan_sm + kScatterThreads;                  // [nbins + 1] row totals -> first row of the tile
+  uint16_t* b_s = reinterpret_cast<uint16_t*>(r_s + nbins + 1);   // [nbins] first block, relative to bfirst_s
   for (int b = threadIdx.x; b < nbins; b += kScatterThreads) r_s[b] = tot[b];
   __syncthreads();
   // thread t owns tiles t*per .. t*per + per - 1
@@ -190,9 +191,10 @@ tc_bin_scatter_kernel(TcGeom G, const float* __restrict__ coords, const int64_t*
       nrow += c;
       blks += (c + kTcRows - 1) / kTcRows;
     }
-    int rpre, bpre, btot;
-    Scan(tmp_r).ExclusiveSum(nrow, rpre);
+    int rpre, bpre, rtot, btot;
+    Scan(tmp_r).ExclusiveSum(nrow, rpre, rtot);
     Scan(tmp_b).ExclusiveSum(blks, bpre, btot);
+    if (threadIdx.x == 0) r_s[nbins] = rtot;
     if (blockIdx.x == 0 && threadIdx.x == 0) total_blocks[0] = btot;
     // in place: counts -> exclusive row offsets; block offsets relative to the thread's first block fit 16 bits
     bfirst_s[threadIdx.x] = bpre;
@@ -208,7 +210,6 @@ tc_bin_scatter_kernel(TcGeom G, const float* __restrict__ coords, const int64_t*
     }
   }
   __syncthreads();
-
   const int NL = G.nlevels;
   const int Ri = (int)R;                                     // < 2^31 (checked on the host)
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < Ri; r += gridDim.x * blockDim.x) {
@@ -264,19 +265,18 @@ tc_bin_scatter_kernel(TcGeom G, const float* __restrict__ coords, const int64_t*
     rows[pos] = rec;
     // the row that opens a 128-row block of its tile also writes the block's header
     const int k = pos - rs;
+    const int total = r_s[tile + 1] - rs;
     if ((k & (kTcRows - 1)) == 0) {
-      const int total = tot[tile];
-      TcHdr h;
-      h.nrows = min(kTcRows, total - k);
-      h.rbase = pos;
-      h.lvl = lvl;
-      h.f = (int)jf;
-      h.X0 = tx * kTcStep - kTcWin;
-      h.Y0 = ty * kTcStep - kTcWin;
-      h.flags = (k > 0 ? 1 : 0) | (k + kTcRows < total ? 2 : 0);
-      h.pad1 = 0;
-      hdr[bfirst_s[tile / per] + b_s[tile] + k / kTcRows] = h;
+      // (field by field: oy_max of the same header belongs to another thread)
+      int* h = reinterpret_cast<int*>(hdr + (bfirst_s[tile / per] + b_s[tile] + k / kTcRows));
+      *reinterpret_cast<int4*>(h) = make_int4(min(kTcRows, total - k), pos, lvl, (int)jf);
+      *reinterpret_cast<int2*>(h + 4) = make_int2(tx * kTcStep - kTcWin, ty * kTcStep - kTcWin);
+      h[6] = (k > 0 ? 1 : 0) | (k + kTcRows < total ? 2 : 0) | (oy << 8);
     }
+    // rows of a block are ordered by oy: its last row knows the largest one, which bounds the accumulator rows
+    // (= MMA N) the block needs
+    if ((k & (kTcRows - 1)) == kTcRows - 1 || k == total - 1)
+      reinterpret_cast<int*>(hdr + (bfirst_s[tile / per] + b_s[tile] + k / kTcRows))[7] = oy;
   }
 }
 
@@ -292,7 +292,7 @@ __device__ __forceinline__ TcHdr ld_hdr(const TcHdr* __restrict__ hdr, int b) {
   const uint4 a = p[0], c = p[1];
   TcHdr h;
   h.nrows = (int)a.x; h.rbase = (int)a.y; h.lvl = (int)a.z; h.f = (int)a.w;
-  h.X0 = (int)c.x; h.Y0 = (int)c.y; h.flags = (int)c.z; h.pad1 = 0;
+  h.X0 = (int)c.x; h.Y0 = (int)c.y; h.flags = (int)c.z; h.oy_max = (int)c.w;
   return h;
 }
 
@@ -307,8 +307,8 @@ __device__ __forceinline__ TcHdr ld_hdr(const TcHdr* __restrict__ hdr, int b) {
 //             SWIZZLE_128B lands exactly in the UMMA canonical layout, and out-of-map positions
 //             (negative coordinates included) are zero-filled by the hardware.  A tile is loaded
 //             ONCE for all consecutive row blocks that share it (level 2 has ~5 blocks per tile);
-//   chunks    a CTA takes chunks of kChunk consecutive blocks (so tile sharing survives the
-//             persistent schedule) strided by the grid;
+//   chunks    a CTA takes chunks of consecutive blocks (so tile sharing survives the persistent
+//             schedule) strided by the grid, 8 or 2 blocks long (tma_block);
 //   A rows    two producer groups (4 warps each, alternate blocks) gather the 128 patch-pixel
 //             vectors with cp.async into a 3-stage ring: the gather of block i starts when the MMAs
 //             of block i - 3 have retired;
@@ -321,8 +321,6 @@ __device__ __forceinline__ TcHdr ld_hdr(const TcHdr* __restrict__ hdr, int b) {
 //             per-thread x offset is applied by 19 selects for its high bits and a 5-tap blend for the
 //             low bits — the half-rate ALU pipe (FSEL) is what bounds the epilogue, so work is moved to
 //             the FMA pipe — followed by the vertical blend and the fp16 pack.
-constexpr int kChunkLog2 = 3;
-constexpr int kChunk = 1 << kChunkLog2;
 constexpr int kTmaThreads = 640;              // warps 0-7 A producers, 8 TMA, 9 MMA, 12-19 epilogue
 constexpr int kTmaTmaWarp = 8;
 constexpr int kTmaMmaWarp = 9;
@@ -332,9 +330,14 @@ constexpr int kTmaOffB = 0;                   // 2 x 64 KB
 constexpr int kTmaOffA = 2 * kTcSmemB;        // 3 x 32 KB
 constexpr int kTmaSmemBytes = kTmaOffA + kTmaAStages * kTcSmemA + 1024;
 
+// Persistent schedule: a CTA takes chunks of 2^CL consecutive blocks, strided by the grid.  A chunk keeps the blocks
+// of one tile together (its features are loaded once per run of blocks), which pays when the tiles hold several
+// blocks each (precise.yaml: chunks of 8, 836 vs 849 us); with about one block per level-1 tile (default.yaml) short
+// chunks mix cheap and expensive blocks evenly over the CTAs instead (chunks of 2: 95 vs 101 us).  The host picks.
 // block index of the i-th block of this CTA's schedule
+template <int CL>
 __device__ __forceinline__ int tma_block(int i) {
-  return ((int)blockIdx.x + (i >> kChunkLog2) * (int)gridDim.x) * kChunk + (i & (kChunk - 1));
+  return (((int)blockIdx.x + (i >> CL) * (int)gridDim.x) << CL) + (i & ((1 << CL) - 1));
 }
 
 // row of a block that lives in TMEM lane (quadrant q, lane l).
@@ -402,6 +405,7 @@ __device__ __forceinline__ uint4 epi_pack(const float (&h0)[7], const float (&h1
 __device__ long long g_tc_trace[8 * 256];
 #define TC_TRACE(slot, i) do { if ((dbg & 16) && blockIdx.x == 0 && (i) < 256) g_tc_trace[(slot) * 256 + (i)] = clock64(); } while (0)
 
+template <int CL>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__ TcTmap tm1,
                      const __half* __restrict__ gmap, const TcHdr* __restrict__ hdr,
@@ -457,19 +461,19 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
     const int my_q = ptid >> 5, my_l = ptid & 31;             // the M slot whose source this thread fetches
     TcHdr H1, H2;
     int src_n = -1;
-    if (tma_block(pg) < nblk) {
-      H1 = ld_hdr(hdr, tma_block(pg));
+    if (tma_block<CL>(pg) < nblk) {
+      H1 = ld_hdr(hdr, tma_block<CL>(pg));
       const int r = tma_row_of(my_q, my_l, H1.nrows, pg);
       if (r >= 0) src_n = (int)rows[H1.rbase + r].src;
     }
-    if (tma_block(pg + 2) < nblk) H1 = ld_hdr(hdr, tma_block(pg + 2));
+    if (tma_block<CL>(pg + 2) < nblk) H1 = ld_hdr(hdr, tma_block<CL>(pg + 2));
     for (int i = pg;; i += 2) {
-      const int b = tma_block(i);
+      const int b = tma_block<CL>(i);
       if (b >= nblk) break;
       const int my_src = src_n;
       src_n = -1;
-      if (tma_block(i + 4) < nblk) H2 = ld_hdr(hdr, tma_block(i + 4));
-      if (tma_block(i + 2) < nblk) {
+      if (tma_block<CL>(i + 4) < nblk) H2 = ld_hdr(hdr, tma_block<CL>(i + 4));
+      if (tma_block<CL>(i + 2) < nblk) {
         const int r = tma_row_of(my_q, my_l, H1.nrows, pg);
         if (r >= 0) src_n = (int)rows[H1.rbase + r].src;
       }
@@ -503,13 +507,13 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
     if (lane == 0) {
       int ib = 0;
       TcHdr Hn;
-      if (tma_block(0) < nblk) Hn = ld_hdr(hdr, tma_block(0));
+      if (tma_block<CL>(0) < nblk) Hn = ld_hdr(hdr, tma_block<CL>(0));
       for (int i = 0;; i++) {
-        const int b = tma_block(i);
+        const int b = tma_block<CL>(i);
         if (b >= nblk) break;
         const TcHdr B = Hn;
-        if (tma_block(i + 1) < nblk) Hn = ld_hdr(hdr, tma_block(i + 1));
-        const bool newB = (i & (kChunk - 1)) == 0 || !(B.flags & 1);
+        if (tma_block<CL>(i + 1) < nblk) Hn = ld_hdr(hdr, tma_block<CL>(i + 1));
+        const bool newB = (i & ((1 << CL) - 1)) == 0 || !(B.flags & 1);
         if (!newB) continue;
         const int s = ib & 1;
         mbar_wait(&bempty[s], ((ib >> 1) & 1) ^ 1);
@@ -526,48 +530,54 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
       }
     }
   } else if (warp == kTmaMmaWarp) {
-    // ===== MMA issuer =====
-    int ib = -1;
-    TcHdr Hn;
-    if (tma_block(0) < nblk) Hn = ld_hdr(hdr, tma_block(0));
-    int sa = 0, pa = 0;
-    for (int i = 0;; i++) {
-      const int b = tma_block(i);
-      if (b >= nblk) break;
-      const TcHdr B = Hn;
-      if (tma_block(i + 1) < nblk) Hn = ld_hdr(hdr, tma_block(i + 1));
-      const bool newB = (i & (kChunk - 1)) == 0 || !(B.flags & 1);
-      const bool lastB = (i & (kChunk - 1)) == kChunk - 1 || !(B.flags & 2);
-      if (lane == 0) TC_TRACE(2, i);
-      if (newB) {
-        ib++;
-        mbar_wait_spin(&bfull[ib & 1], (ib >> 1) & 1);
-      }
-      const int st = i & 1, sb = ib & 1;
-      mbar_wait_spin(&afull[sa], pa);
-      mbar_wait_spin(&tempty[st], ((i >> 1) & 1) ^ 1);
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // A rows: cp.async writes -> tensor-core reads
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      if (lane == 0) TC_TRACE(3, i);
-      if (lane == 0) {
+    // ===== MMA issuer: ONE thread runs the whole loop (the other lanes of the warp go straight to the final barrier).
+    // The tensor pipe executes an M128 N256 K16 step at its 128-cycle floor, but its queue is shallow — the thread is
+    // blocked in the issue of a block until the previous block's steps have executed — so whatever the thread spends
+    // between two blocks (barrier waits, fences, warp re-convergence) leaves the pipe idle. =====
+    if (lane == 0) {
+      int ib = -1;
+      TcHdr Hn;
+      if (tma_block<CL>(0) < nblk) Hn = ld_hdr(hdr, tma_block<CL>(0));
+      int sa = 0, pa = 0;
+      for (int i = 0;; i++) {
+        const int b = tma_block<CL>(i);
+        if (b >= nblk) break;
+        const TcHdr B = Hn;
+        if (tma_block<CL>(i + 1) < nblk) Hn = ld_hdr(hdr, tma_block<CL>(i + 1));
+        const bool newB = (i & ((1 << CL) - 1)) == 0 || !(B.flags & 1);
+        const bool lastB = (i & ((1 << CL) - 1)) == (1 << CL) - 1 || !(B.flags & 2);
+        TC_TRACE(2, i);
+        // descriptors before the waits: nothing but the MMAs themselves follows the last barrier.  One descriptor per
+        // stage, advanced by constants (the address field counts 16-byte units and cannot carry out of its 14 bits
+        // below 256 KB).  Only the tile rows the block's windows cover are computed (rows are ordered by
+        // window-origin row): accumulator column 0 is tile row wbase, N = 16 positions per covered row.
+        if (newB) ib++;
+        const int st = i & 1, sb = ib & 1;
         const uint32_t As_u = smem_u32(smem + kTmaOffA + sa * kTcSmemA);
         const uint32_t Bs_u = smem_u32(smem + kTmaOffB + sb * kTcSmemB);
-        // one descriptor per stage, advanced by constants (the address field counts 16-byte units and
-        // cannot carry out of its 14 bits below 256 KB): the issuing thread is the critical path
-        const uint64_t da0 = umma_desc(As_u), db0 = umma_desc(Bs_u);
+        const int wbase = (B.flags >> 8) & ~1;
+        const int nt = B.oy_max + kTcWin - wbase;
+        const uint64_t da0 = umma_desc(As_u), db0 = umma_desc(Bs_u + wbase * (kTcTile * 128));
+        const uint32_t idesc = umma_idesc_f16(128, nt * kTcTile);
+        const uint32_t dcol = tmem_base + st * 256;
+        mbar_wait_spin(&tempty[st], ((i >> 1) & 1) ^ 1);
+        if (newB) mbar_wait_spin(&bfull[sb], (ib >> 1) & 1);
+        mbar_wait_spin(&afull[sa], pa);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // A rows: cp.async writes -> tensor-core reads
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        TC_TRACE(3, i);
 #pragma unroll
         for (int kb = 0; kb < 2; kb++)
 #pragma unroll
           for (int k = 0; k < 4; k++)
-            umma_f16(tmem_base + st * 256, da0 + (uint64_t)((kb * (kTcRows * 128) + k * 32) >> 4),
-                     db0 + (uint64_t)((kb * (256 * 128) + k * 32) >> 4), umma_idesc_f16(128, 256), (kb | k) ? 1u : 0u);
+            umma_f16(dcol, da0 + (uint64_t)((kb * (kTcRows * 128) + k * 32) >> 4),
+                     db0 + (uint64_t)((kb * (256 * 128) + k * 32) >> 4), idesc, (kb | k) ? 1u : 0u);
         umma_commit(&aempty[sa]);
         umma_commit(&tfull[st]);
         if (lastB) umma_commit(&bempty[sb]);
         TC_TRACE(4, i);
+        if (++sa == kTmaAStages) { sa = 0; pa ^= 1; }
       }
-      __syncwarp();
-      if (++sa == kTmaAStages) { sa = 0; pa ^= 1; }
     }
   } else if (warp >= kTmaEpiWarp0) {
     // ===== epilogue: accumulator g, TMEM lane quadrant q; this group's blocks are i = g, g + 2, ... =====
@@ -579,21 +589,21 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
     const uint32_t tlane = tmem_base + g * 256 + ((uint32_t)(q * 32) << 16);
     TcHdr B, H1, H2;                                          // headers of blocks i, i + 2, i + 4
     uint4 r0n = make_uint4(0, 0, 0, 0), r1n = make_uint4(0, 0, 0, 0);
-    if (tma_block(g) < nblk) {
-      B = ld_hdr(hdr, tma_block(g));
+    if (tma_block<CL>(g) < nblk) {
+      B = ld_hdr(hdr, tma_block<CL>(g));
       const int r = tma_row_of(q, lane, B.nrows, g);
       if (r >= 0) {
         const uint4* rp = reinterpret_cast<const uint4*>(rows + B.rbase + r);
         r0n = rp[0]; r1n = rp[1];
       }
     }
-    if (tma_block(g + 2) < nblk) H1 = ld_hdr(hdr, tma_block(g + 2));
+    if (tma_block<CL>(g + 2) < nblk) H1 = ld_hdr(hdr, tma_block<CL>(g + 2));
     for (int i = g;; i += 2) {
-      const int b = tma_block(i);
+      const int b = tma_block<CL>(i);
       if (b >= nblk) break;
       const uint4 r0 = r0n, r1 = r1n;
-      if (tma_block(i + 4) < nblk) H2 = ld_hdr(hdr, tma_block(i + 4));
-      if (tma_block(i + 2) < nblk) {                         // next own block's row record in flight
+      if (tma_block<CL>(i + 4) < nblk) H2 = ld_hdr(hdr, tma_block<CL>(i + 4));
+      if (tma_block<CL>(i + 2) < nblk) {                         // next own block's row record in flight
         const int r = tma_row_of(q, lane, H1.nrows, g);
         if (r >= 0) {
           const uint4* rp = reinterpret_cast<const uint4*>(rows + H1.rbase + r);
@@ -624,6 +634,7 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
         for (int k = 0; k < 7; k++) hprev[k] = 0.f;
         // accumulator rows w_lo .. w_hi in trips of two; a block of duplicated rows (tma_row_of) is split between the
         // warps of quadrants q and q + 2: the second one starts from the blended row just above its first trip
+        const int wbase = (B.flags >> 8) & ~1;              // accumulator column 0 = tile row wbase (see the MMA issuer)
         int w_lo = (lo + a_first) & ~1, w_hi = hi + a_last;
         if (B.nrows <= kTcDupRows) {
           const int trips = ((w_hi - w_lo) >> 1) + 1, first = (trips + 1) >> 1;
@@ -633,7 +644,7 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
             w_lo += 2 * first;
             if (w_lo <= w_hi && !(dbg & 1)) {
               float v[16];
-              tmem_ld16(tlane + (w_lo - 1) * kTcTile, v);
+              tmem_ld16(tlane + (w_lo - 1 - wbase) * kTcTile, v);
               epi_hrow(v, p8, p4, w, hprev);
             }
           }
@@ -641,7 +652,7 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
 #pragma unroll 1
         for (int wy = w_lo; wy <= w_hi; wy += 2) {                 // accumulator rows wy, wy + 1
           float v[32];
-          tmem_ld32(tlane + wy * kTcTile, v);
+          tmem_ld32(tlane + (wy - wbase) * kTcTile, v);
           if (dbg & 1) continue;
           // one basic block for both rows (values are computed unconditionally, only the stores are
           // predicated), so the selects (ALU), blends (FMA) and conversions of independent rows interleave
@@ -791,7 +802,7 @@ extern "C" int rvo_corr_tiles(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, co
   tc_bin_count_kernel<<<(int)((T + 255) / 256), 256, 0, st>>>(G, coords, kk, jj, pmod, fmod, fmap1->N, E, w.cnt, w.tot);
   RVO_LAUNCH_CHECK("tc_bin_count_kernel");
   // scatter pass, every CTA with its own copy of the scanned tile table in shared memory
-  const size_t scan_smem = (size_t)G.nbins * 6 + (size_t)kScatterThreads * 4 + 64;
+  const size_t scan_smem = (size_t)(G.nbins + 1) * 6 + (size_t)kScatterThreads * 4 + 64;
   RVO_CUDA(cudaFuncSetAttribute(tc_bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kScanMaxBins * 6 + kScatterThreads * 4 + 64));
   int grid = sm_budget() * (scan_smem <= 100 * 1024 ? 2 : 1);         // two CTAs per SM while the table allows it
@@ -812,9 +823,13 @@ extern "C" int rvo_corr_tiles(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, co
     rc = tc_make_tmap(G.lv[l], &tm[l]);
     if (rc != RVO_OK) return rc;
   }
-  RVO_CUDA(cudaFuncSetAttribute(corr_tile_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
-  corr_tile_tma_kernel<<<sm_budget(), kTmaThreads, kTmaSmemBytes, st>>>(tm[0], tm[1], (const __half*)fmap1->data,
-                                                                    w.hdr, w.rows, w.total, (__half*)out, dbg);
+  // schedule granularity (tma_block): short chunks while the level-1 tiles hold about one 128-row block each
+  const int64_t bins1 = (int64_t)G.lv[0].N * G.lv[0].TX * G.lv[0].TY;
+  const bool short_chunks = (int64_t)E * 9 < 96 * bins1;
+  auto kern = short_chunks ? corr_tile_tma_kernel<1> : corr_tile_tma_kernel<3>;
+  RVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
+  kern<<<sm_budget(), kTmaThreads, kTmaSmemBytes, st>>>(tm[0], tm[1], (const __half*)fmap1->data, w.hdr, w.rows, w.total,
+                                                       (__half*)out, dbg);
   RVO_LAUNCH_CHECK("corr_tile_tma_kernel");
   return RVO_OK;
 }
