@@ -256,6 +256,14 @@ def run_ours(args):
             gi, gj, gk = _s.replay_graph(M_, life, rem, vo.n)
             vo.ii, vo.jj, vo.kk = [torch.from_numpy(x).to(dev) for x in (gi, gj, gk)]
             E_dev = int(vo.ii.numel())
+        # context block, run BEFORE the graph captures below (torch.cuda.graph empties the caching allocator on entry;
+        # measured right after them this block dropped from ~470 to ~220 frames/s)
+        kf_block = None
+        if rank == 0 and world == 1 and args.config == "default" and not args.no_keyframe_path:
+            try:
+                kf_block = keyframe_path_block(frames, intr, dev, min(K, 100))
+            except Exception as e:
+                kf_block = {"unavailable": "%s: %s" % (type(e).__name__, e)}
         # roofline of the dominant hand-written kernel (altcorr lookup), timed live on this stream
         coords = vo.reproject()
         # cold L2 before every timed launch: 256 MB (> 126 MB L2) written, then 256 MB of a second buffer read, so that
@@ -264,13 +272,21 @@ def run_ours(args):
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         flush_r = torch.zeros(64 << 20, dtype=torch.int32, device=dev)
         out = vo.corr_tiles(coords)
+        # the call is timed the way the frame runs it: as a captured CUDA graph (memset + 2 binning kernels + tile
+        # kernel back to back).  Launched eagerly from Python, the host needs longer for the call (workspace lookup,
+        # two tensor-map encodes, 4 launches: ~150 us) than the GPU does, and the events would time the host.
+        torch.cuda.synchronize()
+        g_corr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_corr):
+            out = vo.corr_tiles(coords)
+        g_corr.replay()
         ts = []
         for _ in range(10):
             flush.zero_()
             flush_r.max()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            vo.corr_tiles(coords)
+            g_corr.replay()
             b.record()
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b) * 1e-3)
@@ -282,7 +298,7 @@ def run_ours(args):
         alg = E * 882 * 2 + E * (18 * 4 + 16) + U * 128 * 9 * 2
         for (h, w) in ((120, 160), (30, 40)):
             alg += min(Fr * 128 * h * w * 2, E * 100 * 128 * 2)
-        del out, flush, flush_r
+        del out, flush, flush_r, g_corr
         stages_ours = our_stages(vo, frames) if (rank == 0 and world == 1 and args.config == "default") else None
         state["sd"] = {k: v.detach().clone() for k, v in vo.network.state_dict().items()}
 
@@ -323,7 +339,8 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": "altcorr lookup, both pyramid levels: corr_tile_tma_kernel (tcgen05/TMEM, TMA "
-                               "tile loads) incl. its 2 binning passes and their memset (the whole rvo_corr_tiles call)", "bound": "hbm",
+                               "tile loads) incl. its 2 binning passes and their memset (the whole rvo_corr_tiles call, replayed as a "
+                               "CUDA graph like in the frame)", "bound": "hbm",
                      "achieved": alg / corr_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": alg / corr_s / 1e9 / peaks["hbm_gbs"], "traffic": traffic,
                      "peak_source": which, "algorithmic_bytes": alg, "launch_us": corr_s * 1e6},
@@ -335,11 +352,8 @@ def run_ours(args):
                                "note": "per rank, since the start of the stream (setup + warm-up + timed frames)"}
     if rank == 0 and world == 1 and stages_ours is not None:
         line["stages"] = stages_ours
-    if rank == 0 and world == 1 and args.config == "default" and not args.no_keyframe_path:
-        try:
-            line["keyframe_path"] = keyframe_path_block(frames, intr, dev, min(K, 100))
-        except Exception as e:
-            line["keyframe_path"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+    if kf_block is not None:
+        line["keyframe_path"] = kf_block
     if rank == 0 and world == 1 and not args.no_ref_gpu and args.config == "default":
         try:
             line["ref_gpu"] = ref_gpu_block(state["sd"], frames, intr, min(K, 20), 3, dev)
@@ -504,8 +518,18 @@ def our_stages(vo, frames):
         g = vo._pgraph
         if g is not None:
             st["patchify_encoder_us"], _ = stage(lambda: g.graph.replay())
-        st["reproject_us"], coords = stage(lambda: vo.reproject())
-        st["corr_us"], cv = stage(lambda: vo.corr_tiles(coords))
+        # reproject and corr are shorter on the GPU than their eager launch sequence is on the host: replayed as
+        # captured graphs (the form they have inside the frame's update graph)
+        coords = vo.reproject()
+        cv = vo.corr_tiles(coords)
+        torch.cuda.synchronize()
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            coords = vo.reproject()
+        with torch.cuda.graph(g2):
+            cv = vo.corr_tiles(coords)
+        st["reproject_us"], _ = stage(lambda: g1.replay())
+        st["corr_us"], _ = stage(lambda: g2.replay())
         plans = vo._graph_plans()
         E = vo.ii.numel()
         other = vo._net_other(E)

@@ -126,6 +126,48 @@ def test_keyframe_drop_matches_a_restatement_of_the_reference(vo_cpu):
     assert sum(vo._pair_counts().values()) == ri.numel()
 
 
+def test_deferred_keyframe_drop_flushes_to_the_same_graph(vo_cpu):
+    """pipeline mode leaves a keyframe drop to the fused patch-graph step of the next frame (rvo_edges_step drop_k):
+    _keyframe_finish(defer_removal=True) only records it (host pair counts already updated); if no new frame comes
+    (sync(), terminate()) the tensor-op path applies it — the graph must equal the one of an immediate drop."""
+    vo = vo_cpu
+    M, life, removal, KI = vo.M, vo.cfg.PATCH_LIFETIME, vo.cfg.REMOVAL_WINDOW, vo.cfg.KEYFRAME_INDEX
+    n = 30
+    ii, jj, kk = (torch.from_numpy(a) for a in synth.replay_graph(M, life, removal, n))
+
+    def reset():
+        vo.n, vo.m = n, n * M
+        vo.ii, vo.jj, vo.kk = ii.clone(), jj.clone(), kk.clone()
+        vo._pair_cnt, vo._min_src = None, 0
+        vo._net_bufs, vo._net_cur = [None, None], 0
+        vo.net = torch.zeros(1, 0, vo.DIM)
+        vo._net_reserve(ii.numel())
+        vo.net = vo._net_bufs[0][:, :ii.numel()]
+        vo.net[0, :, 0] = (kk * 1000 + jj).float()
+        vo.tstamps_[:n] = torch.arange(n)
+        vo.delta = {}
+
+    old_thresh = vo.cfg.KEYFRAME_THRESH
+    vo.cfg.KEYFRAME_THRESH = 1e9
+    try:
+        reset()
+        vo._keyframe_finish([0.0, 1.0, 0.0, 1.0])
+        want = (vo.ii.clone(), vo.jj.clone(), vo.kk.clone(), vo.net[0, :, 0].clone(), dict(vo._pair_counts()), vo.n)
+        reset()
+        vo._keyframe_finish([0.0, 1.0, 0.0, 1.0], defer_removal=True)
+        k = n - KI
+        assert vo._pending_drop == k and vo._pending_lim == vo.n - removal
+        assert torch.equal(vo.ii, ii) and torch.equal(vo.jj, jj)        # the device lists wait for the fused step
+        assert sum(vo._pair_cnt.values()) == int((~((ii == k) | (jj == k))).sum())   # the host counts do not
+        vo.sync()
+    finally:
+        vo.cfg.KEYFRAME_THRESH = old_thresh
+    assert vo._pending_drop == -1 and vo._pending_lim is None and vo.n == want[5]
+    assert torch.equal(vo.ii, want[0]) and torch.equal(vo.jj, want[1]) and torch.equal(vo.kk, want[2])
+    assert torch.equal(vo.net[0, :, 0], want[3])
+    assert vo._pair_counts() == want[4]
+
+
 def _q_mul(a, b):
     ax, ay, az, aw = a
     bx, by, bz, bw = b
