@@ -229,3 +229,47 @@ def test_corr_tiles_full_size_agrees_with_per_edge_kernel():
     b = altcorr.corr_tiles(g_t, p_t, c_t, k_t, j_t, 96 * 32, 32)
     cols, ref = altcorr.tile_layout_index(2)
     assert (a[0][:, ref.cuda()].float() - b[0][:, cols.cuda()].float()).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("case", ["one_tile_one_row", "rows_64", "rows_65", "rows_129", "long_chunks"])
+def test_corr_tiles_block_structure_corners(case):
+    """Inputs built to hit the corners of the tile kernel's block structure (corr_tc.cu): every row in ONE tile with
+    ONE window-origin row (many 128-row blocks whose MMA covers only 8 of the 16 tile rows), tiles holding exactly
+    64 / 65 rows (the limit of the blocks whose rows sit in two TMEM lanes and are split between two epilogue
+    warps), 129 rows (a full block + a 1-row block of the same tile), and a graph large enough for the schedule
+    with 8-block chunks (tile reuse across blocks).  Checked against the float64 oracle and the per-edge kernel."""
+    rng = np.random.default_rng(31)
+    Np, Nf, C, H, W, P = 60, 5, 128, 30, 40, 3
+    E = {"one_tile_one_row": 100, "rows_64": 24, "rows_65": 24, "rows_129": 40, "long_chunks": 2400}[case]
+    gmap, pyr = synth.make_features(Nf, Np, C, H, W, P, seed=31)
+    kk = rng.integers(0, Np, E)
+    jj = rng.integers(0, Nf, E)
+    _, _, coords = _corr_case(rng, E, Np, Nf, C, H, W, P, 1.0)
+    if case == "one_tile_one_row":
+        jj[:] = 2
+        coords[:, 0] = rng.uniform(14.0, 16.9, (E, P, P))       # window origins x0 = 11..13, one level-1 tile column
+        coords[:, 1] = rng.uniform(17.01, 17.99, (E, P, P))     # y0 = 14 for every row: one window-origin row
+    elif case in ("rows_64", "rows_65", "rows_129"):
+        n_in = int(case.split("_")[1])
+        jj[:] = 1
+        coords[:] = 1e6                                          # everything else: outside the maps (zero rows)
+        n = np.arange(n_in)
+        e_, py, px = n // 9, (n % 9) // 3, n % 3
+        coords[e_, 0, py, px] = rng.uniform(13.0, 19.9, n_in)    # tile x index 2 at level 1 (origins 10..16)
+        coords[e_, 1, py, px] = rng.uniform(13.0, 19.9, n_in)    # all nine window-origin rows
+    g_t = torch.from_numpy(gmap).cuda().permute(0, 3, 1, 2)[None]
+    p_t = [torch.from_numpy(p).cuda().permute(0, 3, 1, 2)[None] for p in pyr]
+    c_t = torch.from_numpy(coords).cuda()[None]
+    k_t, j_t = torch.from_numpy(kk).cuda(), torch.from_numpy(jj).cuda()
+    out = altcorr.corr_tiles(g_t, p_t, c_t, k_t, j_t, Np, Nf)
+    cols, ref = altcorr.tile_layout_index(2)
+    got = torch.empty(E, 882, dtype=torch.float16, device="cuda")
+    got[:, ref.cuda()] = out[0][:, cols.cuda()]
+    exp = O.corr_pyramid(gmap.transpose(0, 3, 1, 2), [p.transpose(0, 3, 1, 2) for p in pyr], coords, kk, jj, Np, Nf, 3)
+    g = got.float().cpu().numpy().astype(np.float64)
+    assert np.isfinite(g).all()
+    assert (np.abs(g - exp) <= 2.0 ** -10 * np.abs(exp) + 2e-4).all()
+    if case.startswith("rows_"):
+        assert np.count_nonzero(np.abs(exp).reshape(E, -1).sum(-1)) > 0          # the rows inside the map are live
+    v1 = altcorr.corr_pyramid(g_t, p_t, c_t, k_t, j_t, Np, Nf, 3)
+    assert (v1[0].float() - got.float()).abs().max().item() < 2e-3
