@@ -119,7 +119,8 @@ __device__ __forceinline__ void tc_edge_bins(const TcGeom& G, int lvl, const flo
 __global__ void __launch_bounds__(256)
 tc_bin_count_kernel(TcGeom G, const float* __restrict__ coords, const int64_t* __restrict__ kk,
                     const int64_t* __restrict__ jj, int64_t pmod, int64_t fmod, int64_t gN, int E,
-                    int32_t* __restrict__ cnt, int32_t* __restrict__ tot) {
+                    int32_t* __restrict__ cnt, int32_t* __restrict__ tot, int32_t* __restrict__ rowsub,
+                    int2* __restrict__ edge_pf) {
   const int NL = G.nlevels;
   const int T = E * NL;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
@@ -127,7 +128,13 @@ tc_bin_count_kernel(TcGeom G, const float* __restrict__ coords, const int64_t* _
     const int lvl = t - e * NL;
     TcEdgeBins B;
     float xs[9], ys[9];
-    tc_edge_bins(G, lvl, coords + (int64_t)e * 18, tc_mod(kk[e], pmod), tc_mod(jj[e], fmod), gN, B, xs, ys);
+    const int64_t ip = tc_mod(kk[e], pmod), jf = tc_mod(jj[e], fmod);
+    tc_edge_bins(G, lvl, coords + (int64_t)e * 18, ip, jf, gN, B, xs, ys);
+    // what the row-parallel scatter pass would otherwise recompute per row: the rows' sub-bins and the edge's ring
+    // indices (only read for rows with a sub-bin, whose indices are in range)
+    if (lvl == 0) edge_pf[e] = make_int2((int)ip, (int)jf);
+#pragma unroll
+    for (int pix = 0; pix < 9; pix++) rowsub[(e * 9 + pix) * NL + lvl] = B.sub[pix];
 #pragma unroll
     for (int pix = 0; pix < 9; pix++) {
       if (B.sub[pix] < 0) continue;
@@ -167,11 +174,11 @@ constexpr int kScatterThreads = 1024;
 // inside its sub-bin — first row of the tile + rows of the lower sub-bins + cursor — and the thread writes the row's
 // record there.  The row that opens a 128-row block also writes the block header.
 __global__ void __launch_bounds__(kScatterThreads)
-tc_bin_scatter_kernel(TcGeom G, const float* __restrict__ coords, const int64_t* __restrict__ kk,
-                      const int64_t* __restrict__ jj, int64_t pmod, int64_t fmod, int64_t gN, int64_t g_sN,
-                      int64_t g_sH, int64_t g_sW, int64_t out_ld, int64_t R, const int32_t* __restrict__ cnt,
-                      const int32_t* __restrict__ tot, int32_t* __restrict__ cursor, TcRow* __restrict__ rows,
-                      TcHdr* __restrict__ hdr, int32_t* __restrict__ total_blocks, __half* __restrict__ out) {
+tc_bin_scatter_kernel(TcGeom G, const float* __restrict__ coords, const int32_t* __restrict__ rowsub,
+                      const int2* __restrict__ edge_pf, int g_sN, int g_sH, int g_sW, int64_t out_ld, int64_t R,
+                      const int32_t* __restrict__ cnt, int32_t* __restrict__ cursor, const int32_t* __restrict__ tot,
+                      TcRow* __restrict__ rows, TcHdr* __restrict__ hdr, int32_t* __restrict__ total_blocks,
+                      __half* __restrict__ out) {
   typedef cub::BlockScan<int, kScatterThreads, cub::BLOCK_SCAN_WARP_SCANS> Scan;
   __shared__ typename Scan::TempStorage tmp_r, tmp_b;
   extern __shared__ int32_t scan_sm[];
@@ -213,34 +220,22 @@ tc_bin_scatter_kernel(TcGeom G, const float* __restrict__ coords, const int64_t*
   const int NL = G.nlevels;
   const int Ri = (int)R;                                     // < 2^31 (checked on the host)
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < Ri; r += gridDim.x * blockDim.x) {
-    const int ep = r / NL;
+    const int sub = rowsub[r];
+    const bool ok = sub >= 0;
+    const int ep = NL == 2 ? r >> 1 : r / NL;
     const int lvl = r - ep * NL;
     const int e = ep / 9;
     const int pix = ep - e * 9;
-    const bool l1 = lvl != 0;
-    const float scale = l1 ? G.lv[1].scale : G.lv[0].scale;
-    const int LW = l1 ? G.lv[1].W : G.lv[0].W, LH = l1 ? G.lv[1].H : G.lv[0].H;
-    const int LN = l1 ? G.lv[1].N : G.lv[0].N, TX = l1 ? G.lv[1].TX : G.lv[0].TX;
-    const int TY = l1 ? G.lv[1].TY : G.lv[0].TY, base = l1 ? G.lv[1].binbase : G.lv[0].binbase;
-    const int64_t ip = tc_mod(kk[e], pmod), jf = tc_mod(jj[e], fmod);
-    const float x = coords[(int64_t)e * 18 + pix] * scale;
-    const float y = coords[(int64_t)e * 18 + 9 + pix] * scale;
-    const int x0 = tc_floor(x) - kTcR, y0 = tc_floor(y) - kTcR;
-    const long long out_off = (long long)e * out_ld + (lvl * 9 + pix) * kTcGroup;
-    const bool ok = ip >= 0 && ip < gN && jf >= 0 && jf < LN && x0 > -kTcWin && x0 < LW && y0 > -kTcWin && y0 < LH;
-    const int wx = x0 + kTcWin, wy = y0 + kTcWin;            // > 0 for a valid row
-    const int tx = wx / kTcStep, ty = wy / kTcStep;
-    const int ox = wx - tx * kTcStep, oy = wy - ty * kTcStep;
-    const int tile = base + ((int)jf * TY + ty) * TX + tx;
     // neighbouring lanes are the pixels of one edge and mostly share a sub-bin: one atomic per distinct sub-bin of
     // the warp, its lanes take consecutive slots
     const unsigned act = __activemask();
-    const int sub = ok ? tile * kTcSub + oy : -1 - (int)(threadIdx.x & 31);
-    const unsigned peers = __match_any_sync(act, sub);
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(act, ok ? sub : -1 - (int)lane);
     const int leader = __ffs(peers) - 1;
     int rank = 0;
-    if (ok && (int)(threadIdx.x & 31) == leader) rank = atomicAdd(&cursor[sub], __popc(peers));
-    rank = __shfl_sync(act, rank, leader) + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+    if (ok && (int)lane == leader) rank = atomicAdd(&cursor[sub], __popc(peers));
+    rank = __shfl_sync(act, rank, leader) + __popc(peers & ((1u << lane) - 1u));
+    const long long out_off = (long long)e * out_ld + (lvl * 9 + pix) * kTcGroup;
     if (!ok) {
       // window entirely outside the map (or invalid index): the 7x7 outputs are zero
       uint4* o = reinterpret_cast<uint4*>(out + out_off);
@@ -248,15 +243,23 @@ tc_bin_scatter_kernel(TcGeom G, const float* __restrict__ coords, const int64_t*
       for (int q = 0; q < kTcGroup / 8; q++) o[q] = make_uint4(0u, 0u, 0u, 0u);
       continue;
     }
-    const int4* c4 = reinterpret_cast<const int4*>(cnt) + tile * 3;
-    const int4 v0 = c4[0], v1 = c4[1];
+    const int tile = sub / kTcSub, oy = sub - tile * kTcSub;
+    const float scale = lvl ? G.lv[1].scale : G.lv[0].scale;
+    const float x = coords[e * 18 + pix] * scale;
+    const float y = coords[e * 18 + 9 + pix] * scale;
+    const float fxf = floorf(x), fyf = floorf(y);
+    const int wx = (int)fxf - kTcR + kTcWin, wy = (int)fyf - kTcR + kTcWin;   // > 0: the row has a sub-bin
+    const int ox = wx % kTcStep;
+    const int2 pf = edge_pf[e];
     TcRow rec;
-    rec.src = ip * g_sN + (pix / 3) * g_sH + (pix % 3) * g_sW;
+    rec.src = pf.x * g_sN + (pix / 3) * g_sH + (pix % 3) * g_sW;               // < 2^31 (checked on the host)
     rec.out = out_off;
-    rec.dx = x - floorf(x);
-    rec.dy = y - floorf(y);
+    rec.dx = x - fxf;
+    rec.dy = y - fyf;
     rec.ox = ox;
     rec.oy = oy;
+    const int4* c4 = reinterpret_cast<const int4*>(cnt) + tile * 3;
+    const int4 v0 = c4[0], v1 = c4[1];
     // rows of a tile are ordered by oy: first row of the tile + rows of the lower sub-bins + rank
     const int rs = r_s[tile];
     int pos = rs + rank;
@@ -269,8 +272,8 @@ tc_bin_scatter_kernel(TcGeom G, const float* __restrict__ coords, const int64_t*
     if ((k & (kTcRows - 1)) == 0) {
       // (field by field: oy_max of the same header belongs to another thread)
       int* h = reinterpret_cast<int*>(hdr + (bfirst_s[tile / per] + b_s[tile] + k / kTcRows));
-      *reinterpret_cast<int4*>(h) = make_int4(min(kTcRows, total - k), pos, lvl, (int)jf);
-      *reinterpret_cast<int2*>(h + 4) = make_int2(tx * kTcStep - kTcWin, ty * kTcStep - kTcWin);
+      *reinterpret_cast<int4*>(h) = make_int4(min(kTcRows, total - k), pos, lvl, pf.y);
+      *reinterpret_cast<int2*>(h + 4) = make_int2(wx - ox - kTcWin, wy - oy - kTcWin);
       h[6] = (k > 0 ? 1 : 0) | (k + kTcRows < total ? 2 : 0) | (oy << 8);
     }
     // rows of a block are ordered by oy: its last row knows the largest one, which bounds the accumulator rows
@@ -684,7 +687,8 @@ corr_tile_tma_kernel(const __grid_constant__ TcTmap tm0, const __grid_constant__
 // ------------------------------------------------------------------ host ----
 
 struct TcWs {
-  int32_t *cnt, *cursor, *tot, *total;
+  int32_t *cnt, *cursor, *tot, *total, *rowsub;
+  int2* edge_pf;
   TcRow* rows;
   TcHdr* hdr;
   size_t total_bytes;
@@ -703,6 +707,8 @@ static TcWs tc_layout(void* base, int64_t R, int nbins) {
   w.cursor = (int32_t*)take((size_t)nbins * kTcSub * 4);
   w.tot = (int32_t*)take((size_t)nbins * 4);
   w.total = (int32_t*)take(16);
+  w.rowsub = (int32_t*)take((size_t)R * 4);
+  w.edge_pf = (int2*)take((size_t)(R / 9 + 1) * sizeof(int2));
   w.rows = (TcRow*)take((size_t)R * sizeof(TcRow));
   w.hdr = (TcHdr*)take((size_t)w.maxblocks * sizeof(TcHdr));
   w.total_bytes = off;
@@ -792,6 +798,7 @@ extern "C" int rvo_corr_tiles(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, co
                 "rvo_corr_tiles: output rows need >= %d halves, stride %% 8 == 0, 16-byte alignment", 9 * nlevels * kTcGroup);
   const int64_t R = (int64_t)E * 9 * nlevels;
   RVO_CHECK_ARG(R < 0x7fffffff, "rvo_corr_tiles: too many rows");
+  RVO_CHECK_ARG((int64_t)fmap1->N * fmap1->sN < 0x7fffffff, "rvo_corr_tiles: fmap1 too large for 32-bit offsets");
   TcWs w = tc_layout(ws, R, G.nbins);
   RVO_CHECK_ARG((int64_t)w.total_bytes <= ws_bytes, "rvo_corr_tiles: workspace %lld < %lld bytes",
                 (long long)ws_bytes, (long long)w.total_bytes);
@@ -799,7 +806,8 @@ extern "C" int rvo_corr_tiles(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, co
   RVO_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)((char*)w.total - (char*)w.cnt), st));   // cnt + cursor + tot: one memset
   RVO_CHECK_ARG(G.nbins <= kScanMaxBins, "rvo_corr_tiles: %d tiles exceed the scan capacity", G.nbins);
   const int64_t T = (int64_t)E * nlevels;
-  tc_bin_count_kernel<<<(int)((T + 255) / 256), 256, 0, st>>>(G, coords, kk, jj, pmod, fmod, fmap1->N, E, w.cnt, w.tot);
+  tc_bin_count_kernel<<<(int)((T + 255) / 256), 256, 0, st>>>(G, coords, kk, jj, pmod, fmod, fmap1->N, E, w.cnt, w.tot,
+                                                              w.rowsub, w.edge_pf);
   RVO_LAUNCH_CHECK("tc_bin_count_kernel");
   // scatter pass, every CTA with its own copy of the scanned tile table in shared memory
   const size_t scan_smem = (size_t)(G.nbins + 1) * 6 + (size_t)kScatterThreads * 4 + 64;
@@ -807,9 +815,9 @@ extern "C" int rvo_corr_tiles(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, co
                                 kScanMaxBins * 6 + kScatterThreads * 4 + 64));
   int grid = sm_budget() * (scan_smem <= 100 * 1024 ? 2 : 1);         // two CTAs per SM while the table allows it
   if ((int64_t)grid * kScatterThreads > R) grid = (int)((R + kScatterThreads - 1) / kScatterThreads);
-  tc_bin_scatter_kernel<<<grid, kScatterThreads, scan_smem, st>>>(G, coords, kk, jj, pmod, fmod, fmap1->N, fmap1->sN,
-                                                                fmap1->sH, fmap1->sW, out_ld, R, w.cnt, w.tot, w.cursor,
-                                                                w.rows, w.hdr, w.total, (__half*)out);
+  tc_bin_scatter_kernel<<<grid, kScatterThreads, scan_smem, st>>>(G, coords, w.rowsub, w.edge_pf, (int)fmap1->sN,
+                                                                (int)fmap1->sH, (int)fmap1->sW, out_ld, R, w.cnt, w.cursor,
+                                                                w.tot, w.rows, w.hdr, w.total, (__half*)out);
   RVO_LAUNCH_CHECK("tc_bin_scatter_kernel");
 #ifdef RVO_DEBUG
   const char* dbg_s = getenv("RVO_CORR_DBG");      // debugging aid: see the kernel's dbg bits
@@ -817,7 +825,6 @@ extern "C" int rvo_corr_tiles(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, co
 #else
   const int dbg = 0;                               // the release library never reads the environment
 #endif
-  RVO_CHECK_ARG((int64_t)fmap1->N * fmap1->sN < 0x7fffffff, "rvo_corr_tiles: fmap1 too large for 32-bit offsets");
   TcTmap tm[kTcMaxLevels];
   for (int l = 0; l < kTcMaxLevels; l++) {
     rc = tc_make_tmap(G.lv[l], &tm[l]);
