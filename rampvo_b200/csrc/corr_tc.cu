@@ -311,7 +311,7 @@ __device__ __forceinline__ TcHdr ld_hdr(const TcHdr* __restrict__ hdr, int b) {
 //             (negative coordinates included) are zero-filled by the hardware.  A tile is loaded
 //             ONCE for all consecutive row blocks that share it (level 2 has ~5 blocks per tile);
 //   chunks    a CTA takes chunks of consecutive blocks (so tile sharing survives the persistent
-//             schedule) strided by the grid, 8 or 2 blocks long (tma_block);
+//             schedule) strided by the grid, 8 blocks or 1 block long (tma_block);
 //   A rows    two producer groups (4 warps each, alternate blocks) gather the 128 patch-pixel
 //             vectors with cp.async into a 3-stage ring: the gather of block i starts when the MMAs
 //             of block i - 3 have retired;
@@ -336,7 +336,8 @@ constexpr int kTmaSmemBytes = kTmaOffA + kTmaAStages * kTcSmemA + 1024;
 // Persistent schedule: a CTA takes chunks of 2^CL consecutive blocks, strided by the grid.  A chunk keeps the blocks
 // of one tile together (its features are loaded once per run of blocks), which pays when the tiles hold several
 // blocks each (precise.yaml: chunks of 8, 836 vs 849 us); with about one block per level-1 tile (default.yaml) short
-// chunks mix cheap and expensive blocks evenly over the CTAs instead (chunks of 2: 95 vs 101 us).  The host picks.
+// chunks mix cheap and expensive blocks evenly over the CTAs instead (µs, chunks of 8 / 4 / 2 / 1: 101 / 99 / 95-97 /
+// 96 on a uniform synthetic graph, 105.7 / - / 99-101 / 98.6 on the running VO's graph).  The host picks 8 or 1.
 // block index of the i-th block of this CTA's schedule
 template <int CL>
 __device__ __forceinline__ int tma_block(int i) {
@@ -830,10 +831,10 @@ extern "C" int rvo_corr_tiles(const rvo_fmap_t* fmap1, const rvo_fmap_t* pyr, co
     rc = tc_make_tmap(G.lv[l], &tm[l]);
     if (rc != RVO_OK) return rc;
   }
-  // schedule granularity (tma_block): short chunks while the level-1 tiles hold about one 128-row block each
+  // schedule granularity (tma_block): single blocks while the level-1 tiles hold about one 128-row block each
   const int64_t bins1 = (int64_t)G.lv[0].N * G.lv[0].TX * G.lv[0].TY;
   const bool short_chunks = (int64_t)E * 9 < 96 * bins1;
-  auto kern = short_chunks ? corr_tile_tma_kernel<1> : corr_tile_tma_kernel<3>;
+  auto kern = short_chunks ? corr_tile_tma_kernel<0> : corr_tile_tma_kernel<3>;
   RVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
   kern<<<sm_budget(), kTmaThreads, kTmaSmemBytes, st>>>(tm[0], tm[1], (const __half*)fmap1->data, w.hdr, w.rows, w.total,
                                                        (__half*)out, dbg);
