@@ -6,12 +6,14 @@
 //
 //   bin      every (edge, patch pixel, level) row is assigned to the 16x16-position tile of its target
 //            frame that contains its 8x8 window (tiles step by 9 so every window fits in exactly one
-//            tile) and, inside the tile, ordered by the tile row its window starts in: warp-aggregated
-//            histogram + single-CTA scan + scatter on the device, no host sync;
+//            tile) and, inside the tile, ordered by the tile row its window starts in: a histogram pass
+//            (register-aggregated per edge) and a scatter pass whose CTAs each scan the tile table into
+//            shared memory for themselves (no scan launch), on the device, no host sync;
 //   GEMM     persistent CTAs walk the (tile, <=128 rows) blocks: A = the rows' 128-channel patch vectors
 //            gathered with cp.async, B = the tile's 256 feature vectors brought by TMA (zero-filled
 //            outside the map), both in the canonical K-major SWIZZLE_128B layout; ONE elected thread
-//            issues 8 tcgen05.mma (M=128, N=256, K=16) into a 128x256 fp32 accumulator in TMEM;
+//            issues 8 tcgen05.mma (M=128, N = 16 x covered tile rows <= 256, K=16) into a 128x256 fp32
+//            accumulator in TMEM;
 //   epilogue thread r owns TMEM lane r: tcgen05.ld brings two tile rows at a time, the thread picks its
 //            own 8-wide window in registers, does the separable bilinear blend and writes each of its
 //            7 output rows as one aligned 16-byte store.
